@@ -1,0 +1,670 @@
+// so3d_math.cuh -- per-rotation SO(3) / IGSO(3) arithmetic shared by every kernel.
+//
+// One rotation lives in the registers of one thread (9 floats, row-major).  Everything here is a
+// small inline function so that the kernels in so3d_kernels.cu can fuse axis-angle extraction,
+// series/closed-form evaluation, sampling and composition without going through memory.
+//
+// The functions are __host__ __device__ on purpose: tests/host_math compiles this header with g++
+// (SO3D_HOST_ONLY) so the CPU-only test tier can check the very same arithmetic against the oracle
+// here, where no GPU exists.  That host build is a test harness -- the product never runs it.
+//
+// Reference behaviour is cited as file:line of qazwsxal/diffusion-extensions @ f100885d.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
+#define SO3D_HD __host__ __device__ __forceinline__
+#define SO3D_D __device__ __forceinline__
+#else
+#define SO3D_HD inline
+#define SO3D_D inline
+#endif
+
+namespace so3d {
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr double kPiD = 3.14159265358979323846;
+constexpr int kGrid = 1000;      // distributions.py:15 -- CDF grid points
+constexpr int kCdf = kGrid - 1;  // entries per CDF row (trap / trap_loc)
+constexpr float kNearPiCos = -0.9f;  // (tr R - 1)/2 below this: axis from the symmetric part
+
+struct Vec3 {
+  float x, y, z;
+};
+struct Mat3 {
+  float m[9];  // row-major: m[3*i+j]
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+SO3D_HD float fast_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // MUFU.EX2, 2 ulp
+  return y;
+#else
+  return exp2f(x);
+#endif
+}
+
+SO3D_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+
+SO3D_HD float rsqrt_f(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+SO3D_HD void sincos_f(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x);
+  *c = cosf(x);
+#endif
+}
+
+SO3D_HD Mat3 identity() {
+  Mat3 r;
+  r.m[0] = 1.f; r.m[1] = 0.f; r.m[2] = 0.f;
+  r.m[3] = 0.f; r.m[4] = 1.f; r.m[5] = 0.f;
+  r.m[6] = 0.f; r.m[7] = 0.f; r.m[8] = 1.f;
+  return r;
+}
+
+// C = A B
+SO3D_HD Mat3 mul_nn(const Mat3& a, const Mat3& b) {
+  Mat3 c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c.m[3 * i + j] = fmaf(a.m[3 * i + 2], b.m[6 + j], fmaf(a.m[3 * i + 1], b.m[3 + j], a.m[3 * i] * b.m[j]));
+  return c;
+}
+// C = A^T B
+SO3D_HD Mat3 mul_tn(const Mat3& a, const Mat3& b) {
+  Mat3 c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c.m[3 * i + j] = fmaf(a.m[6 + i], b.m[6 + j], fmaf(a.m[3 + i], b.m[3 + j], a.m[i] * b.m[j]));
+  return c;
+}
+// C = A B^T
+SO3D_HD Mat3 mul_nt(const Mat3& a, const Mat3& b) {
+  Mat3 c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c.m[3 * i + j] = fmaf(a.m[3 * i + 2], b.m[3 * j + 2], fmaf(a.m[3 * i + 1], b.m[3 * j + 1], a.m[3 * i] * b.m[3 * j]));
+  return c;
+}
+
+// hat map, util.py:87-92
+SO3D_HD Mat3 hat(Vec3 v) {
+  Mat3 k;
+  k.m[0] = 0.f;  k.m[1] = -v.z; k.m[2] = v.y;
+  k.m[3] = v.z;  k.m[4] = 0.f;  k.m[5] = -v.x;
+  k.m[6] = -v.y; k.m[7] = v.x;  k.m[8] = 0.f;
+  return k;
+}
+// vee map, util.py:79-84: (m21, -m20, m10)
+SO3D_HD Vec3 vee(const Mat3& a) { return Vec3{a.m[7], -a.m[6], a.m[3]}; }
+
+// ------------------------------------------------------------------------------------------------
+// log map / axis-angle.   util.py:164-192 (log_rmat), :208-219 (rmat_to_aa)
+//   v = vee(R - R^T); s = |v|/2; c = (tr R - 1)/2; theta = atan2(s, c); log = theta/(2 s) * v.
+// Deviation: for c < kNearPiCos the axis is recovered from the symmetric part
+// (R + R^T)/2 = c I + (1 - c) n n^T, which stays accurate up to and at theta = pi where the
+// reference's skew-part formula is 0/0 and its eigh fallback picks a wrong axis; at the identity
+// the axis is the fixed unit vector (0,0,1) instead of NaN.
+// ------------------------------------------------------------------------------------------------
+struct AxisAngle {
+  Vec3 axis;    // unit
+  float theta;  // [0, pi]
+  float s, c;   // |v|/2 and (tr-1)/2 of the input (NOT renormalised): needed by the backward
+};
+
+SO3D_HD AxisAngle axis_angle(const Mat3& r) {
+  AxisAngle o;
+  const float vx = r.m[7] - r.m[5], vy = r.m[2] - r.m[6], vz = r.m[3] - r.m[1];
+  const float n2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+  const float nv = sqrtf(n2);
+  o.s = 0.5f * nv;
+  o.c = 0.5f * (r.m[0] + r.m[4] + r.m[8] - 1.0f);
+  o.theta = atan2f(o.s, o.c);
+  if (o.c >= kNearPiCos) {
+    if (nv > 0.f) {
+      const float inv = 1.0f / nv;
+      o.axis = Vec3{vx * inv, vy * inv, vz * inv};
+    } else {
+      o.axis = Vec3{0.f, 0.f, 1.f};
+    }
+  } else {
+    // symmetric part: d_i = R_ii, off-diagonals (R_ij + R_ji)/2; n_k from the largest diagonal
+    const float omc = 1.0f - o.c;
+    const float d0 = r.m[0], d1 = r.m[4], d2 = r.m[8];
+    float nx, ny, nz;
+    if (d0 >= d1 && d0 >= d2) {
+      nx = sqrtf(fmaxf((d0 - o.c) / omc, 0.f));
+      const float q = 0.5f / (omc * nx);
+      ny = (r.m[1] + r.m[3]) * q;
+      nz = (r.m[2] + r.m[6]) * q;
+    } else if (d1 >= d2) {
+      ny = sqrtf(fmaxf((d1 - o.c) / omc, 0.f));
+      const float q = 0.5f / (omc * ny);
+      nx = (r.m[1] + r.m[3]) * q;
+      nz = (r.m[5] + r.m[7]) * q;
+    } else {
+      nz = sqrtf(fmaxf((d2 - o.c) / omc, 0.f));
+      const float q = 0.5f / (omc * nz);
+      nx = (r.m[2] + r.m[6]) * q;
+      ny = (r.m[5] + r.m[7]) * q;
+    }
+    const float inv = rsqrt_f(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+    const float sgn = (fmaf(nx, vx, fmaf(ny, vy, nz * vz)) < 0.f) ? -inv : inv;
+    o.axis = Vec3{nx * sgn, ny * sgn, nz * sgn};
+  }
+  return o;
+}
+
+// vee(log R) = theta * axis
+SO3D_HD Vec3 log_vec(const Mat3& r) {
+  const AxisAngle a = axis_angle(r);
+  return Vec3{a.theta * a.axis.x, a.theta * a.axis.y, a.theta * a.axis.z};
+}
+
+// ------------------------------------------------------------------------------------------------
+// exp map.  Replaces torch.matrix_exp + SVD re-orthogonalisation (util.py:195-205, :360,
+// diffusion.py:294) by the Rodrigues closed form, always orthonormal to fp32 rounding.
+//   R = I + sin(t) K + (1 - cos(t)) K^2,  K = hat(n), |n| = 1;   1 - cos t = 2 sin^2(t/2).
+// ------------------------------------------------------------------------------------------------
+SO3D_HD Mat3 rodrigues_sc(Vec3 n, float sn, float omc /* 1 - cos */) {
+  Mat3 r;
+  const float xx = n.x * n.x, yy = n.y * n.y, zz = n.z * n.z;
+  const float xy = omc * n.x * n.y, xz = omc * n.x * n.z, yz = omc * n.y * n.z;
+  const float sx = sn * n.x, sy = sn * n.y, sz = sn * n.z;
+  r.m[0] = fmaf(-omc, yy + zz, 1.0f);
+  r.m[1] = xy - sz;
+  r.m[2] = xz + sy;
+  r.m[3] = xy + sz;
+  r.m[4] = fmaf(-omc, xx + zz, 1.0f);
+  r.m[5] = yz - sx;
+  r.m[6] = xz - sy;
+  r.m[7] = yz + sx;
+  r.m[8] = fmaf(-omc, xx + yy, 1.0f);
+  return r;
+}
+
+SO3D_HD Mat3 rodrigues(Vec3 n_unit, float theta) {
+  float sh, ch;
+  sincos_f(0.5f * theta, &sh, &ch);
+  return rodrigues_sc(n_unit, 2.0f * sh * ch, 2.0f * sh * sh);
+}
+
+// exp(hat(v)) for a rotation vector (no normalisation problem at |v| -> 0)
+SO3D_HD Mat3 exp_vec(Vec3 v) {
+  const float t2 = fmaf(v.x, v.x, fmaf(v.y, v.y, v.z * v.z));
+  const float t = sqrtf(t2);
+  float sh, ch;
+  sincos_f(0.5f * t, &sh, &ch);
+  // a = sin(t)/t, b = (1-cos t)/t^2 = (sin(t/2)/(t/2))^2 / 2
+  float a, b;
+  if (t > 1e-4f) {
+    const float sinc_h = sh / (0.5f * t);
+    a = sinc_h * ch;
+    b = 0.5f * sinc_h * sinc_h;
+  } else {
+    a = 1.0f - t2 * (1.0f / 6.0f);
+    b = 0.5f - t2 * (1.0f / 24.0f);
+  }
+  Mat3 r;
+  const float xx = v.x * v.x, yy = v.y * v.y, zz = v.z * v.z;
+  const float xy = b * v.x * v.y, xz = b * v.x * v.z, yz = b * v.y * v.z;
+  r.m[0] = fmaf(-b, yy + zz, 1.0f);
+  r.m[1] = fmaf(-a, v.z, xy);
+  r.m[2] = fmaf(a, v.y, xz);
+  r.m[3] = fmaf(a, v.z, xy);
+  r.m[4] = fmaf(-b, xx + zz, 1.0f);
+  r.m[5] = fmaf(-a, v.x, yz);
+  r.m[6] = fmaf(-a, v.y, xz);
+  r.m[7] = fmaf(a, v.x, yz);
+  r.m[8] = fmaf(-b, xx + yy, 1.0f);
+  return r;
+}
+
+// util.py:195-205: normalise the axis (0-axis -> NaN like the reference), rotate by `ang`.
+SO3D_HD Mat3 aa_to_rmat(Vec3 axis, float ang) {
+  const float inv = 1.0f / sqrtf(fmaf(axis.x, axis.x, fmaf(axis.y, axis.y, axis.z * axis.z)));
+  return rodrigues(Vec3{axis.x * inv, axis.y * inv, axis.z * inv}, ang);
+}
+
+// util.py:349-361: exp(s log R) = rotation by s*theta about the axis of R.
+SO3D_HD Mat3 scale_rot(const Mat3& r, float s) {
+  const AxisAngle a = axis_angle(r);
+  return rodrigues(a.axis, s * a.theta);
+}
+
+// util.py:222-252: real-first quaternion, un-normalised input allowed.
+SO3D_HD Mat3 quat_to_rmat(float qr, float qi, float qj, float qk) {
+  const float two_s = 2.0f / fmaf(qr, qr, fmaf(qi, qi, fmaf(qj, qj, qk * qk)));
+  Mat3 o;
+  o.m[0] = 1.0f - two_s * (qj * qj + qk * qk);
+  o.m[1] = two_s * (qi * qj - qk * qr);
+  o.m[2] = two_s * (qi * qk + qj * qr);
+  o.m[3] = two_s * (qi * qj + qk * qr);
+  o.m[4] = 1.0f - two_s * (qi * qi + qk * qk);
+  o.m[5] = two_s * (qj * qk - qi * qr);
+  o.m[6] = two_s * (qi * qk - qj * qr);
+  o.m[7] = two_s * (qj * qk + qi * qr);
+  o.m[8] = 1.0f - two_s * (qi * qi + qj * qj);
+  return o;
+}
+
+// No reference counterpart.  Unit quaternion, real-first, real part >= 0.
+SO3D_HD void rmat_to_quat(const Mat3& r, float q[4]) {
+  const float tr = r.m[0] + r.m[4] + r.m[8];
+  float w, x, y, z;
+  if (tr > 0.f) {
+    const float s = sqrtf(tr + 1.0f) * 2.0f;
+    w = 0.25f * s; x = (r.m[7] - r.m[5]) / s; y = (r.m[2] - r.m[6]) / s; z = (r.m[3] - r.m[1]) / s;
+  } else if (r.m[0] > r.m[4] && r.m[0] > r.m[8]) {
+    const float s = sqrtf(1.0f + r.m[0] - r.m[4] - r.m[8]) * 2.0f;
+    w = (r.m[7] - r.m[5]) / s; x = 0.25f * s; y = (r.m[1] + r.m[3]) / s; z = (r.m[2] + r.m[6]) / s;
+  } else if (r.m[4] > r.m[8]) {
+    const float s = sqrtf(1.0f + r.m[4] - r.m[0] - r.m[8]) * 2.0f;
+    w = (r.m[2] - r.m[6]) / s; x = (r.m[1] + r.m[3]) / s; y = 0.25f * s; z = (r.m[5] + r.m[7]) / s;
+  } else {
+    const float s = sqrtf(1.0f + r.m[8] - r.m[0] - r.m[4]) * 2.0f;
+    w = (r.m[3] - r.m[1]) / s; x = (r.m[2] + r.m[6]) / s; y = (r.m[5] + r.m[7]) / s; z = 0.25f * s;
+  }
+  const float n = rsqrt_f(fmaf(w, w, fmaf(x, x, fmaf(y, y, z * z)))) * (w < 0.f ? -1.f : 1.f);
+  q[0] = w * n; q[1] = x * n; q[2] = y * n; q[3] = z * n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward pieces (what autograd through the reference's torch ops yields, in closed form).
+// ------------------------------------------------------------------------------------------------
+// <G, hat(u)> = u . vee_adj(G)
+SO3D_HD Vec3 vee_adj(const Mat3& g) { return Vec3{g.m[7] - g.m[5], g.m[2] - g.m[6], g.m[3] - g.m[1]}; }
+
+// Gradient of  L(R) = <GL, log_rmat(R)>  w.r.t. the 9 entries of R, differentiating the reference's
+// formula util.py:165-176 (theta = atan2(s, c), scale = theta/(2 s), log = scale (R - R^T)):
+//   dL = a * dscale + scale <GL - GL^T, dR>,   a = <GL, R - R^T>
+//   dscale = ds [ c/(2 s (s^2+c^2)) - theta/(2 s^2) ] - dc / (2 (s^2+c^2)),
+//   ds = <R - R^T, dR>/(4 s),  dc = tr(dR)/2.
+SO3D_HD Mat3 log_bwd(const Mat3& r, const Mat3& gl) {
+  const float vx = r.m[7] - r.m[5], vy = r.m[2] - r.m[6], vz = r.m[3] - r.m[1];
+  const float s = 0.5f * sqrtf(fmaf(vx, vx, fmaf(vy, vy, vz * vz)));
+  const float c = 0.5f * (r.m[0] + r.m[4] + r.m[8] - 1.0f);
+  const float th = atan2f(s, c);
+  const float den = fmaf(s, s, c * c);
+  Mat3 a;  // R - R^T
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a.m[3 * i + j] = r.m[3 * i + j] - r.m[3 * j + i];
+  float ga = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ga = fmaf(gl.m[k], a.m[k], ga);
+  float scale, ks, kc;
+  if (s > 1e-4f) {
+    scale = th / (2.0f * s);
+    ks = (c / (2.0f * s * den) - th / (2.0f * s * s)) / (4.0f * s);
+    kc = -1.0f / (4.0f * den);
+  } else if (c > 0.f) {
+    // theta -> 0 limits: scale -> 1/2 + s^2/12 (orthonormal input), d scale/ds * 1/(4s) -> 1/24
+    scale = 0.5f + s * s * (1.0f / 12.0f);
+    ks = (1.0f / 24.0f);
+    kc = -1.0f / (4.0f * den);
+  } else {
+    // theta -> pi: the formula is singular (scale ~ pi/(2 s)); keep it finite, gradient is ill-defined
+    const float sc = fmaxf(s, 1e-12f);
+    scale = th / (2.0f * sc);
+    ks = (c / (2.0f * sc * den) - th / (2.0f * sc * sc)) / (4.0f * sc);
+    kc = -1.0f / (4.0f * den);
+  }
+  Mat3 g;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float v = ga * ks * a.m[3 * i + j] + scale * (gl.m[3 * i + j] - gl.m[3 * j + i]);
+      if (i == j) v = fmaf(ga, kc, v);
+      g.m[3 * i + j] = v;
+    }
+  return g;
+}
+
+// Gradient of <G, Rodrigues(n, t)> w.r.t. the (un-normalised) axis and the angle.
+//   R = I + sin t K + (1 - cos t)(n n^T - I):  dR/dt = cos t K + sin t K^2,
+//   dR/dn . dn = sin t hat(dn) + (1 - cos t)(dn n^T + n dn^T), then project through n = axis/|axis|.
+SO3D_HD void aa_to_rmat_bwd(Vec3 axis, float ang, const Mat3& g, Vec3* g_axis, float* g_ang) {
+  const float len = sqrtf(fmaf(axis.x, axis.x, fmaf(axis.y, axis.y, axis.z * axis.z)));
+  const float inv = 1.0f / len;
+  const Vec3 n{axis.x * inv, axis.y * inv, axis.z * inv};
+  float sn, cs;
+  sincos_f(ang, &sn, &cs);
+  const Mat3 k = hat(n);
+  const Mat3 k2 = mul_nn(k, k);
+  float ga = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) ga = fmaf(g.m[i], fmaf(cs, k.m[i], sn * k2.m[i]), ga);
+  *g_ang = ga;
+  const Vec3 va = vee_adj(g);
+  const float omc = 1.0f - cs;
+  // (G + G^T) n
+  const float sx = fmaf(2.f * g.m[0], n.x, fmaf(g.m[1] + g.m[3], n.y, (g.m[2] + g.m[6]) * n.z));
+  const float sy = fmaf(g.m[1] + g.m[3], n.x, fmaf(2.f * g.m[4], n.y, (g.m[5] + g.m[7]) * n.z));
+  const float sz = fmaf(g.m[2] + g.m[6], n.x, fmaf(g.m[5] + g.m[7], n.y, 2.f * g.m[8] * n.z));
+  const float gx = fmaf(sn, va.x, omc * sx), gy = fmaf(sn, va.y, omc * sy), gz = fmaf(sn, va.z, omc * sz);
+  const float dot = fmaf(gx, n.x, fmaf(gy, n.y, gz * n.z));
+  *g_axis = Vec3{(gx - dot * n.x) * inv, (gy - dot * n.y) * inv, (gz - dot * n.z) * inv};
+}
+
+// Gradient of <G, exp(hat(w))> w.r.t. w:  d exp(W)[hat(dw)] = exp(W) hat(Jr(w) dw),
+//   Jr(w) = I - (1-cos p)/p^2 hat(w) + (p - sin p)/p^3 hat(w)^2,  p = |w|;  grad = Jr^T vee_adj(R^T G).
+SO3D_HD Vec3 exp_vec_bwd(Vec3 w, const Mat3& r_out, const Mat3& g) {
+  const Vec3 u = vee_adj(mul_tn(r_out, g));
+  const float p2 = fmaf(w.x, w.x, fmaf(w.y, w.y, w.z * w.z));
+  const float p = sqrtf(p2);
+  float b, cfac;
+  if (p > 1e-2f) {
+    float sh, ch;
+    sincos_f(0.5f * p, &sh, &ch);
+    b = 2.0f * sh * sh / p2;
+    cfac = (p - 2.0f * sh * ch) / (p2 * p);
+  } else {
+    b = 0.5f - p2 * (1.0f / 24.0f);
+    cfac = (1.0f / 6.0f) - p2 * (1.0f / 120.0f);
+  }
+  // Jr^T u = u + b (w x u) ... careful with signs: Jr^T = I + b hat(w) + cfac hat(w)^2
+  const float cx = w.y * u.z - w.z * u.y, cy = w.z * u.x - w.x * u.z, cz = w.x * u.y - w.y * u.x;  // w x u
+  const float dx = w.y * cz - w.z * cy, dy = w.z * cx - w.x * cz, dz = w.x * cy - w.y * cx;        // w x (w x u)
+  return Vec3{fmaf(cfac, dx, fmaf(b, cx, u.x)), fmaf(cfac, dy, fmaf(b, cy, u.y)), fmaf(cfac, dz, fmaf(b, cz, u.z))};
+}
+
+// ------------------------------------------------------------------------------------------------
+// IGSO(3) density: closed (Poisson-dual, 3-image) form.  distributions.py:53-72.
+// ------------------------------------------------------------------------------------------------
+// fp64, used only by the CDF-table builder (the reference evaluates in fp64 and rounds to fp32).
+// quirks != 0 follows distributions.py:56-62 literally (0*inf = NaN -> 0 for w > 709 eps^2/pi, D5);
+// the default uses the algebraically identical exp(-pi(pi -+ w)/v).
+SO3D_HD double igso3_closed_f64(double t, double eps, int quirks) {
+  const double v = eps * eps;
+  const double pref = sqrt(kPiD) * pow(v, -1.5) * exp(v / 4) * exp(-((t / 2) * (t / 2)) / v);
+  double inner;
+  if (quirks) {
+    inner = t - exp(-(kPiD * kPiD) / v) * ((t - 2 * kPiD) * exp(kPiD * t / v) + (t + 2 * kPiD) * exp(-kPiD * t / v));
+  } else {
+    inner = t - (t - 2 * kPiD) * exp(-kPiD * (kPiD - t) / v) - (t + 2 * kPiD) * exp(-kPiD * (kPiD + t) / v);
+  }
+  double val = pref * inner / (2 * sin(t / 2));
+  if (isinf(val) || isnan(val)) val = 0.0;
+  if (t == 0.0) {
+    if (quirks) {
+      val = sqrt(kPiD) * (v * exp(2 * kPiD * kPiD / v) - 2 * v * exp(kPiD * kPiD / v) + 4 * kPiD * kPiD * v * exp(kPiD * kPiD / v)) *
+            exp(v / 4 - (2 * kPiD * kPiD) / v) / pow(v, 2.5);
+    } else {
+      const double e1 = exp(-(kPiD * kPiD) / v);
+      val = sqrt(kPiD) * pow(v, -1.5) * exp(v / 4) * (1 - 2 * e1 + 4 * kPiD * kPiD * e1 / v);
+    }
+  }
+  return val;
+}
+
+// phi(w) = 1/w - cot(w/2)/2  (the part of d log f / dw that cancels against the 1/w of the bracket)
+SO3D_HD float half_cot_gap(float w) {
+  if (w < 0.5f) {
+    const float w2 = w * w;
+    // w/12 + w^3/720 + w^5/30240 + w^7/1209600
+    return w * fmaf(w2, fmaf(w2, fmaf(w2, 8.2671958e-7f, 3.3068783e-5f), 1.3888889e-3f), 8.3333333e-2f);
+  }
+  float sh, ch;
+  sincos_f(0.5f * w, &sh, &ch);
+  return 1.0f / w - 0.5f * ch / sh;
+}
+
+// fp32 closed form: log f and g = d log f / d omega, stable for eps <= ~1 (3 images: 2e-7 rel).
+//   f = sqrt(pi) v^-3/2 e^{v/4} e^{-w^2/4v} B(w) / (2 sin(w/2)),
+//   B = w - (w - 2pi) E1 - (w + 2pi) E2,  E1 = e^{-pi(pi-w)/v}, E2 = e^{-pi(pi+w)/v}
+//   g = -w/(2v) + (B'/B - 1/w) + (1/w - cot(w/2)/2)
+//   w B' - B = E1 [-2pi - (pi w/v)(w - 2pi)] + E2 [2pi + (pi w/v)(w + 2pi)]
+// Written in terms of dm = E1 - E2 = 2E sinh(y), sm = E1 + E2 = 2E cosh(y), E = e^{-pi^2/v}, y = pi w/v:
+//   B/w        = (1 - sm) + 2 pi dm / w
+//   (wB'-B)/w^2 = [ -(2pi + y w) dm + 2 pi y sm ] / w^2
+// For y < 1/2 the sinh/cosh Taylor series remove the E1 - E2 and y cosh y - sinh y cancellations and
+// every division by w, so w = 0 needs no special case (limit: B/w = 1 - 2E + 4 pi^2 E / v, g = 0).
+SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out) {
+  const float v = eps * eps;
+  const float iv = 1.0f / v;
+  const float piv = kPi * iv;
+  const float y = piv * w;
+  float bw, ratio;  // B/w and (wB' - B)/(w B)
+  if (y < 0.5f) {
+    const float E = expf(-kPi * piv);
+    const float y2 = y * y;
+    const float sinhc = fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.7557319e-6f, 1.9841270e-4f), 8.3333333e-3f), 1.6666667e-1f), 1.0f);
+    const float coshy = fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.4801587e-5f, 1.3888889e-3f), 4.1666667e-2f), 0.5f), 1.0f);
+    const float p3 = y * fmaf(y2, fmaf(y2, fmaf(y2, 2.2045855e-5f, 1.1904762e-3f), 3.3333333e-2f), 3.3333333e-1f);  // (y cosh y - sinh y)/y^2
+    const float dm_w = 2.0f * E * piv * sinhc;  // (E1 - E2)/w
+    bw = (1.0f - 2.0f * E * coshy) + kTwoPi * dm_w;
+    const float n2 = fmaf(-piv * w, dm_w, 2.0f * kTwoPi * E * piv * piv * p3);  // (wB' - B)/w^2
+    ratio = n2 / bw;
+  } else {
+    // pi - w with pi carried as hi + lo: near w = pi the image weight is e^{-(pi/v)(pi - w)} and an 8.7e-8
+    // error in fp32 pi would be amplified by pi/v
+    const float e1 = expf(-piv * ((kPi - w) + (-8.742278e-8f)));
+    const float e2 = expf(-piv * (kPi + w));
+    const float dm = e1 - e2, sm = e1 + e2;
+    bw = (1.0f - sm) + kTwoPi * dm / w;
+    ratio = (fmaf(-(kTwoPi + y * w), dm, kTwoPi * y * sm)) / (w * w * bw);
+  }
+  // w / (2 sin(w/2))
+  float wr;
+  if (w < 0.1f) {
+    const float w2 = w * w;
+    wr = fmaf(w2, fmaf(w2, 1.2152778e-3f, 4.1666667e-2f), 1.0f);
+  } else {
+    wr = w / (2.0f * sinf(0.5f * w));
+  }
+  const float lead = 0.5723649429247001f /* log sqrt(pi) */ - 1.5f * logf(v) + 0.25f * v - 0.25f * w * w * iv;
+  *logf_out = lead + logf(bw * wr);
+  *g_out = fmaf(-0.5f * w, iv, ratio + half_cot_gap(w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// IGSO(3) truncated series, character form (SURVEY A.1 rewritten with chi_l = sin((l+1/2)w)/sin(w/2)
+//   = 1 + 2 sum_{m<=l} cos(m w), which has no 0/0 at w = 0 and no cancellation against cot(w/2)):
+//     f  = 2 sum_l (l+1/2) e_l chi_l,      e_l = exp(-l(l+1) eps^2)
+//     f' = -4 sum_l (l+1/2) e_l D_l,       D_l = sum_{m<=l} m sin(m w)
+// Per term (m -> m+1), all fp32:  4 ops rotate (sin, cos)(m w) by w, 1 m += 1, 1 chi += 2c,
+// 1 D += m s, 2 ops + 1 MUFU.EX2 for e_m = 2^(m(m+1) * (-eps^2 log2 e)), 2 ops p = (m+1/2) e,
+// 2 FMAs into the two accumulators: 13 FP32 + 1 MUFU.  m(m+1) is exact in fp32 for m < 2896.
+// Every kAnchor terms (sin, cos) is re-seeded from an exact-product sincos so the rotation
+// recurrence never drifts more than ~kAnchor ulps (measured: oracle/proto_series_fp32.py).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAnchor = 32;
+
+// sin/cos of (m * w) with the product carried exactly (hi + lo), first-order correction for lo.
+SO3D_HD void sincos_mw(float m, float w, float* s, float* c) {
+  const float hi = m * w;
+  const float lo = fmaf(m, w, -hi);
+  float sh, ch;
+  sincos_f(hi, &sh, &ch);
+  *s = fmaf(lo, ch, sh);
+  *c = fmaf(-lo, sh, ch);
+}
+
+struct SeriesAcc {
+  float F, Fp;  // sum (l+1/2) e_l chi_l ,  sum (l+1/2) e_l D_l
+};
+
+struct SeriesState {
+  float s, c, m;      // sin(m w), cos(m w), m as float
+  float chi, D;       // running chi_m, D_m
+  float F, Fp;        // accumulators
+};
+
+// `count` consecutive terms starting at the state's m: accumulate term m, then rotate to m + 1.
+template <int kUnroll>
+SO3D_HD void igso3_series_run(SeriesState& st, float sw, float cw, float cexp, int count) {
+#pragma unroll kUnroll
+  for (int i = 0; i < count; ++i) {
+    st.chi = fmaf(2.0f, st.c, st.chi);
+    st.D = fmaf(st.m, st.s, st.D);
+    const float e = fast_ex2(fmaf(st.m, st.m, st.m) * cexp);
+    const float p = e * (st.m + 0.5f);
+    st.F = fmaf(p, st.chi, st.F);
+    st.Fp = fmaf(p, st.D, st.Fp);
+    const float t1 = st.c * sw, t2 = st.s * sw;
+    const float sn = fmaf(st.s, cw, t1);
+    st.c = fmaf(st.c, cw, -t2);
+    st.s = sn;
+    st.m += 1.0f;
+  }
+}
+
+// Evaluate terms l = 0 .. L-1.  Returns F, Fp;  f = 2F, dlogf/dw = -2 Fp / F.
+SO3D_HD SeriesAcc igso3_series_terms(float w, float eps, int L) {
+  const float cexp = -(eps * eps) * 1.4426950408889634f;
+  float sw, cw;
+  sincos_f(w, &sw, &cw);
+  SeriesState st;
+  st.s = sw; st.c = cw; st.m = 1.0f;
+  st.chi = 1.0f; st.D = 0.0f;
+  st.F = 0.5f; st.Fp = 0.0f;  // l = 0 term: (1/2) * e_0 * chi_0, D_0 = 0
+  if (L > 1) igso3_series_run<kAnchor>(st, sw, cw, cexp, (L < kAnchor ? L : kAnchor) - 1);
+  for (int base = kAnchor; base < L; base += kAnchor) {
+    sincos_mw((float)base, w, &st.s, &st.c);
+    st.m = (float)base;
+    const int cnt = (L - base < kAnchor) ? (L - base) : kAnchor;
+    if (cnt == kAnchor) igso3_series_run<kAnchor>(st, sw, cw, cexp, kAnchor);
+    else igso3_series_run<1>(st, sw, cw, cexp, cnt);
+  }
+  return SeriesAcc{st.F, st.Fp};
+}
+
+// Number of leading terms whose weight 2^(l(l+1) cexp) is not flushed to zero (ex2.approx.ftz
+// returns 0 below 2^-126): skipping the rest is bit-identical to summing them.
+SO3D_HD int igso3_series_live_terms(float eps, int L) {
+  const float lim = 9.36f / eps + 2.0f;  // l(l+1) eps^2 log2(e) > 126  <=>  l > ~9.35/eps
+  return lim < (float)L ? (int)lim : L;
+}
+
+enum IgsoMode { kSeries = 0, kClosed = 1, kAuto = 2, kSeriesAdaptive = 3 };
+constexpr float kAutoSeriesEps = 0.6f;  // auto: series (<= ~18 live terms) at or above, closed form below
+
+// log f_eps(w) and g = d log f / dw by the requested evaluator.
+SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, float* g_out) {
+  if (mode == kClosed || (mode == kAuto && eps < kAutoSeriesEps)) {
+    igso3_closed_f32(w, eps, logf_out, g_out);
+  } else {
+    const int terms = (mode == kSeries) ? L : igso3_series_live_terms(eps, L);
+    const SeriesAcc a = igso3_series_terms(w, eps, terms);
+    *logf_out = logf(2.0f * a.F);
+    *g_out = -2.0f * a.Fp / a.F;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverse-CDF angle lookup.  distributions.py:38-49, float32 like the reference.
+//   i1 = #{j : trap[j] <= u}  (binary search; trap is non-decreasing), i0 = max(i1 - 1, 0),
+//   w = clamp((u - trap[i0]) / max(trap[i1] - trap[i0], 1e-6), 0, 1),  angle = lerp(loc[i0], loc[i1], w)
+// `trap` may point to shared or global memory.  loc[j] = pi ((j+1)/999)^3 is passed as a table so
+// the values are bit-identical to the reference's float32 grid.
+// ------------------------------------------------------------------------------------------------
+SO3D_HD float igso3_angle_from_uniform(const float* trap, const float* loc, float u) {
+  int lo = 0, hi = kCdf;  // answer in [lo, hi]
+#pragma unroll 1
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (trap[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  const int i1 = lo < kCdf - 1 ? lo : kCdf - 1;  // u < 1 == trap[998] so lo <= 998; clamp guards u >= 1 inputs
+  const int i0 = i1 > 0 ? i1 - 1 : 0;
+  const float t0 = trap[i0], t1 = trap[i1];
+  const float diff = fmaxf(t1 - t0, 1e-6f);
+  const float wgt = fminf(fmaxf((u - t0) / diff, 0.f), 1.f);
+  const float a0 = loc[i0], a1 = loc[i1];
+  const float d = a1 - a0;
+  // torch.lerp: w < 0.5 ? a0 + w d : a1 - d (1 - w)
+  return (wgt < 0.5f) ? fmaf(wgt, d, a0) : fmaf(-d, 1.0f - wgt, a1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG: key = seed (64 bit), counter = (row index 64 bit, stream offset
+// 64 bit).  The draws of a row do not depend on how the batch is split over GPUs.
+// ------------------------------------------------------------------------------------------------
+struct U4 {
+  uint32_t x, y, z, w;
+};
+
+SO3D_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+SO3D_HD U4 philox4x32_10(uint64_t seed, uint64_t row, uint64_t offset) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  U4 c{(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// 24-bit uniform in [0, 1), the same lattice torch.rand(float32) uses.
+SO3D_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// Uniform point on S^2 from two uniforms (same law as the reference's normalised N(0, I3) draw,
+// distributions.py:35-36).
+SO3D_HD Vec3 sphere_from_uniforms(float ua, float ub) {
+  const float z = fmaf(-2.0f, ua, 1.0f);
+  const float r = sqrtf(fmaxf(fmaf(-z, z, 1.0f), 0.f));
+  float sp, cp;
+#if defined(__CUDA_ARCH__)
+  sincospif(2.0f * ub, &sp, &cp);
+#else
+  sp = sinf(kTwoPi * ub);
+  cp = cosf(kTwoPi * ub);
+#endif
+  return Vec3{r * cp, r * sp, z};
+}
+
+struct NoiseDraw {
+  Vec3 axis;
+  float u;
+};
+SO3D_HD NoiseDraw draw_axis_u(uint64_t seed, uint64_t row, uint64_t offset) {
+  const U4 r = philox4x32_10(seed, row, offset);
+  NoiseDraw d;
+  d.axis = sphere_from_uniforms(u01(r.x), u01(r.y));
+  d.u = u01(r.z);
+  return d;
+}
+
+}  // namespace so3d

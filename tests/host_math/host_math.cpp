@@ -1,0 +1,64 @@
+// Host build of diffusion_extensions_b200/csrc/so3d_math.cuh -- TEST HARNESS ONLY.
+// Lets the CPU-only test tier (no GPU in the build container) exercise the exact per-rotation
+// arithmetic the sm_100a kernels inline, against the oracle.  Never loaded by the product.
+#define SO3D_HOST_ONLY 1
+#include "../../diffusion_extensions_b200/csrc/so3d_math.cuh"
+
+using namespace so3d;
+
+static inline Mat3 ld(const float* p) { Mat3 m; for (int i = 0; i < 9; ++i) m.m[i] = p[i]; return m; }
+static inline void st(float* p, const Mat3& m) { for (int i = 0; i < 9; ++i) p[i] = m.m[i]; }
+
+extern "C" {
+void hm_axis_angle(const float* R, float* axis, float* ang, long n) {
+  for (long i = 0; i < n; ++i) { AxisAngle a = axis_angle(ld(R + 9 * i)); axis[3*i]=a.axis.x; axis[3*i+1]=a.axis.y; axis[3*i+2]=a.axis.z; ang[i]=a.theta; }
+}
+void hm_log_vec(const float* R, float* v, long n) {
+  for (long i = 0; i < n; ++i) { Vec3 a = log_vec(ld(R + 9 * i)); v[3*i]=a.x; v[3*i+1]=a.y; v[3*i+2]=a.z; }
+}
+void hm_aa_to_rmat(const float* axis, const float* ang, float* R, long n) {
+  for (long i = 0; i < n; ++i) st(R + 9 * i, aa_to_rmat(Vec3{axis[3*i], axis[3*i+1], axis[3*i+2]}, ang[i]));
+}
+void hm_exp_vec(const float* v, float* R, long n) {
+  for (long i = 0; i < n; ++i) st(R + 9 * i, exp_vec(Vec3{v[3*i], v[3*i+1], v[3*i+2]}));
+}
+void hm_scale(const float* R, const float* s, float* out, long n) {
+  for (long i = 0; i < n; ++i) st(out + 9 * i, scale_rot(ld(R + 9 * i), s[i]));
+}
+void hm_quat_to_rmat(const float* q, float* R, long n) {
+  for (long i = 0; i < n; ++i) st(R + 9 * i, quat_to_rmat(q[4*i], q[4*i+1], q[4*i+2], q[4*i+3]));
+}
+void hm_rmat_to_quat(const float* R, float* q, long n) {
+  for (long i = 0; i < n; ++i) rmat_to_quat(ld(R + 9 * i), q + 4 * i);
+}
+void hm_closed_f32(const float* w, const float* eps, float* logf, float* g, long n) {
+  for (long i = 0; i < n; ++i) igso3_closed_f32(w[i], eps[i], logf + i, g + i);
+}
+void hm_closed_f64(const double* w, const double* eps, double* f, long n, int quirks) {
+  for (long i = 0; i < n; ++i) f[i] = igso3_closed_f64(w[i], eps[i], quirks);
+}
+void hm_series(const float* w, const float* eps, float* F, float* Fp, long n, int L) {
+  for (long i = 0; i < n; ++i) { SeriesAcc a = igso3_series_terms(w[i], eps[i], L); F[i] = a.F; Fp[i] = a.Fp; }
+}
+void hm_angle_from_uniform(const float* trap, const float* loc, const float* u, float* ang, long n) {
+  for (long i = 0; i < n; ++i) ang[i] = igso3_angle_from_uniform(trap, loc, u[i]);
+}
+void hm_philox(unsigned long long seed, unsigned long long row0, unsigned long long offset, unsigned* out, long n) {
+  for (long i = 0; i < n; ++i) { U4 r = philox4x32_10(seed, row0 + i, offset); out[4*i]=r.x; out[4*i+1]=r.y; out[4*i+2]=r.z; out[4*i+3]=r.w; }
+}
+void hm_draw(unsigned long long seed, unsigned long long row0, unsigned long long offset, float* axis, float* u, long n) {
+  for (long i = 0; i < n; ++i) { NoiseDraw d = draw_axis_u(seed, row0 + i, offset); axis[3*i]=d.axis.x; axis[3*i+1]=d.axis.y; axis[3*i+2]=d.axis.z; u[i]=d.u; }
+}
+void hm_log_bwd(const float* R, const float* G, float* out, long n) {
+  for (long i = 0; i < n; ++i) st(out + 9 * i, log_bwd(ld(R + 9 * i), ld(G + 9 * i)));
+}
+void hm_aa_bwd(const float* axis, const float* ang, const float* G, float* gaxis, float* gang, long n) {
+  for (long i = 0; i < n; ++i) { Vec3 ga; aa_to_rmat_bwd(Vec3{axis[3*i], axis[3*i+1], axis[3*i+2]}, ang[i], ld(G + 9 * i), &ga, gang + i); gaxis[3*i]=ga.x; gaxis[3*i+1]=ga.y; gaxis[3*i+2]=ga.z; }
+}
+void hm_expvec_bwd(const float* w, const float* G, float* gw, long n) {
+  for (long i = 0; i < n; ++i) { Vec3 v{w[3*i], w[3*i+1], w[3*i+2]}; Vec3 g = exp_vec_bwd(v, exp_vec(v), ld(G + 9 * i)); gw[3*i]=g.x; gw[3*i+1]=g.y; gw[3*i+2]=g.z; }
+}
+}
+extern "C" void hm_logf_g(const float* w, const float* eps, float* logf, float* g, long n, int mode, int L) {
+  for (long i = 0; i < n; ++i) igso3_logf_g(w[i], eps[i], mode, L, logf + i, g + i);
+}

@@ -1,0 +1,281 @@
+"""CPU-tier check of the per-rotation arithmetic the sm_100a kernels inline.
+
+diffusion_extensions_b200/csrc/so3d_math.cuh is host+device; tests/host_math/host_math.cpp compiles
+it with g++ so that, in the GPU-less build container, the same code is compared with the oracle.
+(The GPU tier repeats these comparisons through the real kernels and the C-ABI.)
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import so3_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_math", "host_math.cpp")
+LIB = os.path.join(HERE, "host_math", "_host_math.so")
+HDR = os.path.join(HERE, "..", "diffusion_extensions_b200", "csrc", "so3d_math.cuh")
+
+F = ctypes.POINTER(ctypes.c_float)
+D = ctypes.POINTER(ctypes.c_double)
+
+
+def fp(a):
+    return a.ctypes.data_as(F)
+
+
+@pytest.fixture(scope="module")
+def hm():
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        subprocess.check_call(["g++", "-O2", "-march=native", "-shared", "-fPIC", "-o", LIB, SRC])
+    return ctypes.CDLL(LIB)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def rand_rots(n, seed, max_angle=math.pi):
+    rng = np.random.default_rng(seed)
+    R, axis, ang = O.random_rotations(n, rng, max_angle)
+    return f32(R), axis, ang
+
+
+def test_axis_angle_and_log(hm):
+    n = 4096
+    R, _, _ = rand_rots(n, 0)
+    axis = np.empty((n, 3), np.float32); ang = np.empty(n, np.float32); v = np.empty((n, 3), np.float32)
+    hm.hm_axis_angle(fp(R), fp(axis), fp(ang), ctypes.c_long(n))
+    hm.hm_log_vec(fp(R), fp(v), ctypes.c_long(n))
+    ax_t, ang_t = O.rmat_to_aa(R)
+    assert np.max(np.abs(ang - ang_t[:, 0])) < 1e-6
+    # axis error allowed to grow only near pi (sign flips at pi are legitimate) -> compare rotations
+    back = O.rodrigues(axis.astype(np.float64), ang.astype(np.float64))
+    assert np.max(np.abs(back - R)) < 2e-6
+    assert np.max(np.abs(v - O.log_vec(R))[ang_t[:, 0] < 3.1]) < 3e-6
+
+
+def test_log_edge_cases(hm):
+    # identity, exact pi about generic axes, tiny angles
+    rng = np.random.default_rng(3)
+    ax = rng.standard_normal((64, 3)); ax /= np.linalg.norm(ax, axis=-1, keepdims=True)
+    Rpi = f32(O.rodrigues(ax, np.full(64, math.pi)))
+    Rtiny = f32(O.rodrigues(ax, np.full(64, 1e-5)))
+    R = np.concatenate([f32(np.eye(3))[None], Rpi, Rtiny])
+    n = R.shape[0]
+    axis = np.empty((n, 3), np.float32); ang = np.empty(n, np.float32)
+    hm.hm_axis_angle(fp(R), fp(axis), fp(ang), ctypes.c_long(n))
+    assert ang[0] == 0 and np.array_equal(axis[0], [0, 0, 1])
+    assert np.max(np.abs(ang[1:65] - math.pi)) < 1e-6
+    # axis at pi is defined up to sign (Q4: the reference gets it wrong; fp64 truth is +-ax)
+    dots = np.abs((axis[1:65] * ax).sum(-1))
+    assert np.min(dots) > 1 - 1e-6
+    assert np.max(np.abs(ang[65:] - 1e-5)) < 1e-9
+    assert np.min((axis[65:] * ax).sum(-1)) > 1 - 1e-5
+
+
+def test_exp_scale_quat(hm):
+    n = 2048
+    rng = np.random.default_rng(1)
+    R, _, _ = rand_rots(n, 1, 3.0)
+    axes = f32(rng.standard_normal((n, 3)) * 2); ang = f32(rng.uniform(0, math.pi, n))
+    out = np.empty((n, 3, 3), np.float32)
+    hm.hm_aa_to_rmat(fp(axes), fp(ang), fp(out), ctypes.c_long(n))
+    assert np.max(np.abs(out - O.aa_to_rmat(axes, ang[:, None]))) < 1e-6
+    v = f32(rng.standard_normal((n, 3)) * np.exp(rng.uniform(-12, 1, (n, 1))))
+    hm.hm_exp_vec(fp(v), fp(out), ctypes.c_long(n))
+    assert np.max(np.abs(out - O.exp_vec(v))) < 1e-6
+    s = f32(np.exp(rng.uniform(math.log(1e-4), math.log(3.0), n)))
+    hm.hm_scale(fp(R), fp(s), fp(out), ctypes.c_long(n))
+    assert np.max(np.abs(out - O.so3_scale(R, s))) < 3e-6
+    q = f32(rng.standard_normal((n, 4)))
+    hm.hm_quat_to_rmat(fp(q), fp(out), ctypes.c_long(n))
+    assert np.max(np.abs(out - O.quat_to_rmat(q))) < 1e-6
+    q2 = np.empty((n, 4), np.float32)
+    hm.hm_rmat_to_quat(fp(R), fp(q2), ctypes.c_long(n))
+    assert np.max(np.abs(np.linalg.norm(q2, axis=-1) - 1)) < 1e-6 and np.all(q2[:, 0] >= 0)
+    assert np.max(np.abs(O.quat_to_rmat(q2) - R)) < 2e-6
+
+
+def eset(n, seed, kmax=4.0):
+    rng = np.random.default_rng(seed)
+    eps = np.exp(rng.uniform(math.log(6.4e-3), 0.0, n)).astype(np.float32)
+    k = rng.uniform(0, kmax, n)
+    om = np.minimum(eps * math.sqrt(2.0) * k, 3.0).astype(np.float32)
+    return om, eps, om / (math.sqrt(2.0) * eps)
+
+
+def _truth(om, eps):
+    """fp64 truth: the series where it is well conditioned in fp64, the stable closed form (3 images,
+    <= 4e-9 of the series for eps < 1, tests/test_oracle_golden.py) for small eps far in the tail."""
+    om64, e64 = om.astype(np.float64), eps.astype(np.float64)
+    ft, gt = O.igso3_series(om64, e64)
+    # (the fp64 closed-form derivative itself cancels like 1/w - cot(w/2)/2 at small w: series there)
+    small = (e64 < 0.4) & (om64 > 3.0 * e64)
+    ft = np.where(small, O.igso3_closed(om64, e64), ft)
+    gt = np.where(small, O.igso3_closed_dlog(om64, e64), gt)
+    return ft, gt
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_closed_and_auto_fp32(hm, mode):
+    """fp32 closed form (eps <= 1) and the auto evaluator (any eps) vs fp64 truth on the E-set
+    (omega = eps sqrt2 k, k in [0,4], clipped to 3.0): <= 1e-5 relative on density and score."""
+    n = 40000
+    om, eps, k = eset(n, 5)
+    if mode == 2:  # auto also covers eps > 1 where the 3-image closed form breaks down
+        eps[: n // 4] = np.random.default_rng(6).uniform(1.0, 2.0, n // 4).astype(np.float32)
+        om[: n // 4] = np.minimum(om[: n // 4], 3.0)
+    om[:50] = 0.0
+    om[50:100] = np.float32(1e-7)
+    logf = np.empty(n, np.float32); g = np.empty(n, np.float32)
+    hm.hm_logf_g(fp(om), fp(eps), fp(logf), fp(g), ctypes.c_long(n), mode, 2000)
+    ft, gt = _truth(om, eps)
+    assert np.max(np.abs(np.exp(logf.astype(np.float64) - np.log(ft)) - 1)) < 1e-5
+    ok = om > 0
+    assert np.max((np.abs(g - gt) / np.maximum(np.abs(gt), 1e-30))[ok]) < 1e-5
+    assert np.all(g[~ok] == 0)
+
+
+def test_auto_full_angle_range(hm):
+    """omega over all of [0, pi]: density <= 1e-5 relative; the score goes through zero at pi
+    (f is symmetric about pi), so there its error is measured against the score scale 1/eps."""
+    n = 40000
+    rng = np.random.default_rng(8)
+    eps = np.exp(rng.uniform(math.log(0.15), math.log(2.0), n)).astype(np.float32)  # f(pi) > 1e-48: fp64 truth exists
+    om = rng.uniform(0, math.pi, n).astype(np.float32)
+    om[:64] = np.float32(math.pi)
+    logf = np.empty(n, np.float32); g = np.empty(n, np.float32)
+    hm.hm_logf_g(fp(om), fp(eps), fp(logf), fp(g), ctypes.c_long(n), 2, 2000)
+    ft, gt = _truth(om, eps)
+    assert np.max(np.abs(np.exp(logf.astype(np.float64) - np.log(ft)) - 1)) < 2e-5
+    assert np.max(np.abs(g - gt) / np.maximum(np.abs(gt), 1.0 / eps)) < 1e-5
+
+
+def test_series_fp32(hm):
+    """fp32 L=2000 series (character form, 32-term anchors) vs the fp64 series.
+    1e-5 where the alternating sum is well conditioned (omega <= 3.5 eps); beyond that the error
+    of ANY fp32 summation grows with the cancellation (oracle/proto_series_fp32.py), bounded here."""
+    n = 6000
+    om, eps, k = eset(n, 7)
+    om[:20] = 0.0
+    k[:20] = 0.0
+    F = np.empty(n, np.float32); Fp = np.empty(n, np.float32)
+    hm.hm_series(fp(om), fp(eps), fp(F), fp(Fp), ctypes.c_long(n), 2000)
+    ft, gt = O.igso3_series(om.astype(np.float64), eps.astype(np.float64))
+    f = 2.0 * F.astype(np.float64)
+    g = -2.0 * Fp.astype(np.float64) / F.astype(np.float64)
+    ef = np.abs(f - ft) / ft
+    eg = np.abs(g - gt) / np.maximum(np.abs(gt), 1e-30)
+    well = k <= 2.5
+    assert ef[well].max() < 1e-5 and eg[well & (om > 0)].max() < 1e-5
+    assert np.all(g[om == 0] == 0)
+    assert ef[k <= 3.2].max() < 1e-4 and ef.max() < 2e-3
+
+
+def test_series_short_L(hm):
+    om, eps, _ = eset(512, 9)
+    eps = np.maximum(eps, 0.5).astype(np.float32)
+    for L in (1, 2, 31, 32, 33, 64, 100):
+        F = np.empty(512, np.float32); Fp = np.empty(512, np.float32)
+        hm.hm_series(fp(om), fp(eps), fp(F), fp(Fp), ctypes.c_long(512), L)
+        ft, gt = O.igso3_series(om.astype(np.float64), eps.astype(np.float64), L)
+        f0, _ = O.igso3_series(np.zeros_like(om, np.float64), eps.astype(np.float64), L)  # sum of |terms| bound
+        assert np.max(np.abs(2.0 * F - ft) / f0) < 2e-6, L
+
+
+def test_table_density_f64(hm, golden):
+    g = golden("igso3")
+    loc = g["grid_loc"].astype(np.float64)
+    for e, ref in zip(g["eps_list"], g["trap"]):
+        f = np.empty(1000, np.float64)
+        ee = np.full(1000, float(e))
+        hm.hm_closed_f64(loc.ctypes.data_as(D), ee.ctypes.data_as(D), f.ctypes.data_as(D), ctypes.c_long(1000), 0)
+        assert np.max(np.abs(f - O.igso3_closed(loc, float(e))) / np.maximum(O.igso3_closed(loc, float(e)), 1e-300)) < 1e-10
+    # quirk mode reproduces the reference's zeroed tail at the schedule's smallest eps
+    om = g["q_omega"].astype(np.float64)
+    f = np.empty(om.shape[0], np.float64)
+    ee = np.full(om.shape[0], float(g["q_eps"]))
+    hm.hm_closed_f64(om.ctypes.data_as(D), ee.ctypes.data_as(D), f.ctypes.data_as(D), ctypes.c_long(om.shape[0]), 1)
+    assert np.array_equal(f[1:] == 0, g["q_density"][1:] == 0)
+
+
+def test_inverse_cdf_lookup(hm, golden):
+    g = golden("igso3")
+    loc = f32(g["trap_loc"])
+    for k in range(len(g["eps_list"])):
+        trap = f32(g["trap"][k]); u = f32(g["u_draw"][k])
+        ang = np.empty(u.shape[0], np.float32)
+        hm.hm_angle_from_uniform(fp(trap), fp(loc), fp(u), fp(ang), ctypes.c_long(u.shape[0]))
+        want = O.igso3_angle_from_uniform(u, trap, loc)
+        assert np.max(np.abs(ang - want)) <= 1e-7   # same fp32 arithmetic; FMA contraction only
+        ref_ang = O.rmat_to_aa(g["samples"][k])[1][:, 0]
+        assert np.max(np.abs(ang - ref_ang)) < 1e-5  # vs the reference's own samples (north star)
+    # edge uniforms
+    trap = f32(g["trap"][2])
+    u = f32([0.0, 1e-12, trap[0], trap[10], np.nextafter(np.float32(1), np.float32(0)), 1.0])
+    ang = np.empty(u.shape[0], np.float32)
+    hm.hm_angle_from_uniform(fp(trap), fp(loc), fp(u), fp(ang), ctypes.c_long(u.shape[0]))
+    want = O.igso3_angle_from_uniform(u[:-1], trap, loc)
+    assert np.max(np.abs(ang[:-1] - want)) <= 1e-7 and np.isfinite(ang[-1])
+
+
+def test_philox_known_answer_and_draws(hm):
+    # Random123 known-answer test for philox4x32-10: counter = key = 0 and the "pi" vector
+    out = np.empty(4, np.uint32)
+    hm.hm_philox(ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.c_long(1))
+    assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    seed = (0xa4093822 | (0x299f31d0 << 32))
+    row = (0x243f6a88 | (0x85a308d3 << 32))
+    off = (0x13198a2e | (0x03707344 << 32))
+    hm.hm_philox(ctypes.c_ulonglong(seed), ctypes.c_ulonglong(row), ctypes.c_ulonglong(off), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.c_long(1))
+    assert [hex(x) for x in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    n = 200000
+    axis = np.empty((n, 3), np.float32); u = np.empty(n, np.float32)
+    hm.hm_draw(ctypes.c_ulonglong(1234), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), fp(axis), fp(u), ctypes.c_long(n))
+    assert np.max(np.abs(np.linalg.norm(axis, axis=-1) - 1)) < 1e-6
+    assert np.all((u >= 0) & (u < 1))
+    assert np.max(np.abs(axis.mean(0))) < 0.01 and abs(u.mean() - 0.5) < 0.01
+    assert np.max(np.abs((axis ** 2).mean(0) - 1 / 3)) < 0.01
+
+
+def test_backward_pieces(hm):
+    """Closed-form backward of log / aa_to_rmat / exp against central differences of the oracle."""
+    n = 256
+    rng = np.random.default_rng(11)
+    R, _, _ = rand_rots(n, 11, 2.8)
+    G = f32(rng.standard_normal((n, 3, 3)))
+    out = np.empty((n, 3, 3), np.float32)
+    hm.hm_log_bwd(fp(R), fp(G), fp(out), ctypes.c_long(n))
+    h = 1e-6
+    num = np.zeros((n, 3, 3))
+    R64 = R.astype(np.float64)
+    for i in range(3):
+        for j in range(3):
+            d = np.zeros((3, 3)); d[i, j] = h
+            lp = O.log_rmat(R64 + d, reference_quirks=True); lm = O.log_rmat(R64 - d, reference_quirks=True)
+            num[:, i, j] = ((lp - lm) * G).sum((-1, -2)) / (2 * h)
+    assert np.max(np.abs(out - num) / np.maximum(np.abs(num).max((-1, -2), keepdims=True), 1.0)) < 2e-4
+    # aa_to_rmat
+    axes = f32(rng.standard_normal((n, 3)) * 2); ang = f32(rng.uniform(0.01, 3.0, n))
+    ga = np.empty((n, 3), np.float32); gang = np.empty(n, np.float32)
+    hm.hm_aa_bwd(fp(axes), fp(ang), fp(G), fp(ga), fp(gang), ctypes.c_long(n))
+    a64, an64 = axes.astype(np.float64), ang.astype(np.float64)
+    num_ang = ((O.aa_to_rmat(a64, (an64 + h)[:, None]) - O.aa_to_rmat(a64, (an64 - h)[:, None])) * G).sum((-1, -2)) / (2 * h)
+    assert np.max(np.abs(gang - num_ang)) < 2e-4 * max(1.0, np.abs(num_ang).max())
+    for k in range(3):
+        d = np.zeros(3); d[k] = h
+        nk = ((O.aa_to_rmat(a64 + d, an64[:, None]) - O.aa_to_rmat(a64 - d, an64[:, None])) * G).sum((-1, -2)) / (2 * h)
+        assert np.max(np.abs(ga[:, k] - nk)) < 2e-4 * max(1.0, np.abs(nk).max())
+    # exp
+    w = f32(rng.standard_normal((n, 3)) * np.exp(rng.uniform(-6, 0.5, (n, 1))))
+    gw = np.empty((n, 3), np.float32)
+    hm.hm_expvec_bwd(fp(w), fp(G), fp(gw), ctypes.c_long(n))
+    w64 = w.astype(np.float64)
+    for k in range(3):
+        d = np.zeros(3); d[k] = h
+        nk = ((O.exp_vec(w64 + d) - O.exp_vec(w64 - d)) * G).sum((-1, -2)) / (2 * h)
+        assert np.max(np.abs(gw[:, k] - nk)) < 2e-4 * max(1.0, np.abs(nk).max())
