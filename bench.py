@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the SO(3) diffusion hot path (BASELINE.json metric: IGSO(3) score evals/sec &
+reverse-diffusion particle-steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n ROWS] [--L 2000]
+
+Headline workload (BASELINE configs[1]): one *step* = one fused launch evaluating log-density and
+score of the IGSO(3) truncated series (exactly L = 2000 terms per evaluation, no early exit) on
+n = 2^24 random rotations per GPU with per-row eps (E-set of SURVEY 8d).  `value` is device-timed with
+the inputs resident in HBM; `e2e` goes through the public Python API from pinned HOST buffers and
+back.  Secondary numbers (fused reverse step, fused forward noising, closed-form/auto evaluator)
+are reported under "extra" with their own HBM rooflines.  Rank 0 prints ONE JSON line.
+
+--impl reference times the torch-CPU port of the reference's algorithm (oracle/ref_port.py; the
+pure-Python reference cannot travel to the GPU box) on the host cores for the same metric.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "igso3_score_evals_per_sec"
+UNIT = "evals/s"
+SEED = 1234
+
+# ---- algorithmic work of the series kernel ---------------------------------
+# per term: 13 FP32 instructions (4 rotate, 1 m+=1, 1 chi, 1 D, 2 exponent, 2 weight, 2 accumulate)
+# of which 7 are FMAs, plus 1 MUFU.EX2  ->  20 flop + 1 MUFU, 14 issue slots per term per lane.
+FP32_INSTR_PER_TERM = 13
+MUFU_PER_TERM = 1
+FLOP_PER_TERM = 20
+BYTES_PER_EVAL = 56          # 36 R + 4 eps in, 4 logp + 12 score out
+BYTES_PER_PARTICLE_STEP = 84 # 36 x_t + 12 pred in, 36 out
+BYTES_PER_QSAMPLE = 92       # 36 x0 + 8 t in, 36 x_t + 12 target out
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "sm_max_mhz": 1965.0}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update(hbm_gbs=float(m["hbm_gbs"]), sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)), source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def make_eset(n, device, seed):
+    """E-set of SURVEY 8(d): eps log-uniform in [6.4e-3, 1], omega = eps*sqrt2*k, k~U[0,4] (<= 3.0)."""
+    import diffusion_extensions_b200 as dx
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    eps = torch.exp(torch.empty(n, device=device).uniform_(math.log(6.4e-3), 0.0, generator=g))
+    k = torch.empty(n, device=device).uniform_(0.0, 4.0, generator=g)
+    omega = torch.clamp(eps * math.sqrt(2.0) * k, max=3.0)
+    axis = torch.randn(n, 3, device=device, generator=g)
+    R = dx.ops.aa_to_rmat(axis, omega)
+    return R, eps
+
+
+def time_loop(fn, steps, warmup, dist_on):
+    """W untimed + K timed calls, bracketed by barrier + synchronize; device time via CUDA events."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist_on:
+        tt = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        ms = tt.item()
+    return ms
+
+
+def cpu_baseline(seconds_target=15.0):
+    """The reference's CPU path (torch port, all host threads) on a bounded sample of the same
+    workload: IGSO3(eps).log_prob(R) + autograd score, per-row eps, closed form in fp64."""
+    from oracle import ref_port as P
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 1 << 18
+    g = torch.Generator().manual_seed(SEED)
+    eps = torch.exp(torch.empty(n).uniform_(math.log(6.4e-3), 0.0, generator=g))
+    k = torch.empty(n).uniform_(0.0, 4.0, generator=g)
+    ang = torch.clamp(eps * math.sqrt(2.0) * k, min=1e-4, max=3.0)
+    axis = torch.randn(n, 3, generator=g)
+    axis = axis / axis.norm(dim=-1, keepdim=True)
+    K = P.hat(axis)
+    R = torch.eye(3) + torch.sin(ang)[:, None, None] * K + (1 - torch.cos(ang))[:, None, None] * (K @ K)
+    P.score_via_autograd(R[:1024], eps[:1024])
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        P.score_via_autograd(R, eps)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_target or reps >= 64:
+            break
+    return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} x 2^18 rotations, per-row eps, reference closed-form fp64 log_prob + autograd score (oracle/ref_port.py), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_port as P
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 1 << 18
+    g = torch.Generator().manual_seed(SEED)
+    eps = torch.exp(torch.empty(n).uniform_(math.log(6.4e-3), 0.0, generator=g))
+    k = torch.empty(n).uniform_(0.0, 4.0, generator=g)
+    ang = torch.clamp(eps * math.sqrt(2.0) * k, min=1e-4, max=3.0)
+    axis = torch.randn(n, 3, generator=g)
+    axis = axis / axis.norm(dim=-1, keepdim=True)
+    K = P.hat(axis)
+    R = torch.eye(3) + torch.sin(ang)[:, None, None] * K + (1 - torch.cos(ang))[:, None, None] * (K @ K)
+    for _ in range(args.warmup):
+        P.score_via_autograd(R, eps)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        P.score_via_autograd(R, eps)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = f"each step = 2^18 rotations (bounded sample of the 2^24-row step), per-row eps, reference closed-form fp64 log_prob + autograd score"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": "igso3_logp_score E-set, CPU reference port", "rows_per_step": n, "series_terms": None,
+                                         "evaluator": "closed form fp64 (the reference has no series)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 24, help="rotations per GPU per step")
+    ap.add_argument("--L", type=int, default=2000, help="series truncation")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary kernels")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import diffusion_extensions_b200 as dx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if dist_on:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    dx._lib.load()
+    n, L = args.n, args.L
+    pk = peaks()
+
+    # ---- inputs: this rank's shard of the global batch (rows are independent: no exchange) -----
+    R, eps = make_eset(n, device, SEED + rank)
+    logp = torch.empty(n, device=device)
+    score = torch.empty(n, 3, device=device)
+    lib_call, ptr = dx._lib.call, dx._lib.ptr
+
+    def step_series():
+        lib_call("so3d_igso3_logp_score_f32", ptr(R), ptr(eps), 1, ptr(logp), ptr(score), None, n, dx._lib.MODE_SERIES, L, device=device)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_series()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    ms = time_loop(step_series, args.steps, 0, dist_on)
+    clocks = sampler.stop() if sampler else None
+    evals_per_s = world * n * args.steps / (ms * 1e-3)
+    per_gpu = evals_per_s / world
+
+    # ---- e2e: public API, pinned host buffers in, host results out ----------------------------
+    n_e2e = n
+    hR = torch.empty(n_e2e, 3, 3, pin_memory=True).copy_(R[:n_e2e].cpu())
+    heps = torch.empty(n_e2e, pin_memory=True).copy_(eps[:n_e2e].cpu())
+    hlogp = torch.empty(n_e2e, 1, pin_memory=True)
+    hscore = torch.empty(n_e2e, 3, pin_memory=True)
+
+    def step_e2e():
+        dR = hR.to(device, non_blocking=True)
+        deps = heps.to(device, non_blocking=True)
+        lp, sc = dx.IsotropicGaussianSO3(deps, mode="series", series_terms=L).log_prob_and_score(dR)
+        hlogp.copy_(lp, non_blocking=True)
+        hscore.copy_(sc, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = time_loop(step_e2e, e2e_steps, 2, dist_on)
+    e2e = {"value": world * n_e2e * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_e2e * 40, "d2h_bytes_per_step": n_e2e * 16,
+           "ms_per_step": ms_e2e / e2e_steps}
+
+    # ---- secondary kernels ----------------------------------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        def rate(fn, rows, reps=5):
+            m = time_loop(fn, reps, 3, dist_on)
+            return world * rows * reps / (m * 1e-3), m / reps
+
+        for mode_name, mode in (("auto", dx._lib.MODE_AUTO), ("series_adaptive", dx._lib.MODE_SERIES_ADAPTIVE)):
+            v, m = rate(lambda: lib_call("so3d_igso3_logp_score_f32", ptr(R), ptr(eps), 1, ptr(logp), ptr(score), None, n, mode, L, device=device), n)
+            extra[f"score_evals_per_sec_{mode_name}"] = {"value": v, "ms_per_step": m}
+            if mode_name == "auto":
+                gbs = v / world * BYTES_PER_EVAL / 1e9
+                extra[f"score_evals_per_sec_{mode_name}"]["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
+        proc = dx.SO3Diffusion(None).to(device)
+        proc.row_offset = rank * n
+        fwd, post, t_range = proc.tables()
+        pred = torch.zeros(n, 3, device=device)
+        xa, xb = R.clone(), torch.empty_like(R)
+        t_step = t_range[500:501]
+        state = {"off": 0}
+
+        def step_rev():
+            state["off"] += 1
+            lib_call("so3d_p_sample_f32", ptr(xa), ptr(pred), ptr(t_step), 0, ptr(proc.sqrt_recip_alphas_cumprod), ptr(proc.sqrt_recipm1_alphas_cumprod),
+                     ptr(proc.posterior_mean_coef1), ptr(proc.posterior_mean_coef2), 1000, ptr(post), ptr(dx.ops.cdf_grid(device)[2]), SEED, state["off"],
+                     rank * n, ptr(xb), None, n, device=device)
+
+        v, m = rate(step_rev, n, 10)
+        gbs = v / world * BYTES_PER_PARTICLE_STEP / 1e9
+        extra["reverse_particle_steps_per_sec"] = {"value": v, "ms_per_step": m, "note": "fused p_sample kernel, pred = 0 (denoiser excluded), shared t = 500",
+                                                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}}
+        tt = torch.randint(0, 1000, (n,), device=device)
+        tgt = torch.empty(n, 3, device=device)
+
+        def step_fwd():
+            state["off"] += 1
+            lib_call("so3d_q_sample_f32", ptr(xa), ptr(tt), ptr(proc.sqrt_alphas_cumprod), ptr(proc.sqrt_one_minus_alphas_cumprod), 1000, ptr(fwd),
+                     ptr(dx.ops.cdf_grid(device)[2]), SEED, state["off"], rank * n, ptr(xb), ptr(tgt), None, None, n, device=device)
+
+        v, m = rate(step_fwd, n, 10)
+        gbs = v / world * BYTES_PER_QSAMPLE / 1e9
+        extra["noised_rotations_per_sec"] = {"value": v, "ms_per_step": m, "note": "fused q_sample + skewvec target, per-row t",
+                                             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}}
+
+    if rank == 0:
+        sm = torch.cuda.get_device_properties(device).multi_processor_count
+        ghz = pk["sm_max_mhz"] * 1e-3
+        fp32_peak_tflops = sm * 128 * 2 * ghz * 1e-3          # FFMA = 2 flop/lane/clk
+        issue_peak = sm * 128 * ghz * 1e9                      # lane-instructions/s (4 warp-instr/clk/SM)
+        ach_tflops = per_gpu * L * FLOP_PER_TERM * 1e-12
+        roofline = {
+            "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak_tflops,
+            "traffic": None,
+            "issue_slot_frac": per_gpu * L * (FP32_INSTR_PER_TERM + MUFU_PER_TERM) / issue_peak,
+            "mufu_frac": per_gpu * L * MUFU_PER_TERM / (sm * 16 * ghz * 1e9),
+            "hbm_gbs": per_gpu * BYTES_PER_EVAL / 1e9,
+            "naive_3mufu_roofline_evals_per_s": sm * 16 * ghz * 1e9 / (3 * L),
+            "peak_source": f"derived: {sm} SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz ({pk['source']}); HBM {pk['hbm_gbs']} GB/s",
+            "work_per_term": "13 FP32 instr (7 FMA) + 1 MUFU.EX2 = 20 flop, 14 issue slots",
+        }
+        line = {
+            "metric": METRIC, "value": evals_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "igso3_logp_score series L=2000, E-set (BASELINE configs[1])", "rows_per_gpu_per_step": n, "series_terms": L,
+                       "eps": "per-row, log-uniform [6.4e-3,1]", "l2": "inputs (640 MiB/GPU) larger than L2", "parallelism": f"batch-sharded x{world}, no collective in the data path"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "extra": extra,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if dist_on:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

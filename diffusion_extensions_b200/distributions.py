@@ -1,0 +1,126 @@
+"""Drop-in for ``distributions.IsotropicGaussianSO3`` of the reference (distributions.py:8-81).
+
+Same constructor / ``sample`` / ``log_prob`` / ``_eps_ft`` / ``mean`` / ``trap`` / ``trap_loc``
+surface, CUDA float32 only, every method one fused sm_100a kernel:
+
+  * the (999, *E) CDF table of distributions.py:15-30 is built on the device by one kernel
+    (fp64 density -> fp32 trapezoid CDF, same dtype at every step as the reference) and only when
+    something needs it (``sample`` / ``trap``), not in the constructor;
+  * ``sample`` draws axis + uniform with a counter-based Philox stream on the device (the reference
+    draws the axes with the CPU generator and copies them over, distributions.py:35), finds the
+    angle by binary search (shared-memory CDF row for scalar eps) and applies Rodrigues' formula;
+  * ``log_prob`` fuses axis-angle extraction, density and (saved for backward) d log f / d omega;
+    per-row eps is supported (the reference raises);
+  * ``score`` is new: (d/d omega log f) * axis, the quantity the reference only reaches through
+    autograd (distributions.py:186-190).
+
+``mode`` selects the density evaluator: "closed" (the reference's 3-image closed form in its stable
+rewrite), "series" (L-term truncated series), "auto" (default: closed form below eps = 0.6, series
+above; <= 1e-5 relative everywhere), "series_adaptive".
+``reference_quirks=True`` builds the CDF table from the reference's literal overflowing expression
+(density zeroed beyond omega > 709 eps^2/pi) so that samples match the reference at
+tiny eps too.  Quirk Q1 (column-0 gather with batched eps) is a plain bug and is not reproduced.
+"""
+import torch
+from torch.distributions import Distribution, constraints
+
+from . import ops
+
+
+class _LogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rotations, eps, mode, L):
+        logp, _, dlogf = ops.igso3_logp_score(rotations, eps, mode=mode, L=L, want_score=False, want_dlogf=True)
+        ctx.save_for_backward(rotations, dlogf)
+        return logp
+
+    @staticmethod
+    def backward(ctx, grad):
+        rotations, dlogf = ctx.saved_tensors
+        return ops.igso3_logp_bwd(rotations, dlogf, grad.contiguous()), None, None, None
+
+
+class IsotropicGaussianSO3(Distribution):
+    arg_constraints = {"eps": constraints.positive}
+
+    def __init__(self, eps: torch.Tensor, mean: torch.Tensor = None, mode: str = "auto", series_terms: int = 2000,
+                 reference_quirks: bool = False):
+        if not isinstance(eps, torch.Tensor):
+            raise TypeError("eps must be a torch.Tensor on a CUDA device")
+        if not eps.is_cuda:
+            raise RuntimeError("IsotropicGaussianSO3: eps must live on a CUDA device; this package has no CPU path")
+        self.eps = eps.float() if eps.dtype != torch.float32 else eps
+        self._mean = None if mean is None else mean.to(self.eps)
+        self.mode = mode
+        self.series_terms = int(series_terms)
+        self.reference_quirks = bool(reference_quirks)
+        self._table = None  # (E_flat, 999), built on first use
+        super().__init__(batch_shape=self.eps.shape, validate_args=False)
+
+    # -- CDF table (distributions.py:15-30) ------------------------------------------------------
+    @property
+    def table(self) -> torch.Tensor:
+        """(numel(eps), 999): one contiguous CDF row per eps (transpose of the reference layout)."""
+        if self._table is None:
+            self._table = ops.igso3_cdf_table(self.eps.reshape(-1), self.reference_quirks)
+        return self._table
+
+    @property
+    def trap(self) -> torch.Tensor:
+        """Reference layout: (999, *E), or (999, 1) for scalar eps."""
+        t = self.table.t()
+        return t.reshape(ops.CDF_POINTS, *self.eps.shape) if self.eps.dim() > 0 else t
+
+    @property
+    def trap_loc(self) -> torch.Tensor:
+        return ops.cdf_grid(self.eps.device)[2][:, None]
+
+    @property
+    def mean(self):
+        if self._mean is None:
+            return torch.eye(3, dtype=torch.float32, device=self.eps.device)
+        return self._mean
+
+    # -- sampling (distributions.py:33-51) -------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, sample_shape=torch.Size(), *, u=None, axes=None, row_offset=0, return_angle=False):
+        """Rotations of shape (*sample_shape, *eps.shape, 3, 3).
+        u / axes: optional explicit uniforms / (un-normalised) axes, for reproducing given draws."""
+        sample_shape = tuple(sample_shape)
+        shape = sample_shape + tuple(self.eps.shape)
+        if self.eps.dim() == 0:
+            row_idx, row = None, 0
+        else:
+            row_idx = torch.arange(self.eps.numel(), device=self.eps.device).reshape(self.eps.shape).expand(shape)
+            row = 0
+        return ops.igso3_sample(self.table, shape, row_idx=row_idx, row=row, u=u, axes=axes, row_offset=row_offset,
+                                mean=self._mean, want_angle=return_angle)
+
+    # -- density (distributions.py:53-72) --------------------------------------------------------
+    def _eps_ft(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.to(device=self.eps.device, dtype=torch.float32)
+        if self.eps.numel() == 1:
+            return ops.igso3_density(t.contiguous(), self.eps, mode=self.mode, L=self.series_terms)
+        shape = torch.broadcast_shapes(t.shape, self.eps.shape)
+        return ops.igso3_density(t.expand(shape).contiguous(), self.eps.expand(shape).contiguous(), mode=self.mode, L=self.series_terms)
+
+    def log_prob(self, rotations):
+        """distributions.py:74-77: log f_eps(angle(R)), shape (..., 1).  Differentiable w.r.t. rotations."""
+        if torch.is_grad_enabled() and rotations.requires_grad:
+            return _LogProb.apply(rotations, self.eps, self.mode, self.series_terms)[..., None]
+        logp, _, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.mode, L=self.series_terms, want_score=False)
+        return logp[..., None]
+
+    @torch.no_grad()
+    def score(self, rotations):
+        """(d log f / d omega) * axis, shape (..., 3): the Riemannian score in the body frame."""
+        _, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.mode, L=self.series_terms, want_score=True)
+        return score
+
+    @torch.no_grad()
+    def log_prob_and_score(self, rotations):
+        logp, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.mode, L=self.series_terms, want_score=True)
+        return logp[..., None], score
+
+
+__all__ = ["IsotropicGaussianSO3"]

@@ -1,0 +1,396 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see util.py / distributions.py).
+
+Every function takes CUDA float32 tensors with arbitrary leading batch dims, flattens them to
+rows, launches ONE fused kernel on the current stream and returns freshly allocated tensors.
+Nothing here synchronises with the host.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import call, check_f32, ptr
+
+CDF_POINTS = 999
+GRID_POINTS = 1000
+
+
+# ---------------------------------------------------------------------------------------------
+# counter-based RNG state (Philox key/offset), following torch.manual_seed like a torch op would
+# ---------------------------------------------------------------------------------------------
+class _Rng:
+    def __init__(self):
+        self.seed = None
+        self.offset = 0
+        self._torch_seed = None
+
+    def manual_seed(self, seed):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.offset = 0
+        self._torch_seed = torch.initial_seed()
+
+    def next(self):
+        """(seed, offset) for one sampling launch; every launch gets a fresh offset."""
+        ts = torch.initial_seed()
+        if self.seed is None or ts != self._torch_seed:  # torch.manual_seed() was called since
+            self.seed = ts & 0xFFFFFFFFFFFFFFFF
+            self.offset = 0
+            self._torch_seed = ts
+        off = self.offset
+        self.offset += 1
+        return self.seed, off
+
+
+rng = _Rng()
+
+
+def manual_seed(seed):
+    """Seed the Philox stream used by the sampling kernels (torch.manual_seed also resets it)."""
+    rng.manual_seed(seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+def _rows9(x, name):
+    x = check_f32(x, name, (3, 3))
+    return x, x.shape[:-2], x.numel() // 9
+
+
+def _rows3(x, name):
+    x = check_f32(x, name, (3,))
+    return x, x.shape[:-1], x.numel() // 3
+
+
+def _per_row(s, batch_shape, device, name):
+    """Per-row scalar operand -> (tensor, stride): stride 0 for a single shared value."""
+    if not isinstance(s, torch.Tensor):
+        s = torch.tensor(float(s), dtype=torch.float32, device=device)
+    s = check_f32(s, name)
+    if s.numel() == 1:
+        return s.reshape(1), 0
+    s = s.expand(batch_shape).contiguous() if tuple(s.shape) != tuple(batch_shape) else s
+    return s, 1
+
+
+def _bcast2(a, b):
+    """Broadcast the batch dims of two (...,3,3) tensors."""
+    if a.shape != b.shape:
+        bs = torch.broadcast_shapes(a.shape[:-2], b.shape[:-2])
+        a = a.expand(*bs, 3, 3).contiguous()
+        b = b.expand(*bs, 3, 3).contiguous()
+    return a, b
+
+
+# ---------------------------------------------------------------------------------------------
+# L0
+# ---------------------------------------------------------------------------------------------
+def log_rmat(R):
+    R, bs, n = _rows9(R, "r_mat")
+    out = torch.empty_like(R)
+    call("so3d_log_f32", ptr(R), ptr(out), n, device=R.device)
+    return out
+
+
+def log_vec(R):
+    R, bs, n = _rows9(R, "r_mat")
+    out = torch.empty(*bs, 3, dtype=torch.float32, device=R.device)
+    call("so3d_logvec_f32", ptr(R), ptr(out), n, device=R.device)
+    return out
+
+
+def rmat_to_aa(R):
+    """-> unit axis (...,3), angle (...)"""
+    R, bs, n = _rows9(R, "r_mat")
+    axis = torch.empty(*bs, 3, dtype=torch.float32, device=R.device)
+    angle = torch.empty(*bs, dtype=torch.float32, device=R.device)
+    call("so3d_rmat_to_aa_f32", ptr(R), ptr(axis), ptr(angle), n, device=R.device)
+    return axis, angle
+
+
+def aa_to_rmat(axis, angle):
+    """axis (...,3) (normalised inside), angle (...)"""
+    axis = check_f32(axis, "rot_axis", (3,))
+    angle = check_f32(angle, "ang")
+    bs = torch.broadcast_shapes(axis.shape[:-1], angle.shape)
+    axis = axis.expand(*bs, 3).contiguous()
+    angle = angle.expand(bs).contiguous()
+    out = torch.empty(*bs, 3, 3, dtype=torch.float32, device=axis.device)
+    call("so3d_aa_to_rmat_f32", ptr(axis), ptr(angle), ptr(out), angle.numel(), device=axis.device)
+    return out
+
+
+def exp_vec(v):
+    v, bs, n = _rows3(v, "vec")
+    out = torch.empty(*bs, 3, 3, dtype=torch.float32, device=v.device)
+    call("so3d_expvec_f32", ptr(v), ptr(out), n, device=v.device)
+    return out
+
+
+def so3_scale(R, scalars):
+    R = check_f32(R, "rmat", (3, 3))
+    if isinstance(scalars, torch.Tensor) and scalars.numel() > 1 and tuple(scalars.shape) != tuple(R.shape[:-2]):
+        bs = torch.broadcast_shapes(R.shape[:-2], scalars.shape)
+        R = R.expand(*bs, 3, 3).contiguous()
+    bs, n = R.shape[:-2], R.numel() // 9
+    s, stride = _per_row(scalars, bs, R.device, "scalars")
+    out = torch.empty_like(R)
+    call("so3d_scale_f32", ptr(R), ptr(s), stride, ptr(out), n, device=R.device)
+    return out
+
+
+def quat_to_rmat(q):
+    q = check_f32(q, "quaternions", (4,))
+    out = torch.empty(*q.shape[:-1], 3, 3, dtype=torch.float32, device=q.device)
+    call("so3d_quat_to_rmat_f32", ptr(q), ptr(out), q.numel() // 4, device=q.device)
+    return out
+
+
+def rmat_to_quat(R):
+    R, bs, n = _rows9(R, "r_mat")
+    out = torch.empty(*bs, 4, dtype=torch.float32, device=R.device)
+    call("so3d_rmat_to_quat_f32", ptr(R), ptr(out), n, device=R.device)
+    return out
+
+
+def compose(A, B, trans_a=False, trans_b=False):
+    """op(A) @ op(B) for batched 3x3; a single (3,3) operand is shared by all rows."""
+    A = check_f32(A, "A", (3, 3))
+    B = check_f32(B, "B", (3, 3))
+    if A.numel() == 9 and B.numel() > 9:
+        sa, sb, bs, n = 0, 1, B.shape[:-2], B.numel() // 9
+    elif B.numel() == 9 and A.numel() > 9:
+        sa, sb, bs, n = 1, 0, A.shape[:-2], A.numel() // 9
+    else:
+        A, B = _bcast2(A, B)
+        sa, sb, bs, n = 1, 1, A.shape[:-2], A.numel() // 9
+    out = torch.empty(*bs, 3, 3, dtype=torch.float32, device=A.device)
+    call("so3d_compose_f32", ptr(A), sa, int(trans_a), ptr(B), sb, int(trans_b), ptr(out), n, device=A.device)
+    return out
+
+
+def rmat_dist(A, B):
+    A = check_f32(A, "input", (3, 3))
+    B = check_f32(B, "target", (3, 3))
+    A, B = _bcast2(A, B)
+    out = torch.empty(A.shape[:-2], dtype=torch.float32, device=A.device)
+    call("so3d_rmat_dist_f32", ptr(A), ptr(B), ptr(out), A.numel() // 9, device=A.device)
+    return out
+
+
+def so3_lerp(A, B, weight):
+    """weight: (...) (no trailing 1)."""
+    A = check_f32(A, "rot_a", (3, 3))
+    B = check_f32(B, "rot_b", (3, 3))
+    A, B = _bcast2(A, B)
+    w, stride = _per_row(weight, A.shape[:-2], A.device, "weight")
+    out = torch.empty_like(A)
+    call("so3d_lerp_f32", ptr(A), ptr(B), ptr(w), stride, ptr(out), A.numel() // 9, device=A.device)
+    return out
+
+
+# backward passes
+def log_rmat_bwd(R, G):
+    R, _, n = _rows9(R, "r_mat")
+    G = check_f32(G, "grad", (3, 3))
+    out = torch.empty_like(R)
+    call("so3d_log_bwd_f32", ptr(R), ptr(G), ptr(out), n, device=R.device)
+    return out
+
+
+def aa_to_rmat_bwd(axis, angle, G):
+    axis = check_f32(axis, "rot_axis", (3,))
+    angle = check_f32(angle, "ang")
+    G = check_f32(G, "grad", (3, 3))
+    g_axis = torch.empty_like(axis)
+    g_angle = torch.empty_like(angle)
+    call("so3d_aa_to_rmat_bwd_f32", ptr(axis), ptr(angle), ptr(G), ptr(g_axis), ptr(g_angle), angle.numel(), device=axis.device)
+    return g_axis, g_angle
+
+
+def exp_vec_bwd(v, G):
+    v = check_f32(v, "vec", (3,))
+    G = check_f32(G, "grad", (3, 3))
+    out = torch.empty_like(v)
+    call("so3d_expvec_bwd_f32", ptr(v), ptr(G), ptr(out), v.numel() // 3, device=v.device)
+    return out
+
+
+def so3_scale_bwd(R, s, stride, G):
+    """-> grad wrt R (...,3,3), per-row grad wrt the scalar (...)"""
+    R, bs, n = _rows9(R, "rmat")
+    G = check_f32(G, "grad", (3, 3))
+    gR = torch.empty_like(R)
+    gs = torch.empty(bs, dtype=torch.float32, device=R.device)
+    call("so3d_scale_bwd_f32", ptr(R), ptr(s), stride, ptr(G), ptr(gR), ptr(gs), n, device=R.device)
+    return gR, gs
+
+
+# ---------------------------------------------------------------------------------------------
+# L1: IGSO(3)
+# ---------------------------------------------------------------------------------------------
+def _mode(mode):
+    if isinstance(mode, str):
+        if mode not in _lib.MODES:
+            raise ValueError(f"mode must be one of {sorted(_lib.MODES)}")
+        return _lib.MODES[mode]
+    return int(mode)
+
+
+def igso3_density(omega, eps, mode="closed", L=2000):
+    omega = check_f32(omega, "t")
+    eps_t, stride = _per_row(eps, omega.shape, omega.device, "eps")
+    out = torch.empty_like(omega)
+    call("so3d_igso3_density_f32", ptr(omega), ptr(eps_t), stride, ptr(out), omega.numel(), _mode(mode), int(L), device=omega.device)
+    return out
+
+
+def igso3_logp_score(R, eps, mode="auto", L=2000, want_score=True, want_dlogf=False):
+    """-> logp (...), score (...,3) or None, dlogf (...) or None"""
+    R, bs, n = _rows9(R, "rotations")
+    eps_t, stride = _per_row(eps, bs, R.device, "eps")
+    logp = torch.empty(bs, dtype=torch.float32, device=R.device)
+    score = torch.empty(*bs, 3, dtype=torch.float32, device=R.device) if want_score else None
+    dlogf = torch.empty(bs, dtype=torch.float32, device=R.device) if want_dlogf else None
+    call("so3d_igso3_logp_score_f32", ptr(R), ptr(eps_t), stride, ptr(logp), ptr(score), ptr(dlogf), n, _mode(mode), int(L), device=R.device)
+    return logp, score, dlogf
+
+
+def igso3_logp_bwd(R, dlogf, gout):
+    R, bs, n = _rows9(R, "rotations")
+    dlogf = check_f32(dlogf, "dlogf")
+    gout = check_f32(gout.expand(bs), "grad_output")
+    out = torch.empty_like(R)
+    call("so3d_igso3_logp_bwd_f32", ptr(R), ptr(dlogf), ptr(gout), ptr(out), n, device=R.device)
+    return out
+
+
+_grid_cache = {}
+
+
+def cdf_grid(device):
+    """The reference's 1000-point float32 grid and Haar weights, computed with the same torch CPU
+    ops the reference uses (distributions.py:15, :21) so the float32 values are bit-identical.
+    -> (grid_loc[1000], haar_w[1000], trap_loc[999]) on `device`."""
+    key = str(device)
+    if key not in _grid_cache:
+        loc = math.pi * torch.linspace(0, 1.0, GRID_POINTS) ** 3.0
+        haar = (1 - loc.cos()) / math.pi
+        loc_d = loc.to(device)
+        _grid_cache[key] = (loc_d, haar.to(device), loc_d[1:].contiguous())
+    return _grid_cache[key]
+
+
+def igso3_cdf_table(eps, reference_quirks=False):
+    """eps (rows,) -> trap (rows, 999): one CDF row per eps (distributions.py:15-30)."""
+    eps = check_f32(eps, "eps").reshape(-1)
+    loc, haar, _ = cdf_grid(eps.device)
+    out = torch.empty(eps.numel(), CDF_POINTS, dtype=torch.float32, device=eps.device)
+    call("so3d_igso3_cdf_table_f32", ptr(eps), eps.numel(), ptr(loc), ptr(haar), ptr(out), int(bool(reference_quirks)), device=eps.device)
+    return out
+
+
+def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, rng_offset=None, row_offset=0,
+                 mean=None, want_angle=False, want_axis=False):
+    """Draw rotations of batch shape `shape` from the CDF rows in `cdf` (rows, 999).
+    row_idx: int64 tensor of shape `shape` (one table row per sample) or None -> all use `row`.
+    u / axes: optional explicit draws.  -> R (*shape,3,3)[, angle (*shape)][, axis (*shape,3)]"""
+    cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
+    dev = cdf.device
+    shape = tuple(shape)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    _, _, trap_loc = cdf_grid(dev)
+    if row_idx is not None:
+        row_idx = row_idx.to(device=dev, dtype=torch.int64).expand(shape).contiguous()
+    if u is not None:
+        u = check_f32(u, "u").expand(shape).contiguous()
+    if axes is not None:
+        axes = check_f32(axes, "axes", (3,)).expand(*shape, 3).contiguous()
+    if seed is None or rng_offset is None:
+        seed, rng_offset = rng.next()
+    mean_stride = 0
+    if mean is not None:
+        mean = check_f32(mean, "mean", (3, 3))
+        if mean.numel() != 9:
+            mean = mean.expand(*shape, 3, 3).contiguous()
+            mean_stride = 1
+    R = torch.empty(*shape, 3, 3, dtype=torch.float32, device=dev)
+    angle = torch.empty(shape, dtype=torch.float32, device=dev) if want_angle else None
+    axis_out = torch.empty(*shape, 3, dtype=torch.float32, device=dev) if want_axis else None
+    call("so3d_igso3_sample_f32", ptr(cdf), ptr(trap_loc), cdf.numel() // CDF_POINTS, ptr(row_idx), int(row), ptr(u), ptr(axes),
+         seed, rng_offset, int(row_offset), ptr(mean), mean_stride, ptr(R), ptr(angle), ptr(axis_out), n, device=dev)
+    outs = [R]
+    if want_angle:
+        outs.append(angle)
+    if want_axis:
+        outs.append(axis_out)
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+# ---------------------------------------------------------------------------------------------
+# L2: fused diffusion steps
+# ---------------------------------------------------------------------------------------------
+def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, row_offset=0,
+                   want_target=True, want_noise=False, want_score=False):
+    """-> dict(x_t, target, noise, score) (absent entries are None)."""
+    x0, bs, n = _rows9(x0, "x_start")
+    dev = x0.device
+    t = t.to(device=dev, dtype=torch.int64).expand(bs).contiguous()
+    sqrt_ac = check_f32(sqrt_ac, "sqrt_alphas_cumprod")
+    sqrt_1m_ac = check_f32(sqrt_1m_ac, "sqrt_one_minus_alphas_cumprod")
+    cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
+    T = sqrt_ac.numel()
+    if cdf.numel() != T * CDF_POINTS:
+        raise ValueError("cdf table must have one row per timestep")
+    _, _, trap_loc = cdf_grid(dev)
+    if seed is None or rng_offset is None:
+        seed, rng_offset = rng.next()
+    x_t = torch.empty_like(x0)
+    target = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_target else None
+    noise = torch.empty_like(x0) if want_noise else None
+    score = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_score else None
+    call("so3d_q_sample_f32", ptr(x0), ptr(t), ptr(sqrt_ac), ptr(sqrt_1m_ac), T, ptr(cdf), ptr(trap_loc), seed, rng_offset,
+         int(row_offset), ptr(x_t), ptr(target), ptr(noise), ptr(score), n, device=dev)
+    return {"x_t": x_t, "target": target, "noise": noise, "score": score}
+
+
+def q_sample_given(x0, t, sqrt_ac, noise):
+    x0, bs, n = _rows9(x0, "x_start")
+    noise = check_f32(noise, "noise", (3, 3)).expand_as(x0).contiguous()
+    t = t.to(device=x0.device, dtype=torch.int64).expand(bs).contiguous()
+    sqrt_ac = check_f32(sqrt_ac, "sqrt_alphas_cumprod")
+    out = torch.empty_like(x0)
+    call("so3d_q_sample_given_f32", ptr(x0), ptr(t), ptr(sqrt_ac), sqrt_ac.numel(), ptr(noise), ptr(out), n, device=x0.device)
+    return out
+
+
+def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, seed=None, rng_offset=None, row_offset=0,
+                   want_x0_hat=False):
+    """Fused reverse step.  t: int64 tensor with one element (shared step) or one per row.
+    post_cdf None -> posterior mean only.  -> out (...,3,3)[, x0_hat]"""
+    x_t, bs, n = _rows9(x_t, "x")
+    dev = x_t.device
+    pred = check_f32(pred, "predict", (3,)).expand(*bs, 3).contiguous()
+    t = t.to(device=dev, dtype=torch.int64)
+    if t.numel() == 1:
+        t, t_stride = t.reshape(1).contiguous(), 0
+    else:
+        t, t_stride = t.expand(bs).contiguous(), 1
+    recip, recipm1 = check_f32(recip, "sqrt_recip_alphas_cumprod"), check_f32(recipm1, "sqrt_recipm1_alphas_cumprod")
+    coef1, coef2 = check_f32(coef1, "posterior_mean_coef1"), check_f32(coef2, "posterior_mean_coef2")
+    T = recip.numel()
+    trap_loc = None
+    if post_cdf is not None:
+        post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
+        if post_cdf.numel() != T * CDF_POINTS:
+            raise ValueError("posterior cdf table must have one row per timestep")
+        _, _, trap_loc = cdf_grid(dev)
+        if seed is None or rng_offset is None:
+            seed, rng_offset = rng.next()
+    out = torch.empty_like(x_t)
+    x0_hat = torch.empty_like(x_t) if want_x0_hat else None
+    call("so3d_p_sample_f32", ptr(x_t), ptr(pred), ptr(t), t_stride, ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T,
+         ptr(post_cdf), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(x0_hat), n, device=dev)
+    return (out, x0_hat) if want_x0_hat else out

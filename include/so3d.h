@@ -1,0 +1,143 @@
+/* so3d.h -- C ABI of libso3d: sm_100a kernels for batched SO(3) manifold-diffusion math.
+ *
+ * Drop-in boundary for the hot path of qazwsxal/diffusion-extensions (@ f100885d):
+ *   util.py (log/exp/axis-angle/scale/quaternion), distributions.py (IsotropicGaussianSO3) and
+ *   diffusion.py (SO3Diffusion.q_sample / p_losses / p_sample).
+ * The reference has no FFI layer of its own (it is pure Python/PyTorch); each entry point below
+ * cites the reference function (file:line) whose arithmetic it replaces, and INTEGRATION.md shows
+ * the ctypes binding the Python side uses.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device, float32 unless stated, dense
+ *     row-major:  rotations n x 9 (3x3 row-major, 36 B), vectors n x 3, quaternions n x 4
+ *     (real part first), scalars n.  Pointers need only 4-byte alignment; 16-byte aligned buffers
+ *     take the vectorised path.
+ *   - the caller owns all memory (inputs and outputs); the library never allocates, frees or keeps
+ *     a pointer after return.
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); it never synchronises, so calls are CUDA-graph capturable.
+ *   - return value: 0 on success, >0 a cudaError_t from the launch, <0 an argument error
+ *     (SO3D_EINVAL).  so3d_last_error() returns a thread-local message for the last failure.
+ *   - NaN in -> NaN out; nothing traps.  n == 0 is a no-op.
+ *   - `*_stride` arguments for per-row scalars: 1 = one value per row, 0 = a single value shared by
+ *     all rows (the reference's scalar-eps / scalar-scale broadcasting).
+ *   - random draws are counter based (Philox4x32-10): key = seed, counter = (row_offset + row,
+ *     rng_offset).  Results do not depend on how a batch is sharded over GPUs when each shard passes
+ *     its global row_offset.
+ */
+#ifndef SO3D_H_
+#define SO3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO3D_VERSION 100
+#define SO3D_EINVAL (-1)
+
+#define SO3D_CDF_POINTS 999  /* entries per CDF row (distributions.py:15,30: 1000-point grid) */
+#define SO3D_GRID_POINTS 1000
+
+/* evaluator for the IGSO(3) density (mode argument) */
+#define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms                    */
+#define SO3D_MODE_CLOSED 1          /* 3-image closed form, distributions.py:53-72, stable rewrite         */
+#define SO3D_MODE_AUTO 2            /* closed form for eps < 0.6, series (live terms only) otherwise       */
+#define SO3D_MODE_SERIES_ADAPTIVE 3 /* series, skipping terms whose fp32 weight is exactly 0 (same result) */
+
+int so3d_version(void);
+const char* so3d_last_error(void);
+
+/* ---- L0: util.py -------------------------------------------------------------------------- */
+/* util.py:164-192 log_rmat: out = 3x3 skew matrix log(R). */
+int so3d_log_f32(const float* R, float* out9, int64_t n, void* stream);
+/* util.py:79-84 o 164-192: vee(log R) as a 3-vector. */
+int so3d_logvec_f32(const float* R, float* out3, int64_t n, void* stream);
+/* util.py:208-219 rmat_to_aa: unit axis (n x 3) and angle in [0, pi] (n). */
+int so3d_rmat_to_aa_f32(const float* R, float* axis3, float* angle, int64_t n, void* stream);
+/* util.py:195-205 aa_to_rmat: axis is normalised inside, like the reference. */
+int so3d_aa_to_rmat_f32(const float* axis3, const float* angle, float* R, int64_t n, void* stream);
+/* diffusion.py:294 matrix_exp(vec2skew(v)). */
+int so3d_expvec_f32(const float* v3, float* R, int64_t n, void* stream);
+/* util.py:349-361 so3_scale. */
+int so3d_scale_f32(const float* R, const float* s, int s_stride, float* out, int64_t n, void* stream);
+/* util.py:222-252 quat_to_rmat (real-first, un-normalised input allowed). */
+int so3d_quat_to_rmat_f32(const float* q4, float* R, int64_t n, void* stream);
+/* no reference counterpart: unit quaternion (real-first, real part >= 0) of a rotation matrix. */
+int so3d_rmat_to_quat_f32(const float* R, float* q4, int64_t n, void* stream);
+/* batched 3x3 product C = op(A) op(B), op = transpose when trans* != 0 (the `@` at
+ * distributions.py:50, diffusion.py:297,302,326,346).  a_stride/b_stride: 1 = per row, 0 = one
+ * shared matrix. */
+int so3d_compose_f32(const float* A, int a_stride, int trans_a, const float* B, int b_stride, int trans_b,
+                     float* C, int64_t n, void* stream);
+/* util.py:315-322 rmat_dist = |log(A^T B)|_F = sqrt(2) theta. */
+int so3d_rmat_dist_f32(const float* A, const float* B, float* out, int64_t n, void* stream);
+/* util.py:325-338 so3_lerp: A @ rot(axis(A^T B), w * angle(A^T B)). */
+int so3d_lerp_f32(const float* A, const float* B, const float* w, int w_stride, float* out, int64_t n, void* stream);
+
+/* backward passes (what autograd through the reference's torch ops yields; G = upstream grad) */
+int so3d_log_bwd_f32(const float* R, const float* G9, float* gR, int64_t n, void* stream);
+int so3d_aa_to_rmat_bwd_f32(const float* axis3, const float* angle, const float* G9, float* g_axis3,
+                            float* g_angle, int64_t n, void* stream);
+int so3d_expvec_bwd_f32(const float* v3, const float* G9, float* g_v3, int64_t n, void* stream);
+int so3d_scale_bwd_f32(const float* R, const float* s, int s_stride, const float* G9, float* gR, float* g_s,
+                       int64_t n, void* stream);
+
+/* ---- L1: distributions.py IsotropicGaussianSO3 ------------------------------------------ */
+/* distributions.py:53-72 _eps_ft: density f_eps(omega) (w.r.t. Haar measure, no (1-cos)/pi). */
+int so3d_igso3_density_f32(const float* omega, const float* eps, int eps_stride, float* f, int64_t n, int mode,
+                           int L, void* stream);
+/* distributions.py:74-77 log_prob fused with axis-angle extraction and the score:
+ *   logp[n] = log f_eps(angle(R));  score3[n x 3] = (d log f / d omega) * axis (nullable);
+ *   dlogf[n] = d log f / d omega (nullable; saved for the backward). */
+int so3d_igso3_logp_score_f32(const float* R, const float* eps, int eps_stride, float* logp, float* score3,
+                              float* dlogf, int64_t n, int mode, int L, void* stream);
+/* gradient of sum(gout * logp) w.r.t. the 9 matrix entries (matches autograd through
+ * distributions.py:74-77 + util.py:164-219). */
+int so3d_igso3_logp_bwd_f32(const float* R, const float* dlogf, const float* gout, float* gR, int64_t n,
+                            void* stream);
+/* distributions.py:15-30: CDF rows for `rows` values of eps.  grid_loc/haar_w are the reference's
+ * 1000-point float32 grid pi*linspace(0,1,1000)^3 and (1-cos(loc))/pi (host-computed, passed in so
+ * the fp32 values are bit-identical to torch's).  trap_out is rows x 999 (the transpose of the
+ * reference's (999, *E) layout).  quirks != 0 reproduces the reference's overflow behaviour (D5). */
+int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_loc, const float* haar_w,
+                             float* trap_out, int quirks, void* stream);
+/* distributions.py:33-51 sample: R = mean @ rot(axis, angle(u)).
+ *   cdf: table rows x 999;  loc: 999 grid angles;  row_idx: int64[n] row per sample, or NULL with
+ *   `row` = the single shared row (scalar-eps path, staged in shared memory).
+ *   u / axes3: optional explicit draws (u in [0,1), axes un-normalised like randn) -- when NULL
+ *   they come from Philox(seed, row_offset + i, rng_offset).
+ *   mean: optional 3x3 (mean_stride 0) or n x 9 (mean_stride 1) left factor.
+ *   outputs: R (n x 9), and optionally the drawn angle[n] / unit axis3[n x 3]. */
+int so3d_igso3_sample_f32(const float* cdf, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+                          const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset,
+                          uint64_t row_offset, const float* mean, int mean_stride, float* R, float* angle,
+                          float* axis3, int64_t n, void* stream);
+
+/* ---- L2: diffusion.py SO3Diffusion ---------------------------------------------------------- */
+/* diffusion.py:339-346 q_sample + :348-355 p_losses target, fused:
+ *   eps = sqrt_1m_ac[t], noise ~ IGSO3(eps) from cdf row t, x_t = so3_scale(x0, sqrt_ac[t]) @ noise,
+ *   target = vee(log noise) / eps  (nullable), noise (nullable), score of the noise under
+ *   IGSO3(eps) (nullable, auto evaluator).  t: int64[n] in [0, T). */
+int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
+                      const float* cdf, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
+                      float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream);
+/* q_sample with the noise supplied by the caller (diffusion.py:339-346 with noise != None). */
+int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt_ac, int64_t T, const float* noise,
+                            float* x_t, int64_t n, void* stream);
+/* diffusion.py:291-326 reverse step, fused:
+ *   x0_hat = so3_scale(x_t, recip[t]) @ exp(hat(pred * recipm1[t]))^T          (:291-297)
+ *   mean   = so3_scale(x0_hat, coef1[t]) @ so3_scale(x_t, coef2[t])            (:299-302)
+ *   out    = t == 0 ? mean : mean @ noise,  noise ~ IGSO3(sigma_t) from post_cdf row t   (:315-326)
+ *   t: int64[n] per row (t_stride 1) or a single shared step (t_stride 0, CDF row staged in smem).
+ *   post_cdf == NULL returns the mean only (p_mean_variance).  x0_hat_out nullable. */
+int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, int t_stride, const float* recip,
+                      const float* recipm1, const float* coef1, const float* coef2, int64_t T,
+                      const float* post_cdf, const float* loc, uint64_t seed, uint64_t rng_offset,
+                      uint64_t row_offset, float* out, float* x0_hat_out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SO3D_H_ */

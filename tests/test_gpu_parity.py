@@ -1,0 +1,598 @@
+"""GPU parity tests: the sm_100a kernels, called through the Python drop-in API (which goes through
+the C ABI of libso3d.so), against the fp64 oracle and the golden vectors produced by the reference.
+
+Tolerances follow the north star: density / score / exp / log <= 1e-5 relative (fp32 vs fp64
+truth), inverse-CDF angles <= 1e-5 rad given the same uniforms.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import so3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dx(cuda_device):
+    import diffusion_extensions_b200 as pkg
+
+    pkg._lib.load()
+    return pkg
+
+
+def dev(a, device):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(device)
+
+
+def host(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def rand_rots(n, seed, max_angle=math.pi):
+    rng = np.random.default_rng(seed)
+    R, axis, ang = O.random_rotations(n, rng, max_angle)
+    return R.astype(np.float32), axis, ang
+
+
+SIZES = [1, 7, 255, 256, 257, 4099]
+
+
+# ---------------------------------------------------------------------------------------------
+# L0 against golden (reference outputs) and oracle
+# ---------------------------------------------------------------------------------------------
+def test_l0_against_reference_golden(dx, cuda_device, golden):
+    g = golden("util_l0")
+    U = dx.util
+    d = lambda k: dev(g[k], cuda_device)
+    assert np.max(np.abs(host(U.log_rmat(d("Rall"))) - g["log_all"])) < 3e-6
+    axis, ang = U.rmat_to_aa(d("R"))
+    assert ang.shape == (192, 1)
+    assert np.max(np.abs(host(ang) - g["angle"])) < 3e-6
+    assert np.max(np.abs(host(axis) - g["axis"])) < 5e-6
+    assert np.max(np.abs(host(U.aa_to_rmat(d("axes_in"), d("ang_in"))) - g["aa_rmat"])) < 2e-6
+    assert np.max(np.abs(host(U.so3_scale(d("R"), d("scalars"))) - g["scaled"])) < 5e-6
+    assert np.max(np.abs(host(U.quat_to_rmat(d("quat"))) - g["quat_rmat"])) < 1e-6
+    assert np.max(np.abs(host(U.so3_lerp(d("R"), d("R2"), d("lerp_w"))) - g["lerp"])) < 2e-5
+    assert np.max(np.abs(host(U.rmat_dist(d("R"), d("R2"))) - g["dist"])) < 5e-6
+    assert np.max(np.abs(host(U.exp_vec(d("vec"))) - g["expvec"])) < 2e-6
+    assert np.array_equal(host(U.vec2skew(d("vec"))), g["skew"].astype(np.float64))
+    assert np.array_equal(host(U.skew2vec(d("skew"))), g["vee"].astype(np.float64))
+    # util.py:500,507-512 known answers
+    assert torch.all(U.log_rmat(torch.eye(3, device=cuda_device)[None]) == 0)
+    piz = host(U.log_rmat(torch.diag(torch.tensor([-1.0, -1.0, 1.0], device=cuda_device))[None]))
+    assert np.allclose(np.abs(piz), np.abs(g["pi_z"]), atol=1e-6)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_l0_against_oracle_ragged_sizes(dx, cuda_device, n):
+    U = dx.util
+    R, _, _ = rand_rots(n, n)
+    R2, _, _ = rand_rots(n, n + 1)
+    rng = np.random.default_rng(n)
+    Rd, R2d = dev(R, cuda_device), dev(R2, cuda_device)
+    lv = host(dx.ops.log_vec(Rd))
+    ang_t = O.rmat_to_aa(R)[1][:, 0]
+    ok = ang_t < 3.1
+    assert np.max(np.abs(lv - O.log_vec(R))[ok], initial=0) < 3e-6
+    axis, ang = U.rmat_to_aa(Rd)
+    back = O.rodrigues(host(axis), host(ang)[:, 0])
+    assert np.max(np.abs(back - R)) < 2e-6   # log then exp round trip, valid up to pi
+    s = np.exp(rng.uniform(math.log(1e-4), math.log(3.0), n)).astype(np.float32)
+    assert np.max(np.abs(host(U.so3_scale(Rd, dev(s, cuda_device))) - O.so3_scale(R, s))) < 3e-6
+    assert np.max(np.abs(host(U.so3_scale(Rd, 0.37)) - O.so3_scale(R, np.full(n, np.float32(0.37))))) < 3e-6
+    for ta in (False, True):
+        for tb in (False, True):
+            want = (np.swapaxes(R, -1, -2) if ta else R).astype(np.float64) @ (np.swapaxes(R2, -1, -2) if tb else R2).astype(np.float64)
+            assert np.max(np.abs(host(U.compose(Rd, R2d, ta, tb)) - want)) < 1e-6
+    one = dev(R2[0], cuda_device)
+    assert np.max(np.abs(host(U.compose(one, Rd)) - R2[0].astype(np.float64) @ R.astype(np.float64))) < 1e-6
+    assert np.max(np.abs(host(U.compose(Rd, one, trans_b=True)) - R.astype(np.float64) @ R2[0].astype(np.float64).T)) < 1e-6
+    q = rng.standard_normal((n, 4)).astype(np.float32)
+    assert np.max(np.abs(host(U.quat_to_rmat(dev(q, cuda_device))) - O.quat_to_rmat(q))) < 1e-6
+    q2 = host(U.rmat_to_quat(Rd))
+    assert np.max(np.abs(O.quat_to_rmat(q2) - R)) < 2e-6 and np.all(q2[:, 0] >= 0)
+    w = rng.uniform(0, 1, (n, 1)).astype(np.float32)
+    lerp_ok = O.rmat_to_aa(np.swapaxes(R, -1, -2).astype(np.float64) @ R2.astype(np.float64))[1][:, 0] < 3.1
+    assert np.max(np.abs(host(U.so3_lerp(Rd, R2d, dev(w, cuda_device))) - O.so3_lerp(R, R2, w))[lerp_ok], initial=0) < 5e-6
+    assert np.max(np.abs(host(U.rmat_dist(Rd, R2d)) - O.rmat_dist(R, R2))) < 5e-6
+
+
+def test_unaligned_views_and_empty(dx, cuda_device):
+    """Pointers that are only 4-byte aligned (a row-offset view) take the scalar path; n = 0 is a no-op."""
+    U = dx.util
+    R, _, _ = rand_rots(1025, 5)
+    big = dev(R, cuda_device)
+    view = big[1:]  # 36-byte offset: not 16-byte aligned
+    assert view.data_ptr() % 16 != 0
+    assert np.max(np.abs(host(dx.ops.log_vec(view)) - host(dx.ops.log_vec(view.clone())))) == 0
+    assert np.max(np.abs(host(U.so3_scale(view, 0.5)) - host(U.so3_scale(view.clone(), 0.5)))) == 0
+    empty = torch.empty(0, 3, 3, device=cuda_device)
+    assert U.log_rmat(empty).shape == (0, 3, 3)
+    assert U.rmat_to_aa(empty)[1].shape == (0, 1)
+    # leading batch dims
+    R4 = big[:1024].reshape(4, 16, 16, 3, 3)
+    assert U.log_rmat(R4).shape == (4, 16, 16, 3, 3)
+    assert torch.equal(U.log_rmat(R4).reshape(-1, 3, 3), U.log_rmat(big[:1024]))
+
+
+def test_log_edge_cases(dx, cuda_device):
+    rng = np.random.default_rng(3)
+    ax = rng.standard_normal((64, 3)); ax /= np.linalg.norm(ax, axis=-1, keepdims=True)
+    Rpi = O.rodrigues(ax, np.full(64, math.pi)).astype(np.float32)
+    Rtiny = O.rodrigues(ax, np.full(64, 1e-5)).astype(np.float32)
+    R = np.concatenate([np.eye(3, dtype=np.float32)[None], Rpi, Rtiny])
+    axis, ang = dx.util.rmat_to_aa(dev(R, cuda_device))
+    axis, ang = host(axis), host(ang)[:, 0]
+    assert ang[0] == 0 and np.array_equal(axis[0], [0, 0, 1])          # Q10: no NaN at the identity
+    assert np.max(np.abs(ang[1:65] - math.pi)) < 1e-6
+    assert np.min(np.abs((axis[1:65] * ax).sum(-1))) > 1 - 1e-6        # Q4: correct axis at exactly pi
+    assert np.max(np.abs(ang[65:] - 1e-5)) < 1e-9
+    nan_in = torch.full((3, 3, 3), float("nan"), device=cuda_device)
+    assert torch.isnan(dx.util.log_rmat(nan_in)).any()                # NaN in -> NaN out, no trap
+
+
+def test_so3_scale_large_scalars(dx, cuda_device):
+    """Schedule scalars reach 20291; the reference loses orthogonality there (Q5),
+    Rodrigues does not.  Accuracy vs fp64 truth degrades only as |s * theta| * 2^-24."""
+    R, _, _ = rand_rots(4096, 17, 3.0)
+    for s in (100.0, 20291.0):
+        out = host(dx.util.so3_scale(dev(R, cuda_device), s))
+        orth = np.max(np.abs(out @ np.swapaxes(out, -1, -2) - np.eye(3)))
+        assert orth < 1e-6
+        th32 = O.rmat_to_aa(R)[1][:, 0].astype(np.float32)
+        want = O.rodrigues(O.rmat_to_aa(R)[0], (np.float32(s) * th32).astype(np.float64))  # same fp32 product s*theta
+        assert np.max(np.abs(out - want)) < 2e-6 * max(1.0, s * 2 ** -24 * 1e3)
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd functions
+# ---------------------------------------------------------------------------------------------
+def test_backward_against_reference_formulas(dx, cuda_device):
+    """Custom backward kernels vs torch autograd through a float64 restatement of the reference ops."""
+    U = dx.util
+    n = 300
+    R, _, _ = rand_rots(n, 23, 2.8)
+    G = np.random.default_rng(1).standard_normal((n, 3, 3)).astype(np.float32)
+
+    def ref_log(r):  # util.py:164-176 in float64 torch
+        a = r - r.transpose(-1, -2)
+        v = torch.stack((a[..., 2, 1], -a[..., 2, 0], a[..., 1, 0]), -1)
+        s = v.norm(dim=-1) / 2
+        c = (torch.einsum("...ii", r) - 1) / 2
+        return (torch.atan2(s, c) / (2 * s))[..., None, None] * a
+
+    r64 = torch.tensor(R, dtype=torch.float64, requires_grad=True)
+    (ref_g,) = torch.autograd.grad((ref_log(r64) * torch.tensor(G, dtype=torch.float64)).sum(), r64)
+    rd = dev(R, cuda_device).requires_grad_(True)
+    (got,) = torch.autograd.grad((U.log_rmat(rd) * dev(G, cuda_device)).sum(), rd)
+    scale = np.abs(ref_g.numpy()).max((-1, -2), keepdims=True)
+    assert np.max(np.abs(host(got) - ref_g.numpy()) / np.maximum(scale, 1.0)) < 2e-5
+
+    # so3_scale: matrix_exp(s * log R), util.py:349-361
+    s = np.random.default_rng(2).uniform(0.1, 1.5, n).astype(np.float32)
+    s64 = torch.tensor(s, dtype=torch.float64, requires_grad=True)
+    out64 = torch.matrix_exp(ref_log(r64) * s64[..., None, None])
+    ref_gr, ref_gs = torch.autograd.grad((out64 * torch.tensor(G, dtype=torch.float64)).sum(), (r64, s64))
+    sd = dev(s, cuda_device).requires_grad_(True)
+    got_r, got_s = torch.autograd.grad((U.so3_scale(rd, sd) * dev(G, cuda_device)).sum(), (rd, sd))
+    assert np.max(np.abs(host(got_s) - ref_gs.numpy())) < 2e-5 * max(1.0, np.abs(ref_gs.numpy()).max())
+    scale = np.abs(ref_gr.numpy()).max((-1, -2), keepdims=True)
+    assert np.max(np.abs(host(got_r) - ref_gr.numpy()) / np.maximum(scale, 1.0)) < 5e-5
+    # shared scalar: gradient is reduced over the batch
+    s0 = torch.tensor(0.7, device=cuda_device, requires_grad=True)
+    (g0,) = torch.autograd.grad((U.so3_scale(rd.detach(), s0) * dev(G, cuda_device)).sum(), s0)
+    s0_64 = torch.tensor(0.7, dtype=torch.float64, requires_grad=True)
+    (r0,) = torch.autograd.grad((torch.matrix_exp(ref_log(r64.detach()) * s0_64) * torch.tensor(G, dtype=torch.float64)).sum(), s0_64)
+    assert abs(g0.item() - r0.item()) < 1e-3 * max(1.0, abs(r0.item()))
+
+    # aa_to_rmat: matrix_exp(hat(axis/|axis|) * ang), util.py:195-205 (without the SVD projection)
+    axes = np.random.default_rng(3).standard_normal((n, 3)).astype(np.float32) * 2
+    ang = np.random.default_rng(4).uniform(0.01, 3.0, (n, 1)).astype(np.float32)
+    a64 = torch.tensor(axes, dtype=torch.float64, requires_grad=True)
+    an64 = torch.tensor(ang, dtype=torch.float64, requires_grad=True)
+    nrm = a64 / a64.norm(dim=-1, keepdim=True)
+    K = torch.zeros(n, 3, 3, dtype=torch.float64)
+    K = torch.stack((torch.zeros(n, dtype=torch.float64), -nrm[:, 2], nrm[:, 1], nrm[:, 2], torch.zeros(n, dtype=torch.float64), -nrm[:, 0],
+                     -nrm[:, 1], nrm[:, 0], torch.zeros(n, dtype=torch.float64)), -1).reshape(n, 3, 3)
+    ref_ga, ref_gan = torch.autograd.grad((torch.matrix_exp(K * an64[..., None]) * torch.tensor(G, dtype=torch.float64)).sum(), (a64, an64))
+    ad, and_ = dev(axes, cuda_device).requires_grad_(True), dev(ang, cuda_device).requires_grad_(True)
+    got_a, got_an = torch.autograd.grad((U.aa_to_rmat(ad, and_) * dev(G, cuda_device)).sum(), (ad, and_))
+    assert np.max(np.abs(host(got_a) - ref_ga.numpy())) < 2e-5 * max(1.0, np.abs(ref_ga.numpy()).max())
+    assert np.max(np.abs(host(got_an) - ref_gan.numpy())) < 2e-5 * max(1.0, np.abs(ref_gan.numpy()).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# L1: IGSO(3)
+# ---------------------------------------------------------------------------------------------
+def eset(n, seed, kmax=4.0):
+    rng = np.random.default_rng(seed)
+    eps = np.exp(rng.uniform(math.log(6.4e-3), 0.0, n)).astype(np.float32)
+    k = rng.uniform(0, kmax, n)
+    om = np.minimum(eps * math.sqrt(2.0) * k, 3.0).astype(np.float32)
+    axis = rng.standard_normal((n, 3)); axis /= np.linalg.norm(axis, axis=-1, keepdims=True)
+    R = O.rodrigues(axis, om.astype(np.float64)).astype(np.float32)
+    return R, eps
+
+
+def truth_from_R(R, eps):
+    """fp64 truth evaluated at the angle of the float32 matrix the kernel actually sees."""
+    axis, ang = O.rmat_to_aa(R.astype(np.float64))
+    om, e64 = ang[:, 0], eps.astype(np.float64)
+    ft, gt = O.igso3_series(om, e64)
+    small = (e64 < 0.4) & (om > 3.0 * e64)   # far tail at small eps: fp64 series cancels, closed form is exact to 1e-9
+    ft = np.where(small, O.igso3_closed(om, e64), ft)
+    gt = np.where(small, O.igso3_closed_dlog(om, e64), gt)
+    return om, axis, ft, gt
+
+
+def test_density_against_reference_golden(dx, cuda_device, golden):
+    g = golden("igso3")
+    om = dev(g["omega"], cuda_device)
+    for e, ref in zip(g["eps_list"], g["density"]):
+        d = dx.IsotropicGaussianSO3(torch.tensor(float(e), device=cuda_device), mode="closed")
+        got = host(d._eps_ft(om))
+        # reference: NaN at omega == 0 for eps < 0.167 (Q3) and zeroed beyond 709 eps^2/pi (D5)
+        ok = np.isfinite(ref) & (g["omega"] <= 0.99 * 709.0 * float(e) ** 2 / math.pi)
+        assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(ref[ok], 1e-30)) < 1e-5, e
+        for mode in ("auto", "series"):
+            d2 = dx.IsotropicGaussianSO3(torch.tensor(float(e), device=cuda_device), mode=mode)
+            got2 = host(d2._eps_ft(om))
+            well = ok & (g["omega"] <= 3.5 * float(e))
+            assert np.max(np.abs(got2[well] - ref[well]) / ref[well]) < 1e-5, (e, mode)
+
+
+def test_log_prob_and_grad_against_reference_golden(dx, cuda_device, golden):
+    g = golden("igso3")
+    for k, e in enumerate(g["eps_list"]):
+        d = dx.IsotropicGaussianSO3(torch.tensor(float(e), device=cuda_device), mode="closed")
+        R = dev(g["lp_R"][k], cuda_device).requires_grad_(True)
+        lp = d.log_prob(R)
+        assert lp.shape == (96, 1)
+        ref = g["logp"][k]
+        assert np.max(np.abs(host(lp) - ref)) < 2e-5 + 1e-6 * np.max(np.abs(ref))
+        (gr,) = torch.autograd.grad(lp.sum(), R)
+        refg = g["logp_grad"][k]
+        scale = np.max(np.abs(refg), axis=(-1, -2), keepdims=True)
+        # autograd through the reference's fp32 log_rmat carries ~1e-3 relative noise at small angles
+        assert np.max(np.abs(host(gr) - refg) / scale) < 3e-3, e
+        # and tightly against the fp64 ambient gradient
+        R64 = g["lp_R"][k].astype(np.float64)
+        gd = O.igso3_closed_dlog(O.rmat_to_aa(R64)[1][:, 0], float(e))
+        amb = O.log_prob_ambient_grad(R64, gd)
+        assert np.max(np.abs(host(gr) - amb) / np.max(np.abs(amb), axis=(-1, -2), keepdims=True)) < 2e-4
+
+
+@pytest.mark.parametrize("mode", ["auto", "closed"])
+def test_logp_score_eset(dx, cuda_device, mode):
+    """North-star gate: density and score <= 1e-5 relative vs the fp64 series on the E-set."""
+    n = 1 << 16
+    R, eps = eset(n, 11)
+    om, axis, ft, gt = truth_from_R(R, eps)
+    d = dx.IsotropicGaussianSO3(dev(eps, cuda_device), mode=mode)
+    logp, score = d.log_prob_and_score(dev(R, cuda_device))
+    logp, score = host(logp)[:, 0], host(score)
+    assert np.max(np.abs(np.exp(logp - np.log(ft)) - 1)) < 1e-5
+    want = gt[:, None] * axis
+    err = np.linalg.norm(score - want, axis=-1) / np.maximum(np.abs(gt), 1e-30)
+    # the direction of a rotation by omega is only defined to ~6e-8/omega in fp32: exclude omega < 1e-2
+    ok = om > 1e-2
+    assert np.max(err[ok]) < 1e-5
+    g_kernel = (score * axis).sum(-1)
+    assert np.max((np.abs(g_kernel - gt) / np.maximum(np.abs(gt), 1e-30))[om > 1e-4]) < 1e-5
+
+
+def test_logp_score_series_L2000(dx, cuda_device):
+    """The L = 2000 fp32 series itself (the benchmarked kernel): 1e-5 where the alternating sum is
+    well conditioned (omega <= 3.5 eps), bounded growth with the cancellation beyond."""
+    n = 1 << 15
+    R, eps = eset(n, 13)
+    om, axis, ft, gt = truth_from_R(R, eps)
+    k = om / (math.sqrt(2.0) * eps)
+    d = dx.IsotropicGaussianSO3(dev(eps, cuda_device), mode="series", series_terms=2000)
+    logp, score = d.log_prob_and_score(dev(R, cuda_device))
+    ef = np.abs(np.exp(host(logp)[:, 0] - np.log(ft)) - 1)
+    g_kernel = (host(score) * axis).sum(-1)
+    eg = np.abs(g_kernel - gt) / np.maximum(np.abs(gt), 1e-30)
+    well = k <= 2.5
+    assert ef[well].max() < 1e-5 and eg[well & (om > 1e-4)].max() < 1e-5
+    assert ef[k <= 3.2].max() < 1e-4 and ef.max() < 2e-3
+    # adaptive truncation is bit-identical (skipped weights are exactly zero)
+    d2 = dx.IsotropicGaussianSO3(dev(eps, cuda_device), mode="series_adaptive", series_terms=2000)
+    logp2, score2 = d2.log_prob_and_score(dev(R, cuda_device))
+    assert torch.equal(logp, logp2) and torch.equal(score, score2)
+
+
+def test_scalar_vs_per_row_eps(dx, cuda_device):
+    R, _ = eset(5000, 19)
+    Rd = dev(R, cuda_device)
+    e = torch.tensor(0.3, device=cuda_device)
+    a = dx.IsotropicGaussianSO3(e).log_prob(Rd)
+    b = dx.IsotropicGaussianSO3(e.expand(5000).contiguous()).log_prob(Rd)
+    assert torch.equal(a, b)
+
+
+def test_cdf_table_against_reference_golden(dx, cuda_device, golden):
+    g = golden("igso3")
+    loc, haar, trap_loc = dx.ops.cdf_grid(cuda_device)
+    assert np.array_equal(loc.cpu().numpy(), g["grid_loc"]) and np.array_equal(haar.cpu().numpy(), g["grid_haar"])
+    d = dx.IsotropicGaussianSO3(dev(g["eps_list"], cuda_device))
+    assert d.trap.shape == (999, 5) and d.trap_loc.shape == (999, 1)
+    assert np.max(np.abs(d.table.cpu().numpy() - g["trap"])) <= 2.4e-7   # <= 2 ulp at 1.0
+    assert np.array_equal(d.trap_loc[:, 0].cpu().numpy(), g["trap_loc"])
+    ds = dx.IsotropicGaussianSO3(torch.tensor(0.5, device=cuda_device))
+    assert ds.trap.shape == (999, 1)
+    # reference quirk D5 at the schedule's smallest eps, and the batched (999, B) constructor
+    dq = dx.IsotropicGaussianSO3(torch.tensor(float(g["q_eps"]), device=cuda_device), reference_quirks=True)
+    assert np.max(np.abs(dq.table.cpu().numpy()[0] - g["q_trap"])) <= 2.4e-7
+    db = dx.IsotropicGaussianSO3(dev(g["b_eps"], cuda_device), reference_quirks=True)
+    assert np.max(np.abs(db.trap.cpu().numpy() - g["b_trap"])) <= 2.4e-7
+    # the oracle's table from the same grid
+    want, _ = O.igso3_cdf_table(g["eps_list"], g["grid_loc"], g["grid_haar"])
+    assert np.max(np.abs(d.table.cpu().numpy() - want)) <= 2.4e-7
+    # monotone, ends at exactly 1
+    tb = d.table.cpu().numpy()
+    assert np.all(np.diff(tb, axis=1) >= 0) and np.all(tb[:, -1] == 1.0)
+
+
+def test_sampler_given_reference_draws(dx, cuda_device, golden):
+    """Same (axes, u) as the reference's CPU generator produced -> same rotations (1e-5 rad)."""
+    g = golden("igso3")
+    for k, e in enumerate(g["eps_list"]):
+        d = dx.IsotropicGaussianSO3(torch.tensor(float(e), device=cuda_device))
+        R, ang = d.sample((256,), u=dev(g["u_draw"][k], cuda_device), axes=dev(g["axes_draw"][k], cuda_device), return_angle=True)
+        assert R.shape == (256, 3, 3)
+        ref_ang = O.rmat_to_aa(g["samples"][k])[1][:, 0]
+        assert np.max(np.abs(host(ang) - ref_ang)) < 1e-5, e
+        assert np.max(np.abs(host(R) - g["samples"][k])) < 5e-6
+    # batched eps: row 0 matches the reference, other rows match the corrected oracle (Q1)
+    d = dx.IsotropicGaussianSO3(dev(g["b_eps"], cuda_device), reference_quirks=True)
+    R, ang = d.sample(u=dev(g["b_u"], cuda_device), axes=dev(g["b_axes"], cuda_device), return_angle=True)
+    assert R.shape == (6, 3, 3)
+    assert np.max(np.abs(host(R)[0] - g["b_samples"][0])) < 5e-6
+    want = O.igso3_angle_from_uniform(g["b_u"], g["b_trap"].T, g["trap_loc"])
+    assert np.max(np.abs(host(ang) - want)) < 1e-6
+    # mean is applied on the left (distributions.py:50)
+    m, _, _ = rand_rots(1, 99)
+    dm = dx.IsotropicGaussianSO3(torch.tensor(0.2, device=cuda_device), mean=dev(m[0], cuda_device))
+    Rm = dm.sample((256,), u=dev(g["u_draw"][2], cuda_device), axes=dev(g["axes_draw"][2], cuda_device))
+    assert np.max(np.abs(host(Rm) - m[0].astype(np.float64) @ g["samples"][2].astype(np.float64))) < 5e-6
+
+
+def test_sampler_device_rng_statistics(dx, cuda_device):
+    """Device Philox path: reproducible under manual_seed, sharding invariant, and distributed as
+    IGSO3(eps): angle CDF matches the table (KS), axes uniform on the sphere."""
+    n = 1 << 18
+    eps = 0.25
+    d = dx.IsotropicGaussianSO3(torch.tensor(eps, device=cuda_device))
+    dx.manual_seed(7)
+    R1, a1 = d.sample((n,), return_angle=True)
+    dx.manual_seed(7)
+    R2, a2 = d.sample((n,), return_angle=True)
+    assert torch.equal(R1, R2)
+    R3 = d.sample((n,))
+    assert not torch.equal(R1, R3)                      # the stream advances between calls
+    # two half-size shards with global row offsets reproduce the full batch
+    dx.manual_seed(7)
+    Ra = d.sample((n // 2,), row_offset=0)
+    dx.ops.rng.offset = 0
+    Rb = d.sample((n // 2,), row_offset=n // 2)
+    assert torch.equal(torch.cat([Ra, Rb]), R1)
+    ang = np.sort(host(a1))
+    tb = d.table[0].cpu().numpy().astype(np.float64)
+    loc = d.trap_loc[:, 0].cpu().numpy().astype(np.float64)
+    cdf_at = np.interp(ang, loc, tb)
+    ks = np.max(np.abs(cdf_at - (np.arange(n) + 0.5) / n))
+    assert ks < 2.0 / math.sqrt(n)
+    axis = host(dx.util.rmat_to_aa(R1)[0])
+    assert np.max(np.abs(axis.mean(0))) < 5.0 / math.sqrt(n)
+    out = host(R1)
+    assert np.max(np.abs(out @ np.swapaxes(out, -1, -2) - np.eye(3))) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# L2: SO3Diffusion
+# ---------------------------------------------------------------------------------------------
+def test_schedule_and_state_dict(dx, cuda_device, golden):
+    s = golden("schedule")
+    p = dx.SO3Diffusion(None)
+    sd = p.state_dict()
+    assert set(sd.keys()) == set(s.keys())
+    for k in s:
+        assert np.array_equal(sd[k].numpy(), s[k]), k
+    p.load_state_dict({k: torch.tensor(v) for k, v in s.items()})
+
+
+def test_diffusion_algebra_against_reference_golden(dx, cuda_device, golden):
+    g = golden("diffusion")
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    d = lambda k: dev(g[k], cuda_device)
+    t = torch.tensor(g["t"], device=cuda_device)
+    x_t = p.q_sample(d("x0"), t, noise=d("noise"))
+    assert np.max(np.abs(host(x_t) - g["x_t"])) < 5e-6
+    tgt = dx.ops.log_vec(d("noise")) / dev(g["eps_t"], cuda_device)[:, None]
+    assert np.max(np.abs(host(tgt) - g["target"]) / np.maximum(np.abs(g["target"]), 1.0)) < 2e-5
+    tr = torch.tensor(g["t_rev"], device=cuda_device)
+    ok = O.rmat_to_aa(g["x_t"])[1][:, 0] < 3.0  # the reference's fp32 log degrades towards pi
+    xr = p.predict_start_from_noise(d("x_t"), tr, d("pred"))
+    assert np.max(np.abs(host(xr) - g["x_recon"])[ok]) < 2e-5
+    ok2 = ok & (O.rmat_to_aa(g["x_recon"])[1][:, 0] < 3.0)
+    pm, pv, plv = p.q_posterior(d("x_recon"), d("x_t"), tr)
+    assert np.max(np.abs(host(pm) - g["post_mean"])[ok2]) < 2e-5
+    assert np.array_equal(pv.cpu().numpy()[:, 0] if pv.dim() > 1 else pv.cpu().numpy(), g["post_var"])
+    p.denoise_fn = lambda x, tt: d("pred")
+    mm, _, _ = p.p_mean_variance(d("x_t"), tr)
+    assert np.max(np.abs(host(mm) - g["mean_pm"])[ok2]) < 3e-5
+    # and tightly against the fp64 oracle everywhere (including near pi and large schedule scalars)
+    s = golden("schedule")
+    want = O.p_sample_mean(g["x_t"], g["pred"], s["sqrt_recip_alphas_cumprod"][g["t_rev"]], s["sqrt_recipm1_alphas_cumprod"][g["t_rev"]],
+                           s["posterior_mean_coef1"][g["t_rev"]], s["posterior_mean_coef2"][g["t_rev"]])
+    assert np.max(O.geodesic_angle(host(mm), want)) < 2e-5
+
+
+def test_p_sample_shared_t_against_reference_golden(dx, cuda_device, golden):
+    """Full reverse step at shared t with the reference's own draws injected: the fused kernel's
+    mean composed with the sampler given (u, axes) equals the reference's p_sample output."""
+    g = golden("diffusion")
+    p = dx.SO3Diffusion(None, reference_quirks=True).to(cuda_device)
+    d = lambda k: dev(g[k], cuda_device)
+    p.denoise_fn = lambda x, tt: d("pred")
+    _, post, _ = p.tables()
+    for k, step in enumerate(g["ps_steps"]):
+        t1 = torch.tensor([int(step)], device=cuda_device)
+        mean, _, _ = p.p_mean_variance(d("x_t"), t1)
+        if step == 0:
+            out = mean
+            assert torch.equal(p.p_sample(d("x_t"), t1), mean)          # no noise at t == 0
+            assert torch.equal(p.p_sample(d("x_t"), t1.expand(128)), mean)
+        else:
+            noise = dx.ops.igso3_sample(post, (128,), row=int(step), u=dev(g["ps_u"][k], cuda_device), axes=dev(g["ps_axes"][k], cuda_device))
+            out = dx.util.compose(mean, noise)
+        ref = g["ps_out"][k]
+        ok = (O.rmat_to_aa(g["x_t"])[1][:, 0] < 3.0)
+        if step > 600:
+            continue  # reference so3_scale(x, 1/sqrt(abar)) is itself off by > 1e-3 there (Q5); oracle test covers it
+        assert np.max(O.geodesic_angle(host(out), ref)[ok]) < 5e-5, step
+
+
+def test_fused_q_sample_consistency(dx, cuda_device):
+    """The fused training kernel: x_t = so3_scale(x0, a_t) @ noise with noise ~ IGSO3(eps_t), and
+    target = vee(log noise)/eps_t, checked against the oracle applied to the kernel's own noise."""
+    n = 20000
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    x0, _, _ = rand_rots(n, 31)
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 1000, n)
+    t[:4] = [0, 1, 998, 999]
+    dx.manual_seed(3)
+    out = p.noise_and_target(dev(x0, cuda_device), torch.tensor(t, device=cuda_device), want_noise=True, want_score=True)
+    noise, x_t, target, score = host(out["noise"]), host(out["x_t"]), host(out["target"]), host(out["score"])
+    s = O.schedule_buffers(1000)
+    want_xt = O.q_sample(x0, s["sqrt_alphas_cumprod"][t], noise)
+    assert np.max(O.geodesic_angle(x_t, want_xt)) < 3e-6
+    eps = s["sqrt_one_minus_alphas_cumprod"][t].astype(np.float64)
+    want_tgt = O.skewvec_target(noise, eps)
+    assert np.max(np.abs(target - want_tgt) / np.maximum(np.abs(want_tgt), 1.0)) < 2e-5
+    # score of the noise under IGSO3(eps_t): g(omega) * axis
+    axis, ang = O.rmat_to_aa(noise)
+    ft, gt = O.igso3_series(ang[:, 0], eps)
+    well = (ang[:, 0] <= 3.0 * eps) & (ang[:, 0] > 1e-3)
+    err = np.linalg.norm(score - gt[:, None] * axis, axis=-1) / np.abs(gt)
+    assert np.max(err[well]) < 2e-4   # axis recovered from an fp32 matrix with tiny angle: 6e-8/omega
+    # reproducible, and identical without the optional outputs
+    dx.manual_seed(3)
+    out2 = p.noise_and_target(dev(x0, cuda_device), torch.tensor(t, device=cuda_device))
+    assert torch.equal(out2["x_t"], out["x_t"]) and torch.equal(out2["target"], out["target"])
+    # angle distribution at a fixed t follows the forward table
+    tt = torch.full((1 << 17,), 300, device=cuda_device)
+    xx = torch.eye(3, device=cuda_device).expand(1 << 17, 3, 3).contiguous()
+    o3 = p.noise_and_target(xx, tt, want_noise=True)
+    ang = np.sort(O.rmat_to_aa(host(o3["noise"]))[1][:, 0])
+    fwd = p.tables()[0][300].cpu().numpy().astype(np.float64)
+    loc = dx.ops.cdf_grid(cuda_device)[2].cpu().numpy().astype(np.float64)
+    ks = np.max(np.abs(np.interp(ang, loc, fwd) - (np.arange(ang.size) + 0.5) / ang.size))
+    assert ks < 2.5 / math.sqrt(ang.size)
+
+
+def test_fused_p_sample_against_oracle(dx, cuda_device):
+    """Fused reverse step with per-row t vs the oracle mean; the noise factor is recovered as
+    mean^T out and must be a rotation whose angle follows the posterior table."""
+    n = 8192
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    s = O.schedule_buffers(1000)
+    x, _, _ = rand_rots(n, 41, 3.0)
+    rng = np.random.default_rng(6)
+    pred = (rng.standard_normal((n, 3)) * 0.5).astype(np.float32)
+    t = rng.integers(0, 400, n)
+    t[:8] = 0
+    p.denoise_fn = lambda xx, tt: dev(pred, cuda_device)
+    td = torch.tensor(t, device=cuda_device)
+    mean = host(p.p_mean_variance(dev(x, cuda_device), td)[0])
+    want = O.p_sample_mean(x, pred, s["sqrt_recip_alphas_cumprod"][t], s["sqrt_recipm1_alphas_cumprod"][t],
+                           s["posterior_mean_coef1"][t], s["posterior_mean_coef2"][t])
+    assert np.max(O.geodesic_angle(mean, want)) < 1e-5
+    dx.manual_seed(11)
+    out = host(p.p_sample(dev(x, cuda_device), td))
+    assert np.max(np.abs(out[:8] - mean[:8])) == 0           # t == 0 rows: mean only
+    nz = np.swapaxes(mean, -1, -2) @ out
+    assert np.max(np.abs(nz @ np.swapaxes(nz, -1, -2) - np.eye(3))) < 5e-6
+    # shared-t fast path equals the per-row path
+    t5 = torch.full((n,), 250, device=cuda_device)
+    dx.manual_seed(12)
+    a = p.p_sample(dev(x, cuda_device), t5)
+    dx.manual_seed(12)
+    b = p.p_sample(dev(x, cuda_device), t5[:1])
+    assert torch.equal(a, b)
+    ang = np.sort(O.rmat_to_aa(np.swapaxes(host(p.p_mean_variance(dev(x, cuda_device), t5)[0]), -1, -2) @ host(a))[1][:, 0])
+    post = p.tables()[1][250].cpu().numpy().astype(np.float64)
+    loc = dx.ops.cdf_grid(cuda_device)[2].cpu().numpy().astype(np.float64)
+    ks = np.max(np.abs(np.interp(ang, loc, post) - (np.arange(n) + 0.5) / n))
+    assert ks < 2.5 / math.sqrt(n)
+
+
+def test_training_step_and_sampling_loop(dx, cuda_device):
+    """config[0]: the toy so3_train.py setup (two-point target +-90 deg about z, batch 256) steps
+    through SO3Diffusion.forward + backward + Adam, and a short reverse chain stays on SO(3)."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(10, 64), torch.nn.SiLU(), torch.nn.Linear(64, 3)).to(cuda_device)
+
+    def denoise(x, t):
+        return net(torch.cat([x.flatten(-2), (t.float() / 1000)[:, None]], -1))
+
+    proc = dx.SO3Diffusion(denoise, timesteps=100).to(cuda_device)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    z90 = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], device=cuda_device)
+    data = torch.stack([z90, z90.t()]).repeat(128, 1, 1)
+    losses = []
+    for _ in range(30):
+        loss = proc(data)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(math.isfinite(v) for v in losses)
+    assert np.mean(losses[-5:]) < np.mean(losses[:5])
+    x = proc.p_sample_loop((64, 3, 3))
+    assert x.shape == (64, 3, 3) and torch.isfinite(x).all()
+    xx = host(x)
+    assert np.max(np.abs(xx @ np.swapaxes(xx, -1, -2) - np.eye(3))) < 1e-4
+    # prevstep loss (diffusion.py:358-365) is differentiable through rmat_dist
+    proc2 = dx.SO3Diffusion(lambda x, t: dx.util.exp_vec(denoise(x, t)), timesteps=100, loss_type="prevstep").to(cuda_device)
+    l2 = proc2(data)
+    l2.backward()
+    assert math.isfinite(l2.item())
+    with pytest.raises(RuntimeError):
+        dx.SO3Diffusion(denoise, timesteps=100, loss_type="bogus").to(cuda_device)(data)
+
+
+def test_error_behaviour(dx, cuda_device):
+    with pytest.raises(RuntimeError):
+        dx.util.log_rmat(torch.eye(3)[None])            # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        dx.util.log_rmat(torch.eye(3, device=cuda_device, dtype=torch.float64)[None])
+    with pytest.raises(ValueError):
+        dx.util.log_rmat(torch.zeros(4, 3, device=cuda_device))
+    with pytest.raises(RuntimeError):
+        dx.ops.igso3_logp_score(torch.eye(3, device=cuda_device)[None], 0.5, mode="series", L=5000)  # C ABI argument error
+
+
+def test_full_size_properties(dx, cuda_device):
+    """BASELINE config[1] size (2^24 rotations): size-independent properties instead of a CPU oracle:
+    exp(log R) == R, scale(scale(R, s), 1/s) == R, quaternion round trip, score direction == axis."""
+    n = 1 << 24
+    torch.manual_seed(1)
+    R = dx.util.quat_to_rmat(torch.randn(n, 4, device=cuda_device))
+    axis, ang = dx.util.rmat_to_aa(R)
+    back = dx.util.aa_to_rmat(axis, ang)
+    assert (back - R).abs().max().item() < 3e-6
+    far = ang[:, 0] < 3.0
+    half = dx.util.so3_scale(dx.util.so3_scale(R, 0.5), 2.0)
+    assert (half - R)[far].abs().max().item() < 5e-6
+    assert (dx.util.quat_to_rmat(dx.util.rmat_to_quat(R)) - R).abs().max().item() < 3e-6
+    eps = torch.full((n,), 0.8, device=cuda_device)
+    logp, score = dx.IsotropicGaussianSO3(eps).log_prob_and_score(R)
+    g = (score * axis).sum(-1)
+    assert torch.isfinite(logp).all() and (g <= 1e-6).all()   # density decreases with the angle
+    assert ((score - g[:, None] * axis).norm(dim=-1)).max().item() < 1e-6 * g.abs().max().item()
