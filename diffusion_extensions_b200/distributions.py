@@ -51,7 +51,7 @@ class IsotropicGaussianSO3(Distribution):
             raise RuntimeError("IsotropicGaussianSO3: eps must live on a CUDA device; this package has no CPU path")
         self.eps = eps.float() if eps.dtype != torch.float32 else eps
         self._mean = None if mean is None else mean.to(self.eps)
-        self.mode = mode
+        self.eval_mode = mode
         self.series_terms = int(series_terms)
         self.reference_quirks = bool(reference_quirks)
         self._table = None  # (E_flat, 999), built on first use
@@ -100,26 +100,26 @@ class IsotropicGaussianSO3(Distribution):
     def _eps_ft(self, t: torch.Tensor) -> torch.Tensor:
         t = t.to(device=self.eps.device, dtype=torch.float32)
         if self.eps.numel() == 1:
-            return ops.igso3_density(t.contiguous(), self.eps, mode=self.mode, L=self.series_terms)
+            return ops.igso3_density(t.contiguous(), self.eps, mode=self.eval_mode, L=self.series_terms)
         shape = torch.broadcast_shapes(t.shape, self.eps.shape)
-        return ops.igso3_density(t.expand(shape).contiguous(), self.eps.expand(shape).contiguous(), mode=self.mode, L=self.series_terms)
+        return ops.igso3_density(t.expand(shape).contiguous(), self.eps.expand(shape).contiguous(), mode=self.eval_mode, L=self.series_terms)
 
     def log_prob(self, rotations):
         """distributions.py:74-77: log f_eps(angle(R)), shape (..., 1).  Differentiable w.r.t. rotations."""
         if torch.is_grad_enabled() and rotations.requires_grad:
-            return _LogProb.apply(rotations, self.eps, self.mode, self.series_terms)[..., None]
-        logp, _, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.mode, L=self.series_terms, want_score=False)
+            return _LogProb.apply(rotations, self.eps, self.eval_mode, self.series_terms)[..., None]
+        logp, _, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.eval_mode, L=self.series_terms, want_score=False)
         return logp[..., None]
 
     @torch.no_grad()
     def score(self, rotations):
         """(d log f / d omega) * axis, shape (..., 3): the Riemannian score in the body frame."""
-        _, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.mode, L=self.series_terms, want_score=True)
+        _, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.eval_mode, L=self.series_terms, want_score=True)
         return score
 
     @torch.no_grad()
     def log_prob_and_score(self, rotations):
-        logp, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.mode, L=self.series_terms, want_score=True)
+        logp, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.eval_mode, L=self.series_terms, want_score=True)
         return logp[..., None], score
 
 

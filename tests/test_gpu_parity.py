@@ -141,10 +141,11 @@ def test_so3_scale_large_scalars(dx, cuda_device):
     for s in (100.0, 20291.0):
         out = host(dx.util.so3_scale(dev(R, cuda_device), s))
         orth = np.max(np.abs(out @ np.swapaxes(out, -1, -2) - np.eye(3)))
-        assert orth < 1e-6
+        assert orth < 2e-6
         th32 = O.rmat_to_aa(R)[1][:, 0].astype(np.float32)
         want = O.rodrigues(O.rmat_to_aa(R)[0], (np.float32(s) * th32).astype(np.float64))  # same fp32 product s*theta
-        assert np.max(np.abs(out - want)) < 2e-6 * max(1.0, s * 2 ** -24 * 1e3)
+        # the kernel's fp32 theta and the oracle's differ by an ulp or two (2.4e-7 at pi), amplified by s
+        assert np.max(np.abs(out - want)) < 2e-6 + 6e-7 * s
 
 
 # ---------------------------------------------------------------------------------------------
@@ -554,7 +555,7 @@ def test_training_step_and_sampling_loop(dx, cuda_device):
         losses.append(loss.item())
     assert all(math.isfinite(v) for v in losses)
     assert np.mean(losses[-5:]) < np.mean(losses[:5])
-    x = proc.p_sample_loop((64, 3, 3))
+    x = proc.p_sample_loop((64,))  # batch shape, like bingham_test.py:25
     assert x.shape == (64, 3, 3) and torch.isfinite(x).all()
     xx = host(x)
     assert np.max(np.abs(xx @ np.swapaxes(xx, -1, -2) - np.eye(3))) < 1e-4
