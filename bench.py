@@ -33,12 +33,16 @@ METRIC = "igso3_score_evals_per_sec"
 UNIT = "evals/s"
 SEED = 1234
 
-# ---- algorithmic work of the series kernel ---------------------------------
-# per term: 13 FP32 instructions (4 rotate, 1 m+=1, 1 chi, 1 D, 2 exponent, 2 weight, 2 accumulate)
-# of which 7 are FMAs, plus 1 MUFU.EX2  ->  20 flop + 1 MUFU, 14 issue slots per term per lane.
-FP32_INSTR_PER_TERM = 13
+# ---- work of the series kernel per term ------------------------------------
+# Executed: 7 FP32 instructions (1 FMUL, 4 FFMA, 2 FADD = 11 flop) + 1 MUFU.EX2 + 1 uniform constant load
+# (LDCU.64) = 9 issue slots.  SURVEY 8(d) fixed the algorithmic unit for recurrence-based variants at
+# >= 10 FP32 lane-instructions per term (bound 1.86e9 evals/s/GPU at 128 lanes/clk/SM); `roofline.frac` uses
+# that unit, and the executed mix is reported next to it.
+ALGO_LANE_INSTR_PER_TERM = 10
+FP32_INSTR_PER_TERM = 7
 MUFU_PER_TERM = 1
-FLOP_PER_TERM = 20
+UNIFORM_PER_TERM = 1
+FLOP_PER_TERM = 11
 BYTES_PER_EVAL = 56          # 36 R + 4 eps in, 4 logp + 12 score out
 BYTES_PER_PARTICLE_STEP = 84 # 36 x_t + 12 pred in, 36 out
 BYTES_PER_QSAMPLE = 92       # 36 x0 + 8 t in, 36 x_t + 12 target out
@@ -311,18 +315,26 @@ def main():
     if rank == 0:
         sm = torch.cuda.get_device_properties(device).multi_processor_count
         ghz = pk["sm_max_mhz"] * 1e-3
+        issue_peak = sm * 128 * ghz * 1e9                      # FP32 lane-instructions/s (= 4 warp-instr/clk/SM)
+        mufu_peak = sm * 16 * ghz * 1e9
         fp32_peak_tflops = sm * 128 * 2 * ghz * 1e-3          # FFMA = 2 flop/lane/clk
-        issue_peak = sm * 128 * ghz * 1e9                      # lane-instructions/s (4 warp-instr/clk/SM)
-        ach_tflops = per_gpu * L * FLOP_PER_TERM * 1e-12
+        ach = per_gpu * L * ALGO_LANE_INSTR_PER_TERM
+        # time per term implied by each resource for the executed mix, in SMSP clocks per warp-term:
+        #   issue 9 slots; XU pipe 8 (MUFU at 4 lanes/clk/SMSP); FP32 operand reads 8.8 (measured per-form costs:
+        #   1-register 1.0, 2-register 1.09, 3-register 1.5 clk, profiles/microbench/pipes.cu)
+        clk_per_term = sm * 4 * ghz * 1e9 * 32 / (per_gpu * L)
         roofline = {
-            "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": ach_tflops / fp32_peak_tflops,
+            "bound": "fp32", "achieved": ach * 1e-12, "peak": issue_peak * 1e-12, "unit": "T lane-instr/s", "frac": ach / issue_peak,
             "traffic": None,
-            "issue_slot_frac": per_gpu * L * (FP32_INSTR_PER_TERM + MUFU_PER_TERM) / issue_peak,
-            "mufu_frac": per_gpu * L * MUFU_PER_TERM / (sm * 16 * ghz * 1e9),
+            "definition": "SURVEY 8(d): FP32-issue bound with 10 lane-instr/term (1.86e9 evals/s/GPU); executed mix below",
+            "executed_per_term": {"fp32_instr": FP32_INSTR_PER_TERM, "mufu": MUFU_PER_TERM, "uniform_ldc": UNIFORM_PER_TERM, "flop": FLOP_PER_TERM},
+            "clk_per_warp_term": clk_per_term, "clk_floor_issue": 9.0, "clk_floor_xu": 8.0, "clk_floor_fp32_operands": 8.8,
+            "frac_of_executed_mix_floor": 9.0 / clk_per_term,
+            "executed_tflops": per_gpu * L * FLOP_PER_TERM * 1e-12, "fp32_peak_tflops": fp32_peak_tflops,
+            "mufu_frac": per_gpu * L * MUFU_PER_TERM / mufu_peak,
+            "naive_3mufu_roofline_evals_per_s": mufu_peak / (3 * L), "frac_of_naive_3mufu_roofline": per_gpu / (mufu_peak / (3 * L)),
             "hbm_gbs": per_gpu * BYTES_PER_EVAL / 1e9,
-            "naive_3mufu_roofline_evals_per_s": sm * 16 * ghz * 1e9 / (3 * L),
             "peak_source": f"derived: {sm} SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz ({pk['source']}); HBM {pk['hbm_gbs']} GB/s",
-            "work_per_term": "13 FP32 instr (7 FMA) + 1 MUFU.EX2 = 20 flop, 14 issue slots",
         }
         line = {
             "metric": METRIC, "value": evals_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -8,7 +8,8 @@
 //     row from shared memory at a stride of 9 (or 3) words -- odd, hence bank-conflict free;
 //   * grids are persistent: min(#tiles, 148 * CTAs/SM) CTAs striding over the tiles;
 //   * HBM-bound kernels use streaming loads/stores (ld.global.cs / st.global.cs): nothing is re-read;
-//   * the series evaluator is FP32-issue bound (13 FP32 + 1 MUFU per term, see so3d_math.cuh).
+//   * the series evaluator is bound by FP32 operand bandwidth / MUFU / issue at once (7 FP32 + 1 MUFU.EX2 +
+//     1 uniform constant load per term, see so3d_math.cuh).
 // No library calls, no tensor cores (nothing here is GEMM shaped).
 #include <cuda_runtime.h>
 #include <stdio.h>

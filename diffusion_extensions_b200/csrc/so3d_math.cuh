@@ -489,75 +489,107 @@ SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out)
 }
 
 // ------------------------------------------------------------------------------------------------
-// IGSO(3) truncated series, character form (SURVEY A.1 rewritten with chi_l = sin((l+1/2)w)/sin(w/2)
-//   = 1 + 2 sum_{m<=l} cos(m w), which has no 0/0 at w = 0 and no cancellation against cot(w/2)):
-//     f  = 2 sum_l (l+1/2) e_l chi_l,      e_l = exp(-l(l+1) eps^2)
-//     f' = -4 sum_l (l+1/2) e_l D_l,       D_l = sum_{m<=l} m sin(m w)
-// Per term (m -> m+1), all fp32:  4 ops rotate (sin, cos)(m w) by w, 1 m += 1, 1 chi += 2c,
-// 1 D += m s, 2 ops + 1 MUFU.EX2 for e_m = 2^(m(m+1) * (-eps^2 log2 e)), 2 ops p = (m+1/2) e,
-// 2 FMAs into the two accumulators: 13 FP32 + 1 MUFU.  m(m+1) is exact in fp32 for m < 2896.
-// Every kAnchor terms (sin, cos) is re-seeded from an exact-product sincos so the rotation
-// recurrence never drifts more than ~kAnchor ulps (measured: oracle/proto_series_fp32.py).
+// IGSO(3) truncated series in character form,
+//     f(w) = 2 F(w),   F = sum_{l<L} A_l chi_l(w),   A_l = (l+1/2) exp(-l(l+1) eps^2),
+//     chi_l(w) = sin((l+1/2)w)/sin(w/2) = 1 + 2 sum_{m<=l} cos(m w)   (no 0/0 at w = 0),
+// summed by Clenshaw's backward recurrence in Reinsch's difference form.  chi_l obeys
+// chi_{l+1} = (2 - kappa) chi_l - chi_{l-1}, kappa = 4 sin^2(w/2), chi_0 = 1, chi_{-1} = -1, so with
+//     d_l = A_l - kappa b_{l+1} + d_{l+1},        b_l = b_{l+1} + d_l          (b_L = d_L = 0)
+// the sum is F = b_0 + b_1, and differentiating the recurrence w.r.t. w (kappa' = 2 sin w) gives
+//     d'_l = -kappa' b_{l+1} - kappa b'_{l+1} + d'_{l+1},   b'_l = b'_{l+1} + d'_l,   F' = b'_0 + b'_1,
+// hence d log f / dw = F'/F with no cancellation against cot(w/2) and nothing to special-case at w = 0.
+// No sin/cos of (l w) is ever formed: the previous design rotated (sin, cos)(m w) term by term and
+// re-anchored it with an exact-product sincos every 32 terms (13 FP32 + 1 MUFU per term); this form
+// needs 8 FP32 + 1 MUFU.EX2 per term, no anchors, and is MORE accurate (measured on the E-set,
+// oracle/proto_series_fp32.py: max rel err of f 1.5e-6 vs 3.4e-6 for w <= 3.5 eps; the plain
+// Clenshaw form with K = 2 cos w is 3e-4 there because of the rounding of K, hence Reinsch).
+// Per term, all fp32:  x = mm * cexp;  A = ex2(x) * mh;  t = A + d;  d = fma(-kappa, b, t);
+//   u = fma(-kappa', b, d');  d' = fma(-kappa, b', u);  b += d;  b' += d'.
+// m(m+1) is exact in fp32 for m < 2896.
+//
+// The row-invariant factors {m + 1/2, m(m+1)} come from a constant-memory table and reach the FP32 pipe
+// as uniform-register operands (LDCU + FMUL R, R, UR).  Measured on B200 (profiles/microbench/pipes.cu)
+// FP32 instruction throughput is set by vector-register operand reads: 3-register FFMA 85, 2-register
+// forms 117, 1-register forms 129 lanes/clk/SM -- so each factor kept out of the vector register file
+// is a direct saving, and FFMA2 (f32x2) does not help (same operand words per flop).
 // ------------------------------------------------------------------------------------------------
-constexpr int kAnchor = 32;
+constexpr int kSeriesBlock = 32;       // unrolled terms per block
+constexpr int kSeriesMaxTerms = 2896;  // m(m+1) is exact in fp32 below this
 
-// sin/cos of (m * w) with the product carried exactly (hi + lo), first-order correction for lo.
-SO3D_HD void sincos_mw(float m, float w, float* s, float* c) {
-  const float hi = m * w;
-  const float lo = fmaf(m, w, -hi);
-  float sh, ch;
-  sincos_f(hi, &sh, &ch);
-  *s = fmaf(lo, ch, sh);
-  *c = fmaf(-lo, sh, ch);
+struct alignas(16) SeriesTab {
+  float mh[kSeriesMaxTerms + kSeriesBlock];  // m + 1/2
+  float mm[kSeriesMaxTerms + kSeriesBlock];  // m (m + 1)
+};
+constexpr SeriesTab make_series_tab() {
+  SeriesTab t{};
+  for (int m = 0; m < kSeriesMaxTerms + kSeriesBlock; ++m) {
+    t.mh[m] = (float)m + 0.5f;
+    t.mm[m] = (float)((double)m * (double)(m + 1));
+  }
+  return t;
+}
+#if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
+__constant__ SeriesTab c_series_tab = make_series_tab();
+#endif
+static constexpr SeriesTab h_series_tab = make_series_tab();
+
+SO3D_HD float series_mh(int m) {
+#if defined(__CUDA_ARCH__)
+  return c_series_tab.mh[m];
+#else
+  return h_series_tab.mh[m];
+#endif
+}
+SO3D_HD float series_mm(int m) {
+#if defined(__CUDA_ARCH__)
+  return c_series_tab.mm[m];
+#else
+  return h_series_tab.mm[m];
+#endif
 }
 
 struct SeriesAcc {
-  float F, Fp;  // sum (l+1/2) e_l chi_l ,  sum (l+1/2) e_l D_l
+  float F, dF;  // sum (l+1/2) e_l chi_l  and its derivative w.r.t. w:  f = 2 F,  d log f / dw = dF / F
 };
 
 struct SeriesState {
-  float s, c, m;      // sin(m w), cos(m w), m as float
-  float chi, D;       // running chi_m, D_m
-  float F, Fp;        // accumulators
+  float b, d;    // b_{l+1}, d_{l+1}
+  float bp, dp;  // b'_{l+1}, d'_{l+1}
+  float b2, bp2; // b_{l+2}, b'_{l+2}
 };
 
-// `count` consecutive terms starting at the state's m: accumulate term m, then rotate to m + 1.
+// terms l = hi, hi-1, ..., hi-count+1 (descending)
 template <int kUnroll>
-SO3D_HD void igso3_series_run(SeriesState& st, float sw, float cw, float cexp, int count) {
+SO3D_HD void igso3_series_run(SeriesState& st, float kap, float kapp, float cexp, int hi, int count) {
 #pragma unroll kUnroll
   for (int i = 0; i < count; ++i) {
-    st.chi = fmaf(2.0f, st.c, st.chi);
-    st.D = fmaf(st.m, st.s, st.D);
-    const float e = fast_ex2(fmaf(st.m, st.m, st.m) * cexp);
-    const float p = e * (st.m + 0.5f);
-    st.F = fmaf(p, st.chi, st.F);
-    st.Fp = fmaf(p, st.D, st.Fp);
-    const float t1 = st.c * sw, t2 = st.s * sw;
-    const float sn = fmaf(st.s, cw, t1);
-    st.c = fmaf(st.c, cw, -t2);
-    st.s = sn;
-    st.m += 1.0f;
+    const int l = hi - i;
+    const float A = fast_ex2(series_mm(l) * cexp) * series_mh(l);
+    const float dn = fmaf(-kap, st.b, A + st.d);
+    const float dpn = fmaf(-kap, st.bp, fmaf(-kapp, st.b, st.dp));
+    st.b2 = st.b;
+    st.bp2 = st.bp;
+    st.b += dn;
+    st.bp += dpn;
+    st.d = dn;
+    st.dp = dpn;
   }
 }
 
-// Evaluate terms l = 0 .. L-1.  Returns F, Fp;  f = 2F, dlogf/dw = -2 Fp / F.
+// Evaluate terms l = 0 .. L-1.
 SO3D_HD SeriesAcc igso3_series_terms(float w, float eps, int L) {
   const float cexp = -(eps * eps) * 1.4426950408889634f;
-  float sw, cw;
-  sincos_f(w, &sw, &cw);
+  float sh, ch;
+  sincos_f(0.5f * w, &sh, &ch);
+  const float kap = 4.0f * sh * sh, kapp = 4.0f * sh * ch;
   SeriesState st;
-  st.s = sw; st.c = cw; st.m = 1.0f;
-  st.chi = 1.0f; st.D = 0.0f;
-  st.F = 0.5f; st.Fp = 0.0f;  // l = 0 term: (1/2) * e_0 * chi_0, D_0 = 0
-  if (L > 1) igso3_series_run<kAnchor>(st, sw, cw, cexp, (L < kAnchor ? L : kAnchor) - 1);
-  for (int base = kAnchor; base < L; base += kAnchor) {
-    sincos_mw((float)base, w, &st.s, &st.c);
-    st.m = (float)base;
-    const int cnt = (L - base < kAnchor) ? (L - base) : kAnchor;
-    if (cnt == kAnchor) igso3_series_run<kAnchor>(st, sw, cw, cexp, kAnchor);
-    else igso3_series_run<1>(st, sw, cw, cexp, cnt);
-  }
-  return SeriesAcc{st.F, st.Fp};
+  st.b = st.d = st.bp = st.dp = st.b2 = st.bp2 = 0.f;
+  const int ragged = L % kSeriesBlock;  // top partial block first, so that full blocks are 32-aligned
+  if (ragged) igso3_series_run<1>(st, kap, kapp, cexp, L - 1, ragged);
+  // block index as the loop variable: table offsets are provably 128-byte aligned -> LDCU.128
+  for (int blk = L / kSeriesBlock - 1; blk >= 0; --blk)
+    igso3_series_run<kSeriesBlock>(st, kap, kapp, cexp, blk * kSeriesBlock + (kSeriesBlock - 1), kSeriesBlock);
+  return SeriesAcc{st.b + st.b2, st.bp + st.bp2};
 }
 
 // Number of leading terms whose weight 2^(l(l+1) cexp) is not flushed to zero (ex2.approx.ftz
@@ -575,10 +607,15 @@ SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, 
   if (mode == kClosed || (mode == kAuto && eps < kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
   } else {
-    const int terms = (mode == kSeries) ? L : igso3_series_live_terms(eps, L);
+    int terms = (mode == kSeries) ? L : igso3_series_live_terms(eps, L);
+#if defined(__CUDA_ARCH__)
+    // keep the trip count (and with it the constant-table index) warp-uniform: a lane-varying index would
+    // serialise the constant loads.  The extra terms have weight exactly 0, so the result is unchanged.
+    if (mode != kSeries) terms = __reduce_max_sync(__activemask(), terms);
+#endif
     const SeriesAcc a = igso3_series_terms(w, eps, terms);
     *logf_out = logf(2.0f * a.F);
-    *g_out = -2.0f * a.Fp / a.F;
+    *g_out = a.dF / a.F;
   }
 }
 

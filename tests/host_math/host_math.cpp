@@ -38,7 +38,7 @@ void hm_closed_f64(const double* w, const double* eps, double* f, long n, int qu
   for (long i = 0; i < n; ++i) f[i] = igso3_closed_f64(w[i], eps[i], quirks);
 }
 void hm_series(const float* w, const float* eps, float* F, float* Fp, long n, int L) {
-  for (long i = 0; i < n; ++i) { SeriesAcc a = igso3_series_terms(w[i], eps[i], L); F[i] = a.F; Fp[i] = a.Fp; }
+  for (long i = 0; i < n; ++i) { SeriesAcc a = igso3_series_terms(w[i], eps[i], L); F[i] = a.F; Fp[i] = a.dF; }
 }
 void hm_angle_from_uniform(const float* trap, const float* loc, const float* u, float* ang, long n) {
   for (long i = 0; i < n; ++i) ang[i] = igso3_angle_from_uniform(trap, loc, u[i]);

@@ -156,7 +156,7 @@ def test_auto_full_angle_range(hm):
 
 
 def test_series_fp32(hm):
-    """fp32 L=2000 series (character form, 32-term anchors) vs the fp64 series.
+    """fp32 L=2000 series (character form, Reinsch-Clenshaw recurrence) vs the fp64 series.
     1e-5 where the alternating sum is well conditioned (omega <= 3.5 eps); beyond that the error
     of ANY fp32 summation grows with the cancellation (oracle/proto_series_fp32.py), bounded here."""
     n = 6000
@@ -167,7 +167,7 @@ def test_series_fp32(hm):
     hm.hm_series(fp(om), fp(eps), fp(F), fp(Fp), ctypes.c_long(n), 2000)
     ft, gt = O.igso3_series(om.astype(np.float64), eps.astype(np.float64))
     f = 2.0 * F.astype(np.float64)
-    g = -2.0 * Fp.astype(np.float64) / F.astype(np.float64)
+    g = Fp.astype(np.float64) / F.astype(np.float64)  # hm_series returns dF/dw in its second output
     ef = np.abs(f - ft) / ft
     eg = np.abs(g - gt) / np.maximum(np.abs(gt), 1e-30)
     well = k <= 2.5
