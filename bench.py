@@ -292,7 +292,7 @@ def main():
         def step_rev():
             state["off"] += 1
             lib_call("so3d_p_sample_f32", ptr(xa), ptr(pred), ptr(t_step), 0, ptr(proc.sqrt_recip_alphas_cumprod), ptr(proc.sqrt_recipm1_alphas_cumprod),
-                     ptr(proc.posterior_mean_coef1), ptr(proc.posterior_mean_coef2), 1000, ptr(post), ptr(dx.ops.cdf_grid(device)[2]), SEED, state["off"],
+                     ptr(proc.posterior_mean_coef1), ptr(proc.posterior_mean_coef2), 1000, ptr(post), None, ptr(dx.ops.cdf_grid(device)[2]), SEED, state["off"],
                      rank * n, ptr(xb), None, n, device=device)
 
         v, m = rate(step_rev, n, 10)

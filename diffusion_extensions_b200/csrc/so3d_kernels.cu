@@ -17,6 +17,7 @@
 
 #include "../../include/so3d.h"
 #include "so3d_math.cuh"
+#include "so3d_tma.cuh"
 
 using namespace so3d;
 
@@ -568,72 +569,180 @@ struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
   }
 };
 
-template <bool kSharedT>
-__global__ void __launch_bounds__(kTile) p_sample_kernel(const float* __restrict__ x_t, const float* __restrict__ pred3,
-                                                         const int64_t* __restrict__ t, const float* __restrict__ recip,
-                                                         const float* __restrict__ recipm1, const float* __restrict__ coef1,
-                                                         const float* __restrict__ coef2, int64_t T, const float* __restrict__ post_cdf,
-                                                         const float* __restrict__ loc, uint64_t seed, uint64_t rng_offset,
-                                                         uint64_t row_offset, float* __restrict__ out, float* __restrict__ x0_hat_out,
-                                                         int64_t n, unsigned vecmask) {
+// ------------------------------------------------------------------------------------------------
+// Pipelined tile movement for the fused HBM-bound kernels (so3d_tma.cuh): persistent CTAs, two
+// shared-memory stages per array, one elected thread driving the TMA engine.
+//   iteration k (tile = blockIdx.x + k gridDim.x, stage = k & 1):
+//     wait full[stage]  ->  every thread copies its row to registers  ->  barrier A (stage may be refilled;
+//     thread 0 has drained the bulk store issued two iterations ago)  ->  thread 0 issues the bulk loads of
+//     tile k+2 into `stage`  ->  arithmetic  ->  results to out[stage]  ->  proxy fence + barrier B  ->
+//     thread 0 issues the bulk store of out[stage].
+// A tile that is not a full, 16-byte aligned tile (ragged tail, unaligned views) is moved cooperatively
+// with ordinary loads/stores at the same points of the schedule.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void coop_load(float* __restrict__ sm, const float* __restrict__ g, int rows) {
+  for (int i = threadIdx.x; i < rows * W; i += kTile) sm[i] = __ldcs(g + i);
+}
+template <int W>
+__device__ __forceinline__ void coop_store(float* __restrict__ g, const float* __restrict__ sm, int rows) {
+  for (int i = threadIdx.x; i < rows * W; i += kTile) __stcs(g + i, sm[i]);
+}
+
+// CDF row, grid angles and the guide of one shared table row, staged in shared memory by the whole CTA.
+struct SharedCdf {
+  float* loc;       // kCdf (+1 pad)
+  float* trap;      // kCdf (+1 pad)
+  uint16_t* guide;  // kGuideStride
+};
+__device__ __forceinline__ void stage_shared_cdf(const SharedCdf& sc, const float* __restrict__ cdf_row, const float* __restrict__ loc) {
+  for (int k = threadIdx.x; k < kCdf; k += kTile) {
+    sc.loc[k] = loc[k];
+    sc.trap[k] = cdf_row[k];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= kGuide; k += kTile)
+    sc.guide[k] = (uint16_t)cdf_count_le(sc.trap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
+  __syncthreads();
+}
+
+// distributions.py:15-30 companion: guide[row][k] = #{j : trap[row][j] <= k/1024} (so3d_math.cuh).
+__global__ void __launch_bounds__(kTile) cdf_guide_kernel(const float* __restrict__ cdf, uint16_t* __restrict__ guide) {
+  __shared__ float s_trap[kGrid];
+  const int64_t row = blockIdx.x;
+  for (int k = threadIdx.x; k < kCdf; k += kTile) s_trap[k] = cdf[row * kCdf + k];
+  __syncthreads();
+  for (int k = threadIdx.x; k < kGuideStride; k += kTile)
+    guide[row * kGuideStride + k] = (k <= kGuide) ? (uint16_t)cdf_count_le(s_trap, (float)k * (1.0f / (float)kGuide), 0, kCdf) : (uint16_t)kCdf;
+}
+
+// diffusion.py:291-326, fused reverse step.
+//   kSharedT: the whole batch shares t (the reference's semantics, Q7): schedule scalars are uniform and the
+//             posterior CDF row + guide live in shared memory; otherwise per-row t with table rows read from L2.
+//   kX0:      also write x0_hat.
+template <bool kSharedT, bool kX0>
+__global__ void __launch_bounds__(kTile) p_step_kernel(const float* __restrict__ x_t, const float* __restrict__ pred3,
+                                                       const int64_t* __restrict__ t, const float* __restrict__ recip,
+                                                       const float* __restrict__ recipm1, const float* __restrict__ coef1,
+                                                       const float* __restrict__ coef2, int64_t T, const float* __restrict__ post_cdf,
+                                                       const uint16_t* __restrict__ post_guide, const float* __restrict__ loc,
+                                                       uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* __restrict__ out,
+                                                       float* __restrict__ x0_hat_out, int64_t n, int use_tma) {
   extern __shared__ float4 smem4[];
-  float* s_x = reinterpret_cast<float*>(smem4);  // kTile*9
-  float* s_p = s_x + kTile * 9;                  // kTile*3
-  float* s_o = s_p + kTile * 3;                  // kTile*9
-  float* s_h = s_o + kTile * 9;                  // kTile*9 (x0_hat, optional)
-  float* s_loc = s_h + kTile * 9;                // 1000
-  float* s_cdf = s_loc + 1000;                   // 1000 (kSharedT)
+  float* s_x = reinterpret_cast<float*>(smem4);     // [2][kTile*9]
+  float* s_p = s_x + 2 * kTile * 9;                 // [2][kTile*3]
+  float* s_o = s_p + 2 * kTile * 3;                 // [2][kTile*9]
+  float* s_h = s_o + 2 * kTile * 9;                 // [2][kTile*9] (kX0)
+  float* s_tab = s_h + (kX0 ? 2 * kTile * 9 : 0);
+  SharedCdf sc;
+  sc.loc = s_tab;
+  sc.trap = s_tab + kGrid;
+  sc.guide = reinterpret_cast<uint16_t*>(s_tab + 2 * kGrid);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + 2 * kGrid + kGuideStride / 2 + 1);  // 8-byte aligned: all counts even
+  const int tid = threadIdx.x;
+
   int64_t t_shared = 0;
   if (kSharedT) {
     t_shared = t[0];
     t_shared = t_shared < 0 ? 0 : (t_shared >= T ? T - 1 : t_shared);
   }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
   if (post_cdf) {
-    for (int k = threadIdx.x; k < kCdf; k += kTile) {
-      s_loc[k] = loc[k];
-      if (kSharedT) s_cdf[k] = post_cdf[t_shared * kCdf + k];
+    if (kSharedT) {
+      stage_shared_cdf(sc, post_cdf + t_shared * kCdf, loc);
+    } else {
+      for (int k = tid; k < kCdf; k += kTile) sc.loc[k] = loc[k];
     }
   }
+  __syncthreads();
+
   const int64_t tiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kTile;
-    const int rows = (int)((n - row0) < kTile ? (n - row0) : kTile);
-    tile_load<9>(s_x, x_t + row0 * 9, rows, vecmask & 1u);
-    tile_load<3>(s_p, pred3 + row0 * 3, rows, (vecmask >> 1) & 1u);
-    __syncthreads();
-    const int r = threadIdx.x;
-    if (r < rows) {
-      const int64_t i = row0 + r;
-      int64_t ti;
-      if (kSharedT) {
-        ti = t_shared;
-      } else {
+  const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_rows = [&](int64_t k) -> int {
+    const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTile;
+    return (int)((n - row0) < kTile ? (n - row0) : kTile);
+  };
+  auto issue_load = [&](int64_t k) {  // thread 0 only
+    const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTile;
+    const int st = (int)(k & 1);
+    mbar_expect_tx(&bars[st], kTile * 12 * sizeof(float));
+    bulk_load(s_x + st * kTile * 9, x_t + row0 * 9, kTile * 9 * sizeof(float), &bars[st]);
+    bulk_load(s_p + st * kTile * 3, pred3 + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
+  };
+  if (tid == 0 && use_tma) {
+    if (my_tiles > 0 && tile_rows(0) == kTile) issue_load(0);
+    if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
+  }
+
+  float k_recip = 0.f, k_recipm1 = 0.f, k_c1 = 0.f, k_c2 = 0.f;
+  if (kSharedT) {
+    k_recip = __ldg(recip + t_shared); k_recipm1 = __ldg(recipm1 + t_shared);
+    k_c1 = __ldg(coef1 + t_shared); k_c2 = __ldg(coef2 + t_shared);
+  }
+
+  for (int64_t k = 0; k < my_tiles; ++k) {
+    const int st = (int)(k & 1);
+    const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTile;
+    const int rows = tile_rows(k);
+    const bool tma = use_tma && rows == kTile;
+    float* sx = s_x + st * kTile * 9;
+    float* sp = s_p + st * kTile * 3;
+    float* so = s_o + st * kTile * 9;
+    float* sh = s_h + st * kTile * 9;
+    if (tma) {
+      mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+    } else {
+      coop_load<9>(sx, x_t + row0 * 9, rows);
+      coop_load<3>(sp, pred3 + row0 * 3, rows);
+      __syncthreads();
+    }
+    const Mat3 x = sm_mat(sx, tid);
+    const Vec3 p = sm_vec(sp, tid);
+    if (tid == 0) bulk_wait_read<1>();  // the store that read out[st] two iterations ago has drained
+    __syncthreads();                    // A
+    if (tid == 0 && use_tma && k + 2 < my_tiles && tile_rows(k + 2) == kTile) issue_load(k + 2);
+
+    if (tid < rows) {
+      const int64_t i = row0 + tid;
+      int64_t ti = t_shared;
+      if (!kSharedT) {
         ti = t[i];
         ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
+        k_recip = __ldg(recip + ti); k_recipm1 = __ldg(recipm1 + ti);
+        k_c1 = __ldg(coef1 + ti); k_c2 = __ldg(coef2 + ti);
       }
-      const float k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti);
-      const float k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti);
-      const Mat3 x = sm_mat(s_x, r);
-      const Vec3 p = sm_vec(s_p, r);
-      // x0_hat = so3_scale(x_t, recip) @ exp(hat(pred * recipm1))^T                diffusion.py:291-297
-      const AxisAngle ax = axis_angle(x);
-      const Mat3 xt_term = rodrigues(ax.axis, k_recip * ax.theta);
-      const Mat3 nterm = exp_vec(Vec3{p.x * k_recipm1, p.y * k_recipm1, p.z * k_recipm1});
-      const Mat3 x0h = mul_nt(xt_term, nterm);
-      // mean = so3_scale(x0_hat, c1) @ so3_scale(x_t, c2)                          diffusion.py:299-302
-      Mat3 o = mul_nn(scale_rot(x0h, k_c1), rodrigues(ax.axis, k_c2 * ax.theta));
+      Quat qh;
+      Quat qm = p_mean_quat(x, p, k_recip, k_recipm1, k_c1, k_c2, &qh);
       if (post_cdf && ti != 0) {                                                   // diffusion.py:320-326
         const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
-        const float ang = igso3_angle_from_uniform(kSharedT ? s_cdf : post_cdf + ti * kCdf, s_loc, d.u);
-        o = mul_nn(o, rodrigues(d.axis, ang));
+        float ang;
+        if (kSharedT) ang = igso3_angle_from_uniform_guided(sc.trap, sc.loc, sc.guide, d.u);
+        else if (post_guide) ang = igso3_angle_from_uniform_guided(post_cdf + ti * kCdf, sc.loc, post_guide + ti * kGuideStride, d.u);
+        else ang = igso3_angle_from_uniform(post_cdf + ti * kCdf, sc.loc, d.u);
+        qm = qmul(qm, quat_axis_angle(d.axis, ang));
       }
-      sm_put_mat(s_o, r, o);
-      if (x0_hat_out) sm_put_mat(s_h, r, x0h);
+      sm_put_mat(so, tid, quat_to_mat_unit(qm));
+      if (kX0) sm_put_mat(sh, tid, quat_to_mat_unit(qh));
     }
-    __syncthreads();
-    tile_store<9>(out + row0 * 9, s_o, rows, (vecmask >> 2) & 1u);
-    if (x0_hat_out) tile_store<9>(x0_hat_out + row0 * 9, s_h, rows, (vecmask >> 3) & 1u);
+    if (tma) {
+      fence_proxy_async();
+      __syncthreads();  // B
+      if (tid == 0) {
+        bulk_store(out + row0 * 9, so, kTile * 9 * sizeof(float));
+        if (kX0) bulk_store(x0_hat_out + row0 * 9, sh, kTile * 9 * sizeof(float));
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();  // B
+      coop_store<9>(out + row0 * 9, so, rows);
+      if (kX0) coop_store<9>(x0_hat_out + row0 * 9, sh, rows);
+    }
   }
+  if (tid == 0) bulk_wait_read<0>();
 }
 
 }  // namespace
@@ -875,27 +984,51 @@ int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt
   return launch_rowwise(op, n, stream, "so3d_q_sample_given_f32");
 }
 
+int so3d_igso3_cdf_guide_u16(const float* cdf, int64_t rows, uint16_t* guide_out, void* stream) {
+  SO3D_REQUIRE(rows >= 0, "negative rows");
+  if (rows == 0) return 0;
+  SO3D_REQUIRE(cdf && guide_out, "so3d_igso3_cdf_guide_u16: null pointer");
+  SO3D_REQUIRE(rows <= 0x7fffffff, "so3d_igso3_cdf_guide_u16: too many rows");
+  cdf_guide_kernel<<<(int)rows, kTile, 0, (cudaStream_t)stream>>>(cdf, guide_out);
+  return check_launch("so3d_igso3_cdf_guide_u16");
+}
+
+}  // extern "C"
+
+template <bool kSharedT, bool kX0>
+static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
+                         const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint16_t* post_guide,
+                         const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
+                         int64_t n, void* stream) {
+  const size_t smem = sizeof(float) * (size_t)(2 * kTile * (9 + 3 + 9 + (kX0 ? 9 : 0)) + 2 * kGrid + kGuideStride / 2 + 1) + 2 * sizeof(uint64_t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(p_step_kernel<kSharedT, kX0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  const int use_tma = aligned16(x_t) && aligned16(pred3) && aligned16(out) && (!kX0 || aligned16(x0_hat_out));
+  p_step_kernel<kSharedT, kX0><<<grid_for(n, kX0 ? 3 : 4), kTile, smem, (cudaStream_t)stream>>>(
+      x_t, pred3, t, recip, recipm1, coef1, coef2, T, post_cdf, post_guide, loc, seed, rng_offset, row_offset, out, x0_hat_out, n, use_tma);
+  return check_launch("so3d_p_sample_f32");
+}
+
+extern "C" {
+
 int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, int t_stride, const float* recip,
                       const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
-                      const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
-                      int64_t n, void* stream) {
+                      const uint16_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
+                      float* out, float* x0_hat_out, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
   if (n == 0) return 0;
   SO3D_REQUIRE(x_t && pred3 && t && recip && recipm1 && coef1 && coef2 && out, "so3d_p_sample_f32: null pointer");
   SO3D_REQUIRE(T > 0, "so3d_p_sample_f32: T must be positive");
   SO3D_REQUIRE(t_stride == 0 || t_stride == 1, "t_stride must be 0 or 1");
   SO3D_REQUIRE(!post_cdf || loc, "so3d_p_sample_f32: loc required with post_cdf");
-  const unsigned mask = (aligned16(x_t) ? 1u : 0u) | (aligned16(pred3) ? 2u : 0u) | (aligned16(out) ? 4u : 0u) |
-                        (aligned16(x0_hat_out) ? 8u : 0u);
-  const size_t smem = sizeof(float) * (kTile * (9 * 3 + 3) + 2000);
-  const int grid = grid_for(n, 6);
-  if (t_stride == 0)
-    p_sample_kernel<true><<<grid, kTile, smem, (cudaStream_t)stream>>>(x_t, pred3, t, recip, recipm1, coef1, coef2, T, post_cdf, loc, seed,
-                                                                        rng_offset, row_offset, out, x0_hat_out, n, mask);
-  else
-    p_sample_kernel<false><<<grid, kTile, smem, (cudaStream_t)stream>>>(x_t, pred3, t, recip, recipm1, coef1, coef2, T, post_cdf, loc, seed,
-                                                                         rng_offset, row_offset, out, x0_hat_out, n, mask);
-  return check_launch("so3d_p_sample_f32");
+#define SO3D_PSTEP(S, X) \
+  launch_p_step<S, X>(x_t, pred3, t, recip, recipm1, coef1, coef2, T, post_cdf, post_guide, loc, seed, rng_offset, row_offset, out, x0_hat_out, n, stream)
+  if (t_stride == 0) return x0_hat_out ? SO3D_PSTEP(true, true) : SO3D_PSTEP(true, false);
+  return x0_hat_out ? SO3D_PSTEP(false, true) : SO3D_PSTEP(false, false);
+#undef SO3D_PSTEP
 }
 
 }  // extern "C"

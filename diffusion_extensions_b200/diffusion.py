@@ -91,6 +91,7 @@ class SO3Diffusion(nn.Module):
         # batch independent of the number of GPUs (set by the multi-GPU harness)
         self.row_offset = 0
         self._tables = {}  # device -> (fwd_cdf, post_cdf, t_range)
+        self._guides = {}  # device -> (fwd_guide, post_guide)
 
     # ---- per-schedule CDF tables -----------------------------------------------------------------
     def tables(self):
@@ -104,7 +105,13 @@ class SO3Diffusion(nn.Module):
             sigma = (0.5 * self.posterior_log_variance_clipped).exp()  # diffusion.py:324
             post = ops.igso3_cdf_table(sigma, self.reference_quirks)
             self._tables[key] = (fwd, post, torch.arange(self.num_timesteps, device=dev))
+            self._guides[key] = (ops.igso3_cdf_guide(fwd), ops.igso3_cdf_guide(post))
         return self._tables[key]
+
+    def guides(self):
+        """(fwd_guide, post_guide): the (T, 1026) search accelerators of the two CDF tables."""
+        self.tables()
+        return self._guides[str(self.betas.device)]
 
     # ---- forward process ----------------------------------------------------------------------
     def q_mean_variance(self, x_start, t):
@@ -165,7 +172,8 @@ class SO3Diffusion(nn.Module):
         predict = self._denoise(x, t)
         _, post, _ = self.tables()
         return ops.p_sample_fused(x, predict, t, self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
-                                  self.posterior_mean_coef1, self.posterior_mean_coef2, post_cdf=post, row_offset=self.row_offset)
+                                  self.posterior_mean_coef1, self.posterior_mean_coef2, post_cdf=post, post_guide=self.guides()[1],
+                                  row_offset=self.row_offset)
 
     @torch.no_grad()
     def p_sample_loop(self, shape, init="igso3_1", progress=False):

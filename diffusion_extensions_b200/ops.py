@@ -13,6 +13,7 @@ from ._lib import call, check_f32, ptr
 
 CDF_POINTS = 999
 GRID_POINTS = 1000
+GUIDE_STRIDE = 1026  # uint16 entries per guide row (include/so3d.h SO3D_GUIDE_STRIDE)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -290,6 +291,15 @@ def igso3_cdf_table(eps, reference_quirks=False):
     return out
 
 
+def igso3_cdf_guide(cdf):
+    """cdf (rows, 999) -> guide (rows, 1026) int16 storage of uint16 counts (search accelerator)."""
+    cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
+    rows = cdf.numel() // CDF_POINTS
+    out = torch.empty(rows, GUIDE_STRIDE, dtype=torch.int16, device=cdf.device)
+    call("so3d_igso3_cdf_guide_u16", ptr(cdf), rows, ptr(out), device=cdf.device)
+    return out
+
+
 def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, rng_offset=None, row_offset=0,
                  mean=None, want_angle=False, want_axis=False):
     """Draw rotations of batch shape `shape` from the CDF rows in `cdf` (rows, 999).
@@ -367,7 +377,7 @@ def q_sample_given(x0, t, sqrt_ac, noise):
 
 
 def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, seed=None, rng_offset=None, row_offset=0,
-                   want_x0_hat=False):
+                   want_x0_hat=False, post_guide=None):
     """Fused reverse step.  t: int64 tensor with one element (shared step) or one per row.
     post_cdf None -> posterior mean only.  -> out (...,3,3)[, x0_hat]"""
     x_t, bs, n = _rows9(x_t, "x")
@@ -386,11 +396,13 @@ def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, se
         post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
         if post_cdf.numel() != T * CDF_POINTS:
             raise ValueError("posterior cdf table must have one row per timestep")
+        if post_guide is not None and (post_guide.dtype != torch.int16 or post_guide.numel() != T * GUIDE_STRIDE or not post_guide.is_contiguous()):
+            raise ValueError("posterior guide must be the contiguous int16 (T, 1026) tensor of igso3_cdf_guide")
         _, _, trap_loc = cdf_grid(dev)
         if seed is None or rng_offset is None:
             seed, rng_offset = rng.next()
     out = torch.empty_like(x_t)
     x0_hat = torch.empty_like(x_t) if want_x0_hat else None
     call("so3d_p_sample_f32", ptr(x_t), ptr(pred), ptr(t), t_stride, ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T,
-         ptr(post_cdf), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(x0_hat), n, device=dev)
+         ptr(post_cdf), ptr(post_guide), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(x0_hat), n, device=dev)
     return (out, x0_hat) if want_x0_hat else out

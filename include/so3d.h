@@ -39,6 +39,7 @@ extern "C" {
 
 #define SO3D_CDF_POINTS 999  /* entries per CDF row (distributions.py:15,30: 1000-point grid) */
 #define SO3D_GRID_POINTS 1000
+#define SO3D_GUIDE_STRIDE 1026 /* uint16 entries per guide row (1025 used) */
 
 /* evaluator for the IGSO(3) density (mode argument) */
 #define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms                    */
@@ -103,6 +104,11 @@ int so3d_igso3_logp_bwd_f32(const float* R, const float* dlogf, const float* gou
  * reference's (999, *E) layout).  quirks != 0 reproduces the reference's overflow behaviour (D5). */
 int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_loc, const float* haar_w,
                              float* trap_out, int quirks, void* stream);
+/* Search accelerator for the inverse-CDF lookup of distributions.py:38-43 (`(trap <= u).sum()`): for every
+ * CDF row, guide[k] = #{j : trap[j] <= k/1024}, k = 0..1024, stored as uint16 with a row stride of
+ * SO3D_GUIDE_STRIDE entries.  A lookup then needs ~1 probe instead of a 10-step binary search and returns the
+ * identical index.  guide_out: rows x SO3D_GUIDE_STRIDE. */
+int so3d_igso3_cdf_guide_u16(const float* cdf, int64_t rows, uint16_t* guide_out, void* stream);
 /* distributions.py:33-51 sample: R = mean @ rot(axis, angle(u)).
  *   cdf: table rows x 999;  loc: 999 grid angles;  row_idx: int64[n] row per sample, or NULL with
  *   `row` = the single shared row (scalar-eps path, staged in shared memory).
@@ -130,12 +136,13 @@ int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt
  *   x0_hat = so3_scale(x_t, recip[t]) @ exp(hat(pred * recipm1[t]))^T          (:291-297)
  *   mean   = so3_scale(x0_hat, coef1[t]) @ so3_scale(x_t, coef2[t])            (:299-302)
  *   out    = t == 0 ? mean : mean @ noise,  noise ~ IGSO3(sigma_t) from post_cdf row t   (:315-326)
- *   t: int64[n] per row (t_stride 1) or a single shared step (t_stride 0, CDF row staged in smem).
+ *   t: int64[n] per row (t_stride 1) or a single shared step (t_stride 0: CDF row and guide staged in
+ *   shared memory).  post_guide: so3d_igso3_cdf_guide_u16 of post_cdf (nullable; used with per-row t).
  *   post_cdf == NULL returns the mean only (p_mean_variance).  x0_hat_out nullable. */
 int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, int t_stride, const float* recip,
-                      const float* recipm1, const float* coef1, const float* coef2, int64_t T,
-                      const float* post_cdf, const float* loc, uint64_t seed, uint64_t rng_offset,
-                      uint64_t row_offset, float* out, float* x0_hat_out, int64_t n, void* stream);
+                      const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
+                      const uint16_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
+                      float* out, float* x0_hat_out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,25 @@ void hm_closed_f32(const float* w, const float* eps, float* logf, float* g, long
 void hm_closed_f64(const double* w, const double* eps, double* f, long n, int quirks) {
   for (long i = 0; i < n; ++i) f[i] = igso3_closed_f64(w[i], eps[i], quirks);
 }
+void hm_sincos_fast(const float* x, float* s, float* c, long n) {
+  for (long i = 0; i < n; ++i) sincos_fast(x[i], s + i, c + i);
+}
+void hm_atan2_pos(const float* y, const float* x, float* r, long n) {
+  for (long i = 0; i < n; ++i) r[i] = atan2_pos(y[i], x[i]);
+}
+void hm_axis_angle_fast(const float* R, float* axis, float* ang, long n) {
+  for (long i = 0; i < n; ++i) { AxisAngleF a = axis_angle_fast(ld(R + 9 * i)); axis[3*i]=a.axis.x; axis[3*i+1]=a.axis.y; axis[3*i+2]=a.axis.z; ang[i]=a.theta; }
+}
+// fused reverse-step mean on quaternions -> matrices (mean and x0_hat)
+void hm_p_mean_quat(const float* x, const float* pred, const float* a, const float* b, const float* c1, const float* c2, float* mean,
+                    float* x0h, long n) {
+  for (long i = 0; i < n; ++i) {
+    Quat qh;
+    const Quat qm = p_mean_quat(ld(x + 9 * i), Vec3{pred[3*i], pred[3*i+1], pred[3*i+2]}, a[i], b[i], c1[i], c2[i], &qh);
+    st(mean + 9 * i, quat_to_mat_unit(qm));
+    st(x0h + 9 * i, quat_to_mat_unit(qh));
+  }
+}
 void hm_series(const float* w, const float* eps, float* F, float* Fp, long n, int L) {
   for (long i = 0; i < n; ++i) { SeriesAcc a = igso3_series_terms(w[i], eps[i], L); F[i] = a.F; Fp[i] = a.dF; }
 }

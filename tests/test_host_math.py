@@ -279,3 +279,62 @@ def test_backward_pieces(hm):
         d = np.zeros(3); d[k] = h
         nk = ((O.exp_vec(w64 + d) - O.exp_vec(w64 - d)) * G).sum((-1, -2)) / (2 * h)
         assert np.max(np.abs(gw[:, k] - nk)) < 2e-4 * max(1.0, np.abs(nk).max())
+
+
+# ---- lean primitives of the HBM-bound fused kernels ------------------------------------------------
+def test_sincos_fast_and_atan2_pos(hm):
+    rng = np.random.default_rng(21)
+    x = np.concatenate([rng.uniform(-8, 8, 20000), rng.uniform(-3.3e4, 3.3e4, 20000), [0.0, 1e-8, -1e-8, math.pi / 2, math.pi, 1e-3]]).astype(np.float32)
+    s = np.empty_like(x); c = np.empty_like(x)
+    hm.hm_sincos_fast(fp(x), fp(s), fp(c), ctypes.c_long(x.size))
+    x64 = x.astype(np.float64)
+    assert np.max(np.abs(s - np.sin(x64))) < 2e-7 and np.max(np.abs(c - np.cos(x64))) < 2e-7
+    small = np.abs(x64) < 1.0
+    assert np.max(np.abs(s[small] - np.sin(x64[small])) / np.maximum(np.abs(np.sin(x64[small])), 1e-30)) < 3e-7
+    y = np.concatenate([np.abs(rng.standard_normal(20000)), [0.0, 0.0, 1e-20, 1.0, 1e-9]]).astype(np.float32)
+    xx = np.concatenate([rng.standard_normal(20000), [1.0, -1.0, 1.0, 0.0, -1.0]]).astype(np.float32)
+    r = np.empty_like(y)
+    hm.hm_atan2_pos(fp(y), fp(xx), fp(r), ctypes.c_long(y.size))
+    want = np.arctan2(y.astype(np.float64), xx.astype(np.float64))
+    assert np.max(np.abs(r - want)) < 3e-7
+    tiny = (want < 1e-2) & (want > 0)
+    assert np.max(np.abs(r[tiny] - want[tiny]) / want[tiny]) < 3e-7
+
+
+def test_axis_angle_fast(hm):
+    n = 8192
+    R, _, _ = rand_rots(n, 22)
+    R[:8] = np.eye(3, dtype=np.float32)
+    Rpi, _, _ = O.random_rotations(64, np.random.default_rng(23), math.pi)
+    ax = np.random.default_rng(24).standard_normal((64, 3)); ax /= np.linalg.norm(ax, axis=-1, keepdims=True)
+    R[8:72] = f32(O.rodrigues(ax, np.full(64, math.pi)))            # exactly pi
+    R[72:136] = f32(O.rodrigues(ax, math.pi - np.geomspace(1e-6, 1e-1, 64)))
+    axis = np.empty((n, 3), np.float32); ang = np.empty(n, np.float32)
+    hm.hm_axis_angle_fast(fp(R), fp(axis), fp(ang), ctypes.c_long(n))
+    _, ang_t = O.rmat_to_aa(R)
+    assert np.max(np.abs(ang - ang_t[:, 0])) < 5e-7 + 0  # atan2 of the same fp32 inputs
+    assert np.max(np.abs(np.linalg.norm(axis.astype(np.float64), axis=-1) - 1)) < 1e-6
+    back = O.rodrigues(axis.astype(np.float64), ang.astype(np.float64))
+    assert np.max(np.abs(back - R)) < 2e-6
+    assert np.all(axis[:8] == np.array([0, 0, 1], np.float32)) and np.all(ang[:8] == 0)
+
+
+def test_p_mean_quat_against_oracle(hm):
+    """The quaternion formulation of the reverse-step mean equals the reference algebra
+    (diffusion.py:291-313) evaluated in fp64, over the part of the schedule where fp32 inputs determine it."""
+    n = 8192
+    s = O.schedule_buffers(1000)
+    x, _, _ = rand_rots(n, 25, 3.1)
+    rng = np.random.default_rng(26)
+    pred = (rng.standard_normal((n, 3)) * 0.7).astype(np.float32)
+    pred[:16] = 0
+    t = rng.integers(0, 400, n)
+    a = f32(s["sqrt_recip_alphas_cumprod"][t]); b = f32(s["sqrt_recipm1_alphas_cumprod"][t])
+    c1 = f32(s["posterior_mean_coef1"][t]); c2 = f32(s["posterior_mean_coef2"][t])
+    mean = np.empty((n, 3, 3), np.float32); x0h = np.empty((n, 3, 3), np.float32)
+    hm.hm_p_mean_quat(fp(x), fp(pred), fp(a), fp(b), fp(c1), fp(c2), fp(mean), fp(x0h), ctypes.c_long(n))
+    want0 = O.predict_start_from_noise(x, pred, a.astype(np.float64), b.astype(np.float64))
+    assert np.max(O.geodesic_angle(x0h, want0)) < 3e-6
+    want = O.p_sample_mean(x, pred, a.astype(np.float64), b.astype(np.float64), c1.astype(np.float64), c2.astype(np.float64))
+    assert np.max(O.geodesic_angle(mean, want)) < 5e-6
+    assert np.max(np.abs(mean.astype(np.float64) @ np.swapaxes(mean, -1, -2) - np.eye(3))) < 2e-6
