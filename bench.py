@@ -284,6 +284,7 @@ def main():
         proc = dx.SO3Diffusion(None).to(device)
         proc.row_offset = rank * n
         fwd, post, t_range = proc.tables()
+        fwd_guide, post_guide = proc.guides()
         pred = torch.zeros(n, 3, device=device)
         xa, xb = R.clone(), torch.empty_like(R)
         t_step = t_range[500:501]
@@ -305,7 +306,7 @@ def main():
         def step_fwd():
             state["off"] += 1
             lib_call("so3d_q_sample_f32", ptr(xa), ptr(tt), ptr(proc.sqrt_alphas_cumprod), ptr(proc.sqrt_one_minus_alphas_cumprod), 1000, ptr(fwd),
-                     ptr(dx.ops.cdf_grid(device)[2]), SEED, state["off"], rank * n, ptr(xb), ptr(tgt), None, None, n, device=device)
+                     ptr(fwd_guide), ptr(dx.ops.cdf_grid(device)[2]), SEED, state["off"], rank * n, ptr(xb), ptr(tgt), None, None, n, device=device)
 
         v, m = rate(step_fwd, n, 10)
         gbs = v / world * BYTES_PER_QSAMPLE / 1e9

@@ -62,34 +62,30 @@ inline int grid_for(int64_t n, int ctas_per_sm) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------------
-// tile movers: contiguous block of rows*W floats between global and shared memory
+// The row engine: one persistent, TMA-pipelined kernel template shared by every op.
+//
+//   Op provides
+//     static constexpr int kIn9, kIn3, kOut9, kOut3  -- how many n x 9 / n x 3 arrays it reads / writes
+//     const float* in9[kIn9], in3[kIn3]; float* out9[kOut9], out3[kOut3]   (an output may be NULL = skipped)
+//     static constexpr int kTab;  __device__ void setup(float* tab) const   -- CTA-shared tables (CDF row, guide, ...)
+//     __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const
+//   Per-row scalars (angles, eps, t, ...) are read / written directly by Op::row with coalesced accesses.
+//
+//   Schedule of iteration k (tile = blockIdx.x + k gridDim.x, stage = k & 1), see so3d_tma.cuh:
+//     wait full[stage]  ->  every thread copies its row to registers  ->  barrier A (the stage may be refilled;
+//     thread 0 has drained the bulk store issued two iterations ago)  ->  thread 0 issues the bulk loads of
+//     tile k+2 into `stage`  ->  Op::row  ->  results to out[stage]  ->  proxy fence + barrier B  ->
+//     thread 0 issues the bulk stores of out[stage].
+//   A tile that is not a full tile of 16-byte aligned arrays (ragged tail, unaligned views) is moved
+//   cooperatively with ordinary loads/stores at the same points of the schedule.
 // ------------------------------------------------------------------------------------------------
 template <int W>
-__device__ __forceinline__ void tile_load(float* __restrict__ sm, const float* __restrict__ g, int rows, bool vec) {
-  const int nwords = rows * W;
-  if (vec) {
-    const int nvec = nwords >> 2;
-    const float4* g4 = reinterpret_cast<const float4*>(g);
-    float4* s4 = reinterpret_cast<float4*>(sm);
-    for (int i = threadIdx.x; i < nvec; i += kTile) s4[i] = __ldcs(g4 + i);
-    for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += kTile) sm[i] = __ldcs(g + i);
-  } else {
-    for (int i = threadIdx.x; i < nwords; i += kTile) sm[i] = __ldcs(g + i);
-  }
+__device__ __forceinline__ void coop_load(float* __restrict__ sm, const float* __restrict__ g, int rows) {
+  for (int i = threadIdx.x; i < rows * W; i += kTile) sm[i] = __ldcs(g + i);
 }
-
 template <int W>
-__device__ __forceinline__ void tile_store(float* __restrict__ g, const float* __restrict__ sm, int rows, bool vec) {
-  const int nwords = rows * W;
-  if (vec) {
-    const int nvec = nwords >> 2;
-    float4* g4 = reinterpret_cast<float4*>(g);
-    const float4* s4 = reinterpret_cast<const float4*>(sm);
-    for (int i = threadIdx.x; i < nvec; i += kTile) __stcs(g4 + i, s4[i]);
-    for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += kTile) __stcs(g + i, sm[i]);
-  } else {
-    for (int i = threadIdx.x; i < nwords; i += kTile) __stcs(g + i, sm[i]);
-  }
+__device__ __forceinline__ void coop_store(float* __restrict__ g, const float* __restrict__ sm, int rows) {
+  for (int i = threadIdx.x; i < rows * W; i += kTile) __stcs(g + i, sm[i]);
 }
 
 __device__ __forceinline__ Mat3 sm_mat(const float* sm, int r) {
@@ -109,85 +105,149 @@ __device__ __forceinline__ void sm_put_vec(float* sm, int r, Vec3 v) {
   sm[r * 3 + 2] = v.z;
 }
 
-// Generic row-wise kernel.  Op provides:
-//   static constexpr int kIn9, kIn3, kOut9, kOut3   -- how many n x 9 / n x 3 arrays it reads / writes
-//   const float* in9[kIn9], in3[kIn3]; float* out9[kOut9], out3[kOut3]  (an output may be NULL = skipped)
-//   __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3) const
-// Per-row scalars (angles, eps, t, ...) are read/written directly by Op::row with coalesced accesses.
 template <class Op>
-__global__ void __launch_bounds__(kTile) rowwise_kernel(const Op op, const int64_t n, const unsigned vecmask) {
+struct OpLayout {
+  static constexpr int kInWords = Op::kIn9 * 9 + Op::kIn3 * 3;     // per row
+  static constexpr int kOutWords = Op::kOut9 * 9 + Op::kOut3 * 3;  // per row
+  static constexpr int kStageFloats = kTile * (kInWords + kOutWords);
+  static constexpr int kTabFloats = (Op::kTab + 3) & ~3;
+  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kStageFloats + kTabFloats) + 2 * sizeof(uint64_t);
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kTile) rowwise_kernel(const Op op, const int64_t n, const int use_tma) {
   extern __shared__ float4 smem4[];
-  float* smem = reinterpret_cast<float*>(smem4);
   constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
-  float* s_i9 = smem;
-  float* s_i3 = s_i9 + kI9 * kTile * 9;
-  float* s_o9 = s_i3 + ((kI3 * kTile * 3 + 3) & ~3);
-  float* s_o3 = s_o9 + kO9 * kTile * 9;
+  using Lay = OpLayout<Op>;
+  float* smem = reinterpret_cast<float*>(smem4);
+  // stage s: [in9 arrays][in3 arrays][out9 arrays][out3 arrays]; every array starts 16-byte aligned (1 KiB multiples)
+  float* s_tab = smem + 2 * Lay::kStageFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  op.setup(s_tab);
+  __syncthreads();
+
   const int64_t tiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kTile;
-    const int rows = (int)((n - row0) < kTile ? (n - row0) : kTile);
-    unsigned bit = 0;
+  const int64_t my_tiles = (tiles > (int64_t)blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_row0 = [&](int64_t k) -> int64_t { return (blockIdx.x + k * gridDim.x) * (int64_t)kTile; };
+  auto tile_rows = [&](int64_t k) -> int {
+    const int64_t left = n - tile_row0(k);
+    return (int)(left < kTile ? left : kTile);
+  };
+  auto issue_load = [&](int64_t k) {  // thread 0 only
+    if (kI9 + kI3 == 0) return;
+    const int64_t row0 = tile_row0(k);
+    const int st = (int)(k & 1);
+    float* base = smem + st * Lay::kStageFloats;
+    mbar_expect_tx(&bars[st], (uint32_t)(kTile * Lay::kInWords * sizeof(float)));
 #pragma unroll
-    for (int a = 0; a < kI9; ++a, ++bit) tile_load<9>(s_i9 + a * kTile * 9, op.in9[a] + row0 * 9, rows, (vecmask >> bit) & 1u);
+    for (int a = 0; a < kI9; ++a) bulk_load(base + a * kTile * 9, op.in9[a] + row0 * 9, kTile * 9 * sizeof(float), &bars[st]);
 #pragma unroll
-    for (int a = 0; a < kI3; ++a, ++bit) tile_load<3>(s_i3 + a * kTile * 3, op.in3[a] + row0 * 3, rows, (vecmask >> bit) & 1u);
-    if (kI9 + kI3 > 0) __syncthreads();
-    const int r = threadIdx.x;
-    if (r < rows) {
-      Mat3 a9[kI9 > 0 ? kI9 : 1];
-      Vec3 a3[kI3 > 0 ? kI3 : 1];
+    for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
+  };
+  if (tid == 0 && use_tma) {
+    if (my_tiles > 0 && tile_rows(0) == kTile) issue_load(0);
+    if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
+  }
+
+  for (int64_t k = 0; k < my_tiles; ++k) {
+    const int st = (int)(k & 1);
+    const int64_t row0 = tile_row0(k);
+    const int rows = tile_rows(k);
+    const bool tma = use_tma && rows == kTile;
+    float* s_i9 = smem + st * Lay::kStageFloats;
+    float* s_i3 = s_i9 + kI9 * kTile * 9;
+    float* s_o9 = s_i3 + kI3 * kTile * 3;
+    float* s_o3 = s_o9 + kO9 * kTile * 9;
+    if (kI9 + kI3 > 0) {
+      if (tma) {
+        mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+      } else {
+#pragma unroll
+        for (int a = 0; a < kI9; ++a) coop_load<9>(s_i9 + a * kTile * 9, op.in9[a] + row0 * 9, rows);
+#pragma unroll
+        for (int a = 0; a < kI3; ++a) coop_load<3>(s_i3 + a * kTile * 3, op.in3[a] + row0 * 3, rows);
+        __syncthreads();
+      }
+    }
+    Mat3 a9[kI9 > 0 ? kI9 : 1];
+    Vec3 a3[kI3 > 0 ? kI3 : 1];
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) a9[a] = sm_mat(s_i9 + a * kTile * 9, tid);
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, tid);
+    if (tid == 0) bulk_wait_read<1>();  // the stores that read out[st] two iterations ago have drained
+    __syncthreads();                    // A
+    if (tid == 0 && use_tma && k + 2 < my_tiles && tile_rows(k + 2) == kTile) issue_load(k + 2);
+
+    if (tid < rows) {
       Mat3 o9[kO9 > 0 ? kO9 : 1];
       Vec3 o3[kO3 > 0 ? kO3 : 1];
+      op.row(row0 + tid, a9, a3, o9, o3, s_tab);
 #pragma unroll
-      for (int a = 0; a < kI9; ++a) a9[a] = sm_mat(s_i9 + a * kTile * 9, r);
+      for (int a = 0; a < kO9; ++a) sm_put_mat(s_o9 + a * kTile * 9, tid, o9[a]);
 #pragma unroll
-      for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, r);
-      op.row(row0 + r, a9, a3, o9, o3);
-#pragma unroll
-      for (int a = 0; a < kO9; ++a) sm_put_mat(s_o9 + a * kTile * 9, r, o9[a]);
-#pragma unroll
-      for (int a = 0; a < kO3; ++a) sm_put_vec(s_o3 + a * kTile * 3, r, o3[a]);
+      for (int a = 0; a < kO3; ++a) sm_put_vec(s_o3 + a * kTile * 3, tid, o3[a]);
     }
-    if (kO9 + kO3 > 0) __syncthreads();
+    if (kO9 + kO3 > 0) {
+      if (tma) {
+        fence_proxy_async();
+        __syncthreads();  // B
+        if (tid == 0) {
 #pragma unroll
-    for (int a = 0; a < kO9; ++a, ++bit)
-      if (op.out9[a]) tile_store<9>(op.out9[a] + row0 * 9, s_o9 + a * kTile * 9, rows, (vecmask >> bit) & 1u);
+          for (int a = 0; a < kO9; ++a)
+            if (op.out9[a]) bulk_store(op.out9[a] + row0 * 9, s_o9 + a * kTile * 9, kTile * 9 * sizeof(float));
 #pragma unroll
-    for (int a = 0; a < kO3; ++a, ++bit)
-      if (op.out3[a]) tile_store<3>(op.out3[a] + row0 * 3, s_o3 + a * kTile * 3, rows, (vecmask >> bit) & 1u);
-    // the next iteration's __syncthreads (after its loads) orders these smem reads before the next writes
-    if (kI9 + kI3 == 0 && kO9 + kO3 > 0) __syncthreads();
+          for (int a = 0; a < kO3; ++a)
+            if (op.out3[a]) bulk_store(op.out3[a] + row0 * 3, s_o3 + a * kTile * 3, kTile * 3 * sizeof(float));
+          bulk_commit();
+        }
+      } else {
+        __syncthreads();  // B
+#pragma unroll
+        for (int a = 0; a < kO9; ++a)
+          if (op.out9[a]) coop_store<9>(op.out9[a] + row0 * 9, s_o9 + a * kTile * 9, rows);
+#pragma unroll
+        for (int a = 0; a < kO3; ++a)
+          if (op.out3[a]) coop_store<3>(op.out3[a] + row0 * 3, s_o3 + a * kTile * 3, rows);
+      }
+    }
   }
+  if (tid == 0) bulk_wait_read<0>();
 }
 
 template <class Op>
-constexpr size_t op_smem() {
-  return sizeof(float) * (size_t)(Op::kIn9 * kTile * 9 + ((Op::kIn3 * kTile * 3 + 3) & ~3) + Op::kOut9 * kTile * 9 + Op::kOut3 * kTile * 3);
-}
-
-template <class Op>
-int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int ctas_per_sm = 8) {
+int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int ctas_per_sm = 0) {
   if (n < 0) return fail(SO3D_EINVAL, "negative n");
   if (n == 0) return 0;
-  unsigned mask = 0, bit = 0;
-  for (int a = 0; a < Op::kIn9; ++a, ++bit) {
+  int use_tma = 1;
+  for (int a = 0; a < Op::kIn9; ++a) {
     if (!op.in9[a]) return fail(SO3D_EINVAL, "null input pointer");
-    mask |= (aligned16(op.in9[a]) ? 1u : 0u) << bit;
+    use_tma &= aligned16(op.in9[a]);
   }
-  for (int a = 0; a < Op::kIn3; ++a, ++bit) {
+  for (int a = 0; a < Op::kIn3; ++a) {
     if (!op.in3[a]) return fail(SO3D_EINVAL, "null input pointer");
-    mask |= (aligned16(op.in3[a]) ? 1u : 0u) << bit;
+    use_tma &= aligned16(op.in3[a]);
   }
-  for (int a = 0; a < Op::kOut9; ++a, ++bit) mask |= (aligned16(op.out9[a]) ? 1u : 0u) << bit;
-  for (int a = 0; a < Op::kOut3; ++a, ++bit) mask |= (aligned16(op.out3[a]) ? 1u : 0u) << bit;
-  constexpr size_t smem = op_smem<Op>();
+  for (int a = 0; a < Op::kOut9; ++a) use_tma &= aligned16(op.out9[a]);
+  for (int a = 0; a < Op::kOut3; ++a) use_tma &= aligned16(op.out3[a]);
+  constexpr size_t smem = OpLayout<Op>::kSmemBytes;
+  static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
   static bool attr_done = false;
   if (!attr_done && smem > 48 * 1024) {
     cudaFuncSetAttribute(rowwise_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  rowwise_kernel<Op><<<grid_for(n, ctas_per_sm), kTile, smem, (cudaStream_t)stream>>>(op, n, mask);
+  if (ctas_per_sm <= 0) {  // as many CTAs as shared memory allows, at most 8 (2048 threads / SM)
+    ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    ctas_per_sm = ctas_per_sm > 8 ? 8 : (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+  }
+  rowwise_kernel<Op><<<grid_for(n, ctas_per_sm), kTile, smem, (cudaStream_t)stream>>>(op, n, use_tma);
   return check_launch(name);
 }
 
@@ -198,22 +258,29 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
   const float* in3[I3 > 0 ? I3 : 1];                                           \
   float* out9[O9 > 0 ? O9 : 1];                                                \
   float* out3[O3 > 0 ? O3 : 1];
+// ops without CTA-shared tables
+#define SO3D_OP_NO_TAB              \
+  static constexpr int kTab = 0;    \
+  __device__ void setup(float*) const {}
 
 // ------------------------------------------------------------------------------------------------
 // L0 ops
 // ------------------------------------------------------------------------------------------------
 struct LogOp {  // util.py:164-192
   SO3D_OP_ARRAYS(1, 0, 1, 0)
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const { o9[0] = hat(log_vec(a9[0])); }
+  SO3D_OP_NO_TAB
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = hat(log_vec(a9[0])); }
 };
 struct LogVecOp {
   SO3D_OP_ARRAYS(1, 0, 0, 1)
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3) const { o3[0] = log_vec(a9[0]); }
+  SO3D_OP_NO_TAB
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const { o3[0] = log_vec(a9[0]); }
 };
 struct RmatToAaOp {  // util.py:208-219
   SO3D_OP_ARRAYS(1, 0, 0, 1)
+  SO3D_OP_NO_TAB
   float* angle;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const {
     const AxisAngle a = axis_angle(a9[0]);
     o3[0] = a.axis;
     angle[i] = a.theta;
@@ -221,23 +288,27 @@ struct RmatToAaOp {  // util.py:208-219
 };
 struct AaToRmatOp {  // util.py:195-205
   SO3D_OP_ARRAYS(0, 1, 1, 0)
+  SO3D_OP_NO_TAB
   const float* angle;
-  __device__ void row(int64_t i, const Mat3*, const Vec3* a3, Mat3* o9, Vec3*) const { o9[0] = aa_to_rmat(a3[0], angle[i]); }
+  __device__ void row(int64_t i, const Mat3*, const Vec3* a3, Mat3* o9, Vec3*, const float*) const { o9[0] = aa_to_rmat(a3[0], angle[i]); }
 };
 struct ExpVecOp {  // diffusion.py:294
   SO3D_OP_ARRAYS(0, 1, 1, 0)
-  __device__ void row(int64_t, const Mat3*, const Vec3* a3, Mat3* o9, Vec3*) const { o9[0] = exp_vec(a3[0]); }
+  SO3D_OP_NO_TAB
+  __device__ void row(int64_t, const Mat3*, const Vec3* a3, Mat3* o9, Vec3*, const float*) const { o9[0] = exp_vec(a3[0]); }
 };
 struct ScaleOp {  // util.py:349-361
   SO3D_OP_ARRAYS(1, 0, 1, 0)
+  SO3D_OP_NO_TAB
   const float* s;
   int s_stride;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const { o9[0] = scale_rot(a9[0], s[i * s_stride]); }
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = scale_rot(a9[0], s[i * s_stride]); }
 };
 struct RmatToQuatOp {
   SO3D_OP_ARRAYS(1, 0, 0, 0)
+  SO3D_OP_NO_TAB
   float* q;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3*) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3*, const float*) const {
     float qq[4];
     rmat_to_quat(a9[0], qq);
     *reinterpret_cast<float4*>(q + 4 * i) = make_float4(qq[0], qq[1], qq[2], qq[3]);
@@ -245,9 +316,10 @@ struct RmatToQuatOp {
 };
 struct QuatToRmatOp {  // util.py:222-252
   SO3D_OP_ARRAYS(0, 0, 1, 0)
+  SO3D_OP_NO_TAB
   const float* q;
   bool q_vec;
-  __device__ void row(int64_t i, const Mat3*, const Vec3*, Mat3* o9, Vec3*) const {
+  __device__ void row(int64_t i, const Mat3*, const Vec3*, Mat3* o9, Vec3*, const float*) const {
     float4 v;
     if (q_vec) v = __ldcs(reinterpret_cast<const float4*>(q) + i);
     else v = make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
@@ -272,14 +344,16 @@ __device__ __forceinline__ Mat3 mul_op(const Mat3& a, const Mat3& b) {
 template <bool TA, bool TB>
 struct ComposeOp {
   SO3D_OP_ARRAYS(2, 0, 1, 0)
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const { o9[0] = mul_op<TA, TB>(a9[0], a9[1]); }
+  SO3D_OP_NO_TAB
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = mul_op<TA, TB>(a9[0], a9[1]); }
 };
 // one operand shared by all rows (e.g. mean @ R, distributions.py:50)
 template <bool TA, bool TB, bool SharedIsA>
 struct ComposeSharedOp {
   SO3D_OP_ARRAYS(1, 0, 1, 0)
+  SO3D_OP_NO_TAB
   const float* shared;
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const {
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const {
     Mat3 s;
 #pragma unroll
     for (int k = 0; k < 9; ++k) s.m[k] = __ldg(shared + k);
@@ -288,16 +362,18 @@ struct ComposeSharedOp {
 };
 struct RmatDistOp {  // util.py:315-322
   SO3D_OP_ARRAYS(2, 0, 0, 0)
+  SO3D_OP_NO_TAB
   float* out;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3*) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3*, const float*) const {
     out[i] = 1.41421356237f * axis_angle(mul_tn(a9[0], a9[1])).theta;
   }
 };
 struct LerpOp {  // util.py:325-338
   SO3D_OP_ARRAYS(2, 0, 1, 0)
+  SO3D_OP_NO_TAB
   const float* w;
   int w_stride;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const {
     const AxisAngle a = axis_angle(mul_tn(a9[0], a9[1]));
     o9[0] = mul_nn(a9[0], rodrigues(a.axis, w[i * w_stride] * a.theta));
   }
@@ -306,13 +382,15 @@ struct LerpOp {  // util.py:325-338
 // backward ops
 struct LogBwdOp {
   SO3D_OP_ARRAYS(2, 0, 1, 0)
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const { o9[0] = log_bwd(a9[0], a9[1]); }
+  SO3D_OP_NO_TAB
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = log_bwd(a9[0], a9[1]); }
 };
 struct AaToRmatBwdOp {
   SO3D_OP_ARRAYS(1, 1, 0, 1)
+  SO3D_OP_NO_TAB
   const float* angle;
   float* g_angle;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3*, Vec3* o3) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3*, Vec3* o3, const float*) const {
     float ga;
     aa_to_rmat_bwd(a3[0], angle[i], a9[0], &o3[0], &ga);
     g_angle[i] = ga;
@@ -320,17 +398,19 @@ struct AaToRmatBwdOp {
 };
 struct ExpVecBwdOp {
   SO3D_OP_ARRAYS(1, 1, 0, 1)
-  __device__ void row(int64_t, const Mat3* a9, const Vec3* a3, Mat3*, Vec3* o3) const {
+  SO3D_OP_NO_TAB
+  __device__ void row(int64_t, const Mat3* a9, const Vec3* a3, Mat3*, Vec3* o3, const float*) const {
     o3[0] = exp_vec_bwd(a3[0], exp_vec(a3[0]), a9[0]);
   }
 };
 struct ScaleBwdOp {
   // out = exp(hat(s * logvec(R))):  g_s = logvec . Jr^T u,  g_logvec = s Jr^T u, then through the log
   SO3D_OP_ARRAYS(2, 0, 1, 0)
+  SO3D_OP_NO_TAB
   const float* s;
   int s_stride;
   float* g_s;  // per row (caller reduces for a shared scalar)
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const {
     const float sc = s[i * s_stride];
     const Vec3 lv = log_vec(a9[0]);
     const Vec3 w{sc * lv.x, sc * lv.y, sc * lv.z};
@@ -346,13 +426,14 @@ struct ScaleBwdOp {
 // ------------------------------------------------------------------------------------------------
 struct LogpScoreOp {  // distributions.py:74-77 + score, fused with the axis-angle extraction
   SO3D_OP_ARRAYS(1, 0, 0, 1)
+  SO3D_OP_NO_TAB
   const float* eps;
   int eps_stride;
   float* logp;
   float* dlogf;
   int mode, L;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3) const {
-    const AxisAngle a = axis_angle(a9[0]);
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const {
+    const AxisAngleF a = axis_angle_fast(a9[0]);
     float lf, g;
     igso3_logf_g(a.theta, eps[i * eps_stride], mode, L, &lf, &g);
     logp[i] = lf;
@@ -362,9 +443,10 @@ struct LogpScoreOp {  // distributions.py:74-77 + score, fused with 
 };
 struct LogpBwdOp {
   SO3D_OP_ARRAYS(1, 0, 1, 0)
+  SO3D_OP_NO_TAB
   const float* dlogf;
   const float* gout;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const {
     const Mat3& r = a9[0];
     const float vx = r.m[7] - r.m[5], vy = r.m[2] - r.m[6], vz = r.m[3] - r.m[1];
     const float s = 0.5f * sqrtf(fmaf(vx, vx, fmaf(vy, vy, vz * vz)));
@@ -435,175 +517,33 @@ __global__ void __launch_bounds__(256) cdf_table_kernel(const float* __restrict_
   }
 }
 
-// distributions.py:33-51.  kShared: all samples use one CDF row, staged in shared memory.
-template <bool kShared>
-__global__ void __launch_bounds__(kTile) sample_kernel(const float* __restrict__ cdf, const float* __restrict__ loc,
-                                                       const int64_t* __restrict__ row_idx, int64_t row, int64_t rows,
-                                                       const float* __restrict__ u_in, const float* __restrict__ axes_in,
-                                                       uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
-                                                       const float* __restrict__ mean, int mean_stride, float* __restrict__ R,
-                                                       float* __restrict__ angle_out, float* __restrict__ axis_out, int64_t n, bool r_vec) {
-  extern __shared__ float4 smem4[];
-  float* s_out = reinterpret_cast<float*>(smem4);  // kTile * 9
-  float* s_loc = s_out + kTile * 9;                // 1000 (999 used)
-  float* s_cdf = s_loc + 1000;                     // 1000 (999 used) when kShared
+// ------------------------------------------------------------------------------------------------
+// CDF tables in shared memory (shared-row fast paths) and the guide builder
+// ------------------------------------------------------------------------------------------------
+// tab layout: [loc kGrid][trap kGrid][guide kGuideStride u16 = kGuideStride/2 floats (+1)][5 scalars]
+constexpr int kTabLoc = 0, kTabTrap = kGrid, kTabGuide = 2 * kGrid, kTabScal = 2 * kGrid + kGuideStride / 2 + 1;
+constexpr int kTabCdfFloats = kTabScal + 8;
+
+// loc (and, for a shared row, the CDF row and its guide) staged by the whole CTA
+__device__ __forceinline__ void stage_cdf(float* tab, const float* __restrict__ cdf_row, const float* __restrict__ loc) {
   for (int k = threadIdx.x; k < kCdf; k += kTile) {
-    s_loc[k] = loc[k];
-    if (kShared) s_cdf[k] = cdf[row * kCdf + k];
+    tab[kTabLoc + k] = loc[k];
+    if (cdf_row) tab[kTabTrap + k] = cdf_row[k];
   }
   __syncthreads();
-  const int64_t tiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kTile;
-    const int rows_here = (int)((n - row0) < kTile ? (n - row0) : kTile);
-    const int r = threadIdx.x;
-    if (r < rows_here) {
-      const int64_t i = row0 + r;
-      Vec3 axis;
-      float u;
-      if (axes_in) {
-        const float ax = axes_in[3 * i], ay = axes_in[3 * i + 1], az = axes_in[3 * i + 2];
-        const float inv = 1.0f / sqrtf(fmaf(ax, ax, fmaf(ay, ay, az * az)));  // distributions.py:36
-        axis = Vec3{ax * inv, ay * inv, az * inv};
-      }
-      if (!axes_in || !u_in) {
-        const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
-        if (!axes_in) axis = d.axis;
-        u = d.u;
-      }
-      if (u_in) u = u_in[i];
-      const float* trap;
-      if (kShared) {
-        trap = s_cdf;
-      } else {
-        int64_t rr = row_idx[i];
-        rr = rr < 0 ? 0 : (rr >= rows ? rows - 1 : rr);
-        trap = cdf + rr * kCdf;
-      }
-      const float ang = igso3_angle_from_uniform(trap, s_loc, u);
-      Mat3 out = rodrigues(axis, ang);
-      if (mean) {
-        Mat3 m;
-        const float* mp = mean + (mean_stride ? 9 * i : 0);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) m.m[k] = __ldg(mp + k);
-        out = mul_nn(m, out);
-      }
-      sm_put_mat(s_out, r, out);
-      if (angle_out) angle_out[i] = ang;
-      if (axis_out) {
-        axis_out[3 * i] = axis.x;
-        axis_out[3 * i + 1] = axis.y;
-        axis_out[3 * i + 2] = axis.z;
-      }
-    }
-    __syncthreads();
-    tile_store<9>(R + row0 * 9, s_out, rows_here, r_vec);
-    __syncthreads();
+  if (cdf_row) {
+    uint16_t* guide = reinterpret_cast<uint16_t*>(tab + kTabGuide);
+    for (int k = threadIdx.x; k <= kGuide; k += kTile)
+      guide[k] = (uint16_t)cdf_count_le(tab + kTabTrap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
   }
 }
-
-// ------------------------------------------------------------------------------------------------
-// L2: fused forward noising (diffusion.py:339-355) and reverse step (diffusion.py:291-326)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile) q_sample_kernel(const float* __restrict__ x0, const int64_t* __restrict__ t,
-                                                         const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1m_ac, int64_t T,
-                                                         const float* __restrict__ cdf, const float* __restrict__ loc, uint64_t seed,
-                                                         uint64_t rng_offset, uint64_t row_offset, float* __restrict__ x_t,
-                                                         float* __restrict__ target3, float* __restrict__ noise, float* __restrict__ score3,
-                                                         int64_t n, unsigned vecmask) {
-  extern __shared__ float4 smem4[];
-  float* s_in = reinterpret_cast<float*>(smem4);  // kTile*9  x0
-  float* s_xt = s_in + kTile * 9;                 // kTile*9
-  float* s_nz = s_xt + kTile * 9;                 // kTile*9  (noise, optional)
-  float* s_tg = s_nz + kTile * 9;                 // kTile*3  (target)
-  float* s_sc = s_tg + kTile * 3;                 // kTile*3  (score)
-  float* s_loc = s_sc + kTile * 3;                // 1000
-  for (int k = threadIdx.x; k < kCdf; k += kTile) s_loc[k] = loc[k];
-  const int64_t tiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kTile;
-    const int rows = (int)((n - row0) < kTile ? (n - row0) : kTile);
-    tile_load<9>(s_in, x0 + row0 * 9, rows, vecmask & 1u);
-    __syncthreads();
-    const int r = threadIdx.x;
-    if (r < rows) {
-      const int64_t i = row0 + r;
-      int64_t ti = t[i];
-      ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
-      const float eps = __ldg(sqrt_1m_ac + ti);
-      const float sc = __ldg(sqrt_ac + ti);
-      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
-      const float ang = igso3_angle_from_uniform(cdf + ti * kCdf, s_loc, d.u);
-      const Mat3 nz = rodrigues(d.axis, ang);
-      const Mat3 x = sm_mat(s_in, r);
-      sm_put_mat(s_xt, r, mul_nn(scale_rot(x, sc), nz));                      // diffusion.py:344-346
-      if (noise) sm_put_mat(s_nz, r, nz);
-      if (target3) {
-        const float k = ang / eps;                                             // diffusion.py:355
-        sm_put_vec(s_tg, r, Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z});
-      }
-      if (score3) {
-        float lf, g;
-        igso3_logf_g(ang, eps, kAuto, 2000, &lf, &g);
-        sm_put_vec(s_sc, r, Vec3{g * d.axis.x, g * d.axis.y, g * d.axis.z});
-      }
-    }
-    __syncthreads();
-    tile_store<9>(x_t + row0 * 9, s_xt, rows, (vecmask >> 1) & 1u);
-    if (noise) tile_store<9>(noise + row0 * 9, s_nz, rows, (vecmask >> 2) & 1u);
-    if (target3) tile_store<3>(target3 + row0 * 3, s_tg, rows, (vecmask >> 3) & 1u);
-    if (score3) tile_store<3>(score3 + row0 * 3, s_sc, rows, (vecmask >> 4) & 1u);
-  }
+__device__ __forceinline__ float shared_row_angle(const float* tab, float u) {
+  return igso3_angle_from_uniform_guided(tab + kTabTrap, tab + kTabLoc, reinterpret_cast<const uint16_t*>(tab + kTabGuide), u);
 }
-
-struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
-  SO3D_OP_ARRAYS(2, 0, 1, 0)
-  const int64_t* t;
-  const float* sqrt_ac;
-  int64_t T;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*) const {
-    int64_t ti = t[i];
-    ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
-    o9[0] = mul_nn(scale_rot(a9[0], __ldg(sqrt_ac + ti)), a9[1]);
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
-// Pipelined tile movement for the fused HBM-bound kernels (so3d_tma.cuh): persistent CTAs, two
-// shared-memory stages per array, one elected thread driving the TMA engine.
-//   iteration k (tile = blockIdx.x + k gridDim.x, stage = k & 1):
-//     wait full[stage]  ->  every thread copies its row to registers  ->  barrier A (stage may be refilled;
-//     thread 0 has drained the bulk store issued two iterations ago)  ->  thread 0 issues the bulk loads of
-//     tile k+2 into `stage`  ->  arithmetic  ->  results to out[stage]  ->  proxy fence + barrier B  ->
-//     thread 0 issues the bulk store of out[stage].
-// A tile that is not a full, 16-byte aligned tile (ragged tail, unaligned views) is moved cooperatively
-// with ordinary loads/stores at the same points of the schedule.
-// ------------------------------------------------------------------------------------------------
-template <int W>
-__device__ __forceinline__ void coop_load(float* __restrict__ sm, const float* __restrict__ g, int rows) {
-  for (int i = threadIdx.x; i < rows * W; i += kTile) sm[i] = __ldcs(g + i);
-}
-template <int W>
-__device__ __forceinline__ void coop_store(float* __restrict__ g, const float* __restrict__ sm, int rows) {
-  for (int i = threadIdx.x; i < rows * W; i += kTile) __stcs(g + i, sm[i]);
-}
-
-// CDF row, grid angles and the guide of one shared table row, staged in shared memory by the whole CTA.
-struct SharedCdf {
-  float* loc;       // kCdf (+1 pad)
-  float* trap;      // kCdf (+1 pad)
-  uint16_t* guide;  // kGuideStride
-};
-__device__ __forceinline__ void stage_shared_cdf(const SharedCdf& sc, const float* __restrict__ cdf_row, const float* __restrict__ loc) {
-  for (int k = threadIdx.x; k < kCdf; k += kTile) {
-    sc.loc[k] = loc[k];
-    sc.trap[k] = cdf_row[k];
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k <= kGuide; k += kTile)
-    sc.guide[k] = (uint16_t)cdf_count_le(sc.trap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
-  __syncthreads();
+__device__ __forceinline__ float table_row_angle(const float* __restrict__ cdf, const uint16_t* __restrict__ guide, int64_t row,
+                                                 const float* tab, float u) {
+  if (guide) return igso3_angle_from_uniform_guided(cdf + row * kCdf, tab + kTabLoc, guide + row * kGuideStride, u);
+  return igso3_angle_from_uniform(cdf + row * kCdf, tab + kTabLoc, u);
 }
 
 // distributions.py:15-30 companion: guide[row][k] = #{j : trap[row][j] <= k/1024} (so3d_math.cuh).
@@ -616,134 +556,148 @@ __global__ void __launch_bounds__(kTile) cdf_guide_kernel(const float* __restric
     guide[row * kGuideStride + k] = (k <= kGuide) ? (uint16_t)cdf_count_le(s_trap, (float)k * (1.0f / (float)kGuide), 0, kCdf) : (uint16_t)kCdf;
 }
 
-// diffusion.py:291-326, fused reverse step.
-//   kSharedT: the whole batch shares t (the reference's semantics, Q7): schedule scalars are uniform and the
-//             posterior CDF row + guide live in shared memory; otherwise per-row t with table rows read from L2.
-//   kX0:      also write x0_hat.
+// ------------------------------------------------------------------------------------------------
+// L1: sampling (distributions.py:33-51).  kShared: every sample uses one CDF row (scalar eps).
+// ------------------------------------------------------------------------------------------------
+template <bool kShared>
+struct SampleOp {
+  SO3D_OP_ARRAYS(0, 0, 1, 1)
+  static constexpr int kTab = kTabCdfFloats;
+  const float* cdf;
+  const uint16_t* guide;
+  const float* loc;
+  const int64_t* row_idx;
+  int64_t shared_row, rows;
+  const float* u_in;
+  const float* axes_in;
+  uint64_t seed, rng_offset, row_offset;
+  const float* mean;
+  int mean_stride;
+  float* angle_out;
+  __device__ void setup(float* tab) const { stage_cdf(tab, kShared ? cdf + shared_row * kCdf : nullptr, loc); }
+  __device__ void row(int64_t i, const Mat3*, const Vec3*, Mat3* o9, Vec3* o3, const float* tab) const {
+    Vec3 axis;
+    float u;
+    if (axes_in) {
+      const float ax = axes_in[3 * i], ay = axes_in[3 * i + 1], az = axes_in[3 * i + 2];
+      const float inv = 1.0f / sqrtf(fmaf(ax, ax, fmaf(ay, ay, az * az)));  // distributions.py:36
+      axis = Vec3{ax * inv, ay * inv, az * inv};
+    }
+    if (!axes_in || !u_in) {
+      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+      if (!axes_in) axis = d.axis;
+      u = d.u;
+    }
+    if (u_in) u = u_in[i];
+    float ang;
+    if (kShared) {
+      ang = shared_row_angle(tab, u);
+    } else {
+      int64_t rr = row_idx[i];
+      rr = rr < 0 ? 0 : (rr >= rows ? rows - 1 : rr);
+      ang = table_row_angle(cdf, guide, rr, tab, u);
+    }
+    Mat3 out = quat_to_mat_unit(quat_axis_angle(axis, ang));
+    if (mean) {
+      Mat3 m;
+      const float* mp = mean + (mean_stride ? 9 * i : 0);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) m.m[k] = __ldg(mp + k);
+      out = mul_nn(m, out);
+    }
+    o9[0] = out;
+    o3[0] = axis;
+    if (angle_out) angle_out[i] = ang;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// L2: fused forward noising (diffusion.py:339-355) and reverse step (diffusion.py:291-326)
+// ------------------------------------------------------------------------------------------------
+// eps = sqrt_1m_ac[t], noise ~ IGSO3(eps) from cdf row t, x_t = so3_scale(x0, sqrt_ac[t]) @ noise,
+// target = vee(log noise)/eps = angle axis / eps (the noise is built from (axis, angle), so its log is known).
+template <bool kExtra>  // kExtra: the optional noise / score outputs are compiled in (more shared memory per stage)
+struct QSampleOp {
+  SO3D_OP_ARRAYS(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1))  // in: x0;  out9: x_t[, noise];  out3: target[, score]
+  static constexpr int kTab = kTabCdfFloats;
+  const int64_t* t;
+  const float* sqrt_ac;
+  const float* sqrt_1m_ac;
+  int64_t T;
+  const float* cdf;
+  const uint16_t* guide;
+  const float* loc;
+  uint64_t seed, rng_offset, row_offset;
+  __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3* o3, const float* tab) const {
+    int64_t ti = t[i];
+    ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
+    const float eps = __ldg(sqrt_1m_ac + ti);
+    const float sc = __ldg(sqrt_ac + ti);
+    const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+    const float ang = table_row_angle(cdf, guide, ti, tab, d.u);
+    const Quat qn = quat_axis_angle(d.axis, ang);
+    const AxisAngleF ax = axis_angle_fast(a9[0]);
+    o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, sc * ax.theta), qn));  // diffusion.py:344-346
+    if (kExtra && out9[kExtra ? 1 : 0]) o9[kExtra ? 1 : 0] = quat_to_mat_unit(qn);
+    const float k = ang * rcp_approx(eps);                                          // diffusion.py:355
+    o3[0] = Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z};
+    if (kExtra && out3[kExtra ? 1 : 0]) {
+      float lf, g;
+      igso3_logf_g(ang, eps, kAuto, 2000, &lf, &g);
+      o3[kExtra ? 1 : 0] = Vec3{g * d.axis.x, g * d.axis.y, g * d.axis.z};
+    }
+  }
+};
+
+struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
+  SO3D_OP_ARRAYS(2, 0, 1, 0)
+  SO3D_OP_NO_TAB
+  const int64_t* t;
+  const float* sqrt_ac;
+  int64_t T;
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const {
+    int64_t ti = t[i];
+    ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
+    o9[0] = mul_nn(scale_rot(a9[0], __ldg(sqrt_ac + ti)), a9[1]);
+  }
+};
+
+// Reverse step.  kSharedT: the whole batch shares t (the reference's semantics, Q7): the posterior CDF row and
+// its guide live in shared memory; otherwise per-row t with table rows (and the optional guide) read through L2.
 template <bool kSharedT, bool kX0>
-__global__ void __launch_bounds__(kTile) p_step_kernel(const float* __restrict__ x_t, const float* __restrict__ pred3,
-                                                       const int64_t* __restrict__ t, const float* __restrict__ recip,
-                                                       const float* __restrict__ recipm1, const float* __restrict__ coef1,
-                                                       const float* __restrict__ coef2, int64_t T, const float* __restrict__ post_cdf,
-                                                       const uint16_t* __restrict__ post_guide, const float* __restrict__ loc,
-                                                       uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* __restrict__ out,
-                                                       float* __restrict__ x0_hat_out, int64_t n, int use_tma) {
-  extern __shared__ float4 smem4[];
-  float* s_x = reinterpret_cast<float*>(smem4);     // [2][kTile*9]
-  float* s_p = s_x + 2 * kTile * 9;                 // [2][kTile*3]
-  float* s_o = s_p + 2 * kTile * 3;                 // [2][kTile*9]
-  float* s_h = s_o + 2 * kTile * 9;                 // [2][kTile*9] (kX0)
-  float* s_tab = s_h + (kX0 ? 2 * kTile * 9 : 0);
-  SharedCdf sc;
-  sc.loc = s_tab;
-  sc.trap = s_tab + kGrid;
-  sc.guide = reinterpret_cast<uint16_t*>(s_tab + 2 * kGrid);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + 2 * kGrid + kGuideStride / 2 + 1);  // 8-byte aligned: all counts even
-  const int tid = threadIdx.x;
-
-  int64_t t_shared = 0;
-  if (kSharedT) {
-    t_shared = t[0];
-    t_shared = t_shared < 0 ? 0 : (t_shared >= T ? T - 1 : t_shared);
+struct PStepOp {
+  SO3D_OP_ARRAYS(1, 1, (kX0 ? 2 : 1), 0)  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
+  static constexpr int kTab = kTabCdfFloats;
+  const int64_t* t;
+  const float* recip;
+  const float* recipm1;
+  const float* coef1;
+  const float* coef2;
+  int64_t T;
+  const float* post_cdf;
+  const uint16_t* post_guide;
+  const float* loc;
+  uint64_t seed, rng_offset, row_offset;
+  __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
+  __device__ void setup(float* tab) const {
+    if (post_cdf) stage_cdf(tab, kSharedT ? post_cdf + clamp_t(t[0]) * kCdf : nullptr, loc);
   }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
-  }
-  if (post_cdf) {
-    if (kSharedT) {
-      stage_shared_cdf(sc, post_cdf + t_shared * kCdf, loc);
-    } else {
-      for (int k = tid; k < kCdf; k += kTile) sc.loc[k] = loc[k];
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3*, const float* tab) const {
+    const int64_t ti = clamp_t(kSharedT ? t[0] : t[i]);
+    const float k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti);
+    const float k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti);
+    Quat qh;
+    Quat qm = p_mean_quat(a9[0], a3[0], k_recip, k_recipm1, k_c1, k_c2, &qh);
+    if (post_cdf && ti != 0) {                                                     // diffusion.py:320-326
+      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+      const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
+      qm = qmul(qm, quat_axis_angle(d.axis, ang));
     }
+    o9[0] = quat_to_mat_unit(qm);
+    if (kX0) o9[kX0 ? 1 : 0] = quat_to_mat_unit(qh);
   }
-  __syncthreads();
-
-  const int64_t tiles = (n + kTile - 1) / kTile;
-  const int64_t my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  auto tile_rows = [&](int64_t k) -> int {
-    const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTile;
-    return (int)((n - row0) < kTile ? (n - row0) : kTile);
-  };
-  auto issue_load = [&](int64_t k) {  // thread 0 only
-    const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTile;
-    const int st = (int)(k & 1);
-    mbar_expect_tx(&bars[st], kTile * 12 * sizeof(float));
-    bulk_load(s_x + st * kTile * 9, x_t + row0 * 9, kTile * 9 * sizeof(float), &bars[st]);
-    bulk_load(s_p + st * kTile * 3, pred3 + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
-  };
-  if (tid == 0 && use_tma) {
-    if (my_tiles > 0 && tile_rows(0) == kTile) issue_load(0);
-    if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
-  }
-
-  float k_recip = 0.f, k_recipm1 = 0.f, k_c1 = 0.f, k_c2 = 0.f;
-  if (kSharedT) {
-    k_recip = __ldg(recip + t_shared); k_recipm1 = __ldg(recipm1 + t_shared);
-    k_c1 = __ldg(coef1 + t_shared); k_c2 = __ldg(coef2 + t_shared);
-  }
-
-  for (int64_t k = 0; k < my_tiles; ++k) {
-    const int st = (int)(k & 1);
-    const int64_t row0 = (blockIdx.x + k * gridDim.x) * kTile;
-    const int rows = tile_rows(k);
-    const bool tma = use_tma && rows == kTile;
-    float* sx = s_x + st * kTile * 9;
-    float* sp = s_p + st * kTile * 3;
-    float* so = s_o + st * kTile * 9;
-    float* sh = s_h + st * kTile * 9;
-    if (tma) {
-      mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
-    } else {
-      coop_load<9>(sx, x_t + row0 * 9, rows);
-      coop_load<3>(sp, pred3 + row0 * 3, rows);
-      __syncthreads();
-    }
-    const Mat3 x = sm_mat(sx, tid);
-    const Vec3 p = sm_vec(sp, tid);
-    if (tid == 0) bulk_wait_read<1>();  // the store that read out[st] two iterations ago has drained
-    __syncthreads();                    // A
-    if (tid == 0 && use_tma && k + 2 < my_tiles && tile_rows(k + 2) == kTile) issue_load(k + 2);
-
-    if (tid < rows) {
-      const int64_t i = row0 + tid;
-      int64_t ti = t_shared;
-      if (!kSharedT) {
-        ti = t[i];
-        ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
-        k_recip = __ldg(recip + ti); k_recipm1 = __ldg(recipm1 + ti);
-        k_c1 = __ldg(coef1 + ti); k_c2 = __ldg(coef2 + ti);
-      }
-      Quat qh;
-      Quat qm = p_mean_quat(x, p, k_recip, k_recipm1, k_c1, k_c2, &qh);
-      if (post_cdf && ti != 0) {                                                   // diffusion.py:320-326
-        const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
-        float ang;
-        if (kSharedT) ang = igso3_angle_from_uniform_guided(sc.trap, sc.loc, sc.guide, d.u);
-        else if (post_guide) ang = igso3_angle_from_uniform_guided(post_cdf + ti * kCdf, sc.loc, post_guide + ti * kGuideStride, d.u);
-        else ang = igso3_angle_from_uniform(post_cdf + ti * kCdf, sc.loc, d.u);
-        qm = qmul(qm, quat_axis_angle(d.axis, ang));
-      }
-      sm_put_mat(so, tid, quat_to_mat_unit(qm));
-      if (kX0) sm_put_mat(sh, tid, quat_to_mat_unit(qh));
-    }
-    if (tma) {
-      fence_proxy_async();
-      __syncthreads();  // B
-      if (tid == 0) {
-        bulk_store(out + row0 * 9, so, kTile * 9 * sizeof(float));
-        if (kX0) bulk_store(x0_hat_out + row0 * 9, sh, kTile * 9 * sizeof(float));
-        bulk_commit();
-      }
-    } else {
-      __syncthreads();  // B
-      coop_store<9>(out + row0 * 9, so, rows);
-      if (kX0) coop_store<9>(x0_hat_out + row0 * 9, sh, rows);
-    }
-  }
-  if (tid == 0) bulk_wait_read<0>();
-}
+};
 
 }  // namespace
 
@@ -940,7 +894,47 @@ int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_l
   return check_launch("so3d_igso3_cdf_table_f32");
 }
 
-int so3d_igso3_sample_f32(const float* cdf, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+}  // extern "C"
+
+template <bool kShared>
+static int launch_sample(const float* cdf, const uint16_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+                         const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, const float* mean,
+                         int mean_stride, float* R, float* angle, float* axis3, int64_t n, void* stream) {
+  SampleOp<kShared> op;
+  op.out9[0] = R; op.out3[0] = axis3;
+  op.cdf = cdf; op.guide = guide; op.loc = loc; op.row_idx = row_idx; op.shared_row = row; op.rows = rows; op.u_in = u; op.axes_in = axes3;
+  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset; op.mean = mean; op.mean_stride = mean_stride; op.angle_out = angle;
+  return launch_rowwise(op, n, stream, "so3d_igso3_sample_f32");
+}
+
+template <bool kExtra>
+static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T, const float* cdf,
+                           const uint16_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
+                           float* target3, float* noise, float* score3, int64_t n, void* stream) {
+  QSampleOp<kExtra> op;
+  op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
+  if (kExtra) { op.out9[kExtra ? 1 : 0] = noise; op.out3[kExtra ? 1 : 0] = score3; }
+  op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
+  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  return launch_rowwise(op, n, stream, "so3d_q_sample_f32");
+}
+
+template <bool kSharedT, bool kX0>
+static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
+                         const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint16_t* post_guide,
+                         const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
+                         int64_t n, void* stream) {
+  PStepOp<kSharedT, kX0> op;
+  op.in9[0] = x_t; op.in3[0] = pred3; op.out9[0] = out;
+  if (kX0) op.out9[kX0 ? 1 : 0] = x0_hat_out;
+  op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.T = T;
+  op.post_cdf = post_cdf; op.post_guide = post_guide; op.loc = loc; op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  return launch_rowwise(op, n, stream, "so3d_p_sample_f32");
+}
+
+extern "C" {
+
+int so3d_igso3_sample_f32(const float* cdf, const uint16_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
                           const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                           const float* mean, int mean_stride, float* R, float* angle, float* axis3, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
@@ -949,30 +943,21 @@ int so3d_igso3_sample_f32(const float* cdf, const float* loc, int64_t rows, cons
   SO3D_REQUIRE(rows > 0, "so3d_igso3_sample_f32: empty table");
   SO3D_REQUIRE(row_idx || (row >= 0 && row < rows), "so3d_igso3_sample_f32: row out of range");
   SO3D_REQUIRE(mean_stride == 0 || mean_stride == 1, "mean_stride must be 0 or 1");
-  const size_t smem = sizeof(float) * (kTile * 9 + 2000);
-  const int grid = grid_for(n, 8);
   if (row_idx)
-    sample_kernel<false><<<grid, kTile, smem, (cudaStream_t)stream>>>(cdf, loc, row_idx, 0, rows, u, axes3, seed, rng_offset, row_offset,
-                                                                       mean, mean_stride, R, angle, axis3, n, aligned16(R));
-  else
-    sample_kernel<true><<<grid, kTile, smem, (cudaStream_t)stream>>>(cdf, loc, nullptr, row, rows, u, axes3, seed, rng_offset, row_offset,
-                                                                      mean, mean_stride, R, angle, axis3, n, aligned16(R));
-  return check_launch("so3d_igso3_sample_f32");
+    return launch_sample<false>(cdf, guide, loc, rows, row_idx, 0, u, axes3, seed, rng_offset, row_offset, mean, mean_stride, R, angle, axis3, n, stream);
+  return launch_sample<true>(cdf, guide, loc, rows, nullptr, row, u, axes3, seed, rng_offset, row_offset, mean, mean_stride, R, angle, axis3, n, stream);
 }
 
 int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
-                      const float* cdf, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
-                      float* target3, float* noise, float* score3, int64_t n, void* stream) {
+                      const float* cdf, const uint16_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
+                      uint64_t row_offset, float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
   if (n == 0) return 0;
   SO3D_REQUIRE(x0 && t && sqrt_ac && sqrt_1m_ac && cdf && loc && x_t, "so3d_q_sample_f32: null pointer");
   SO3D_REQUIRE(T > 0, "so3d_q_sample_f32: T must be positive");
-  const unsigned mask = (aligned16(x0) ? 1u : 0u) | (aligned16(x_t) ? 2u : 0u) | (aligned16(noise) ? 4u : 0u) |
-                        (aligned16(target3) ? 8u : 0u) | (aligned16(score3) ? 16u : 0u);
-  const size_t smem = sizeof(float) * (kTile * (9 * 3 + 3 * 2) + 1000);
-  q_sample_kernel<<<grid_for(n, 6), kTile, smem, (cudaStream_t)stream>>>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, loc, seed, rng_offset,
-                                                                          row_offset, x_t, target3, noise, score3, n, mask);
-  return check_launch("so3d_q_sample_f32");
+  if (noise || score3)
+    return launch_q_sample<true>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, noise, score3, n, stream);
+  return launch_q_sample<false>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, noise, score3, n, stream);
 }
 
 int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt_ac, int64_t T, const float* noise, float* x_t,
@@ -992,27 +977,6 @@ int so3d_igso3_cdf_guide_u16(const float* cdf, int64_t rows, uint16_t* guide_out
   cdf_guide_kernel<<<(int)rows, kTile, 0, (cudaStream_t)stream>>>(cdf, guide_out);
   return check_launch("so3d_igso3_cdf_guide_u16");
 }
-
-}  // extern "C"
-
-template <bool kSharedT, bool kX0>
-static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
-                         const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint16_t* post_guide,
-                         const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
-                         int64_t n, void* stream) {
-  const size_t smem = sizeof(float) * (size_t)(2 * kTile * (9 + 3 + 9 + (kX0 ? 9 : 0)) + 2 * kGrid + kGuideStride / 2 + 1) + 2 * sizeof(uint64_t);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(p_step_kernel<kSharedT, kX0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  const int use_tma = aligned16(x_t) && aligned16(pred3) && aligned16(out) && (!kX0 || aligned16(x0_hat_out));
-  p_step_kernel<kSharedT, kX0><<<grid_for(n, kX0 ? 3 : 4), kTile, smem, (cudaStream_t)stream>>>(
-      x_t, pred3, t, recip, recipm1, coef1, coef2, T, post_cdf, post_guide, loc, seed, rng_offset, row_offset, out, x0_hat_out, n, use_tma);
-  return check_launch("so3d_p_sample_f32");
-}
-
-extern "C" {
 
 int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, int t_stride, const float* recip,
                       const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,

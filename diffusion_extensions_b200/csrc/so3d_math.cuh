@@ -611,19 +611,17 @@ SO3D_HD double igso3_closed_f64(double t, double eps, int quirks) {
   return val;
 }
 
-// phi(w) = 1/w - cot(w/2)/2  (the part of d log f / dw that cancels against the 1/w of the bracket)
-SO3D_HD float half_cot_gap(float w) {
-  if (w < 0.5f) {
-    const float w2 = w * w;
-    // w/12 + w^3/720 + w^5/30240 + w^7/1209600
-    return w * fmaf(w2, fmaf(w2, fmaf(w2, 8.2671958e-7f, 3.3068783e-5f), 1.3888889e-3f), 8.3333333e-2f);
-  }
-  float sh, ch;
-  sincos_f(0.5f * w, &sh, &ch);
-  return 1.0f / w - 0.5f * ch / sh;
+// e^x through MUFU.EX2 (2 ulp + the rounding of x log2 e: relative error ~1.2e-7 |x|; every use below has
+// either |x| small or a result that is negligible against 1)
+SO3D_HD float exp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return fast_ex2(x * 1.4426950408889634f);
+#else
+  return expf(x);
+#endif
 }
 
-// fp32 closed form: log f and g = d log f / d omega, stable for eps <= ~1 (3 images: 2e-7 rel).
+// fp32 closed form: log f and g = d log f / d omega, stable for eps <= 1 (3 images: <= 1e-6 rel, measured).
 //   f = sqrt(pi) v^-3/2 e^{v/4} e^{-w^2/4v} B(w) / (2 sin(w/2)),
 //   B = w - (w - 2pi) E1 - (w + 2pi) E2,  E1 = e^{-pi(pi-w)/v}, E2 = e^{-pi(pi+w)/v}
 //   g = -w/(2v) + (B'/B - 1/w) + (1/w - cot(w/2)/2)
@@ -633,14 +631,18 @@ SO3D_HD float half_cot_gap(float w) {
 //   (wB'-B)/w^2 = [ -(2pi + y w) dm + 2 pi y sm ] / w^2
 // For y < 1/2 the sinh/cosh Taylor series remove the E1 - E2 and y cosh y - sinh y cancellations and
 // every division by w, so w = 0 needs no special case (limit: B/w = 1 - 2E + 4 pi^2 E / v, g = 0).
+// Division-free: reciprocals are MUFU.RCP (1/v with one Newton step, since it multiplies the large w^2/4);
+// sin/cos of w/2 come from one sincos_fast; the three logarithms are merged into one.
 SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out) {
   const float v = eps * eps;
-  const float iv = 1.0f / v;
+  float iv = rcp_approx(v);
+  iv = iv * fmaf(-v, iv, 2.0f);
   const float piv = kPi * iv;
   const float y = piv * w;
+  const float rw = rcp_approx(fmaxf(w, 1e-30f));
   float bw, ratio;  // B/w and (wB' - B)/(w B)
   if (y < 0.5f) {
-    const float E = expf(-kPi * piv);
+    const float E = exp_fast(-kPi * piv);
     const float y2 = y * y;
     const float sinhc = fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.7557319e-6f, 1.9841270e-4f), 8.3333333e-3f), 1.6666667e-1f), 1.0f);
     const float coshy = fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.4801587e-5f, 1.3888889e-3f), 4.1666667e-2f), 0.5f), 1.0f);
@@ -648,27 +650,30 @@ SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out)
     const float dm_w = 2.0f * E * piv * sinhc;  // (E1 - E2)/w
     bw = (1.0f - 2.0f * E * coshy) + kTwoPi * dm_w;
     const float n2 = fmaf(-piv * w, dm_w, 2.0f * kTwoPi * E * piv * piv * p3);  // (wB' - B)/w^2
-    ratio = n2 / bw;
+    ratio = n2 * rcp_approx(bw);
   } else {
     // pi - w with pi carried as hi + lo: near w = pi the image weight is e^{-(pi/v)(pi - w)} and an 8.7e-8
     // error in fp32 pi would be amplified by pi/v
-    const float e1 = expf(-piv * ((kPi - w) + (-8.742278e-8f)));
-    const float e2 = expf(-piv * (kPi + w));
+    const float e1 = exp_fast(-piv * ((kPi - w) + (-8.742278e-8f)));
+    const float e2 = exp_fast(-piv * (kPi + w));
     const float dm = e1 - e2, sm = e1 + e2;
-    bw = (1.0f - sm) + kTwoPi * dm / w;
-    ratio = (fmaf(-(kTwoPi + y * w), dm, kTwoPi * y * sm)) / (w * w * bw);
+    bw = (1.0f - sm) + kTwoPi * dm * rw;
+    ratio = (fmaf(-(kTwoPi + y * w), dm, kTwoPi * y * sm)) * (rw * rw) * rcp_approx(bw);
   }
-  // w / (2 sin(w/2))
-  float wr;
-  if (w < 0.1f) {
-    const float w2 = w * w;
-    wr = fmaf(w2, fmaf(w2, 1.2152778e-3f, 4.1666667e-2f), 1.0f);
-  } else {
-    wr = w / (2.0f * sinf(0.5f * w));
-  }
-  const float lead = 0.5723649429247001f /* log sqrt(pi) */ - 1.5f * logf(v) + 0.25f * v - 0.25f * w * w * iv;
-  *logf_out = lead + logf(bw * wr);
-  *g_out = fmaf(-0.5f * w, iv, ratio + half_cot_gap(w));
+  float sh, ch;
+  sincos_fast(0.5f * w, &sh, &ch);
+  const float w2 = w * w;
+  // w / (2 sin(w/2))  and  phi(w) = 1/w - cot(w/2)/2 (the part of g that cancels against the 1/w of the bracket)
+  const float rsh = rcp_approx(fmaxf(sh, 1e-30f));
+  const float wr = (w < 0.1f) ? fmaf(w2, fmaf(w2, 1.2152778e-3f, 4.1666667e-2f), 1.0f) : 0.5f * w * rsh;
+  // w/12 + w^3/720 + w^5/30240 + w^7/1209600
+  const float phi = (w < 0.5f) ? w * fmaf(w2, fmaf(w2, fmaf(w2, 8.2671958e-7f, 3.3068783e-5f), 1.3888889e-3f), 8.3333333e-2f)
+                               : fmaf(-0.5f * ch, rsh, rw);
+  // v^-3/2 from MUFU.RSQ with one Newton step
+  float r = rsqrt_approx(v);
+  r = r * fmaf(-0.5f * v * r, r, 1.5f);
+  *logf_out = fmaf(0.25f, v, -0.25f * w2 * iv) + logf(1.7724538509055159f * (r * r * r) * (bw * wr));
+  *g_out = fmaf(-0.5f * w, iv, ratio + phi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -783,11 +788,11 @@ SO3D_HD int igso3_series_live_terms(float eps, int L) {
 }
 
 enum IgsoMode { kSeries = 0, kClosed = 1, kAuto = 2, kSeriesAdaptive = 3 };
-constexpr float kAutoSeriesEps = 0.6f;  // auto: series (<= ~18 live terms) at or above, closed form below
+constexpr float kAutoSeriesEps = 1.0f;  // auto: closed form up to eps = 1 (3 images: <= 1e-6 rel, measured), series (<= 12 live terms) above
 
 // log f_eps(w) and g = d log f / dw by the requested evaluator.
 SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, float* g_out) {
-  if (mode == kClosed || (mode == kAuto && eps < kAutoSeriesEps)) {
+  if (mode == kClosed || (mode == kAuto && eps <= kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
   } else {
     int terms = (mode == kSeries) ? L : igso3_series_live_terms(eps, L);

@@ -126,7 +126,7 @@ class SO3Diffusion(nn.Module):
         if noise is None:
             fwd, _, _ = self.tables()
             return ops.q_sample_fused(x_start, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, fwd,
-                                      row_offset=self.row_offset, want_target=False)["x_t"]
+                                      row_offset=self.row_offset, want_target=False, guide=self.guides()[0])["x_t"]
         return ops.q_sample_given(x_start, t, self.sqrt_alphas_cumprod, noise)
 
     def noise_and_target(self, x_start, t, want_noise=False, want_score=False):
@@ -134,7 +134,8 @@ class SO3Diffusion(nn.Module):
         (diffusion.py:349-355)."""
         fwd, _, _ = self.tables()
         return ops.q_sample_fused(x_start, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, fwd,
-                                  row_offset=self.row_offset, want_target=True, want_noise=want_noise, want_score=want_score)
+                                  row_offset=self.row_offset, want_target=True, want_noise=want_noise, want_score=want_score,
+                                  guide=self.guides()[0])
 
     # ---- reverse process ----------------------------------------------------------------------
     def predict_start_from_noise(self, x_t, t, noise):

@@ -15,7 +15,7 @@ surface, CUDA float32 only, every method one fused sm_100a kernel:
     autograd (distributions.py:186-190).
 
 ``mode`` selects the density evaluator: "closed" (the reference's 3-image closed form in its stable
-rewrite), "series" (L-term truncated series), "auto" (default: closed form below eps = 0.6, series
+rewrite), "series" (L-term truncated series), "auto" (default: closed form up to eps = 1, series
 above; <= 1e-5 relative everywhere), "series_adaptive".
 ``reference_quirks=True`` builds the CDF table from the reference's literal overflowing expression
 (density zeroed beyond omega > 709 eps^2/pi) so that samples match the reference at

@@ -300,8 +300,14 @@ def igso3_cdf_guide(cdf):
     return out
 
 
+def _check_guide(guide, rows, name):
+    if guide is not None and (guide.dtype != torch.int16 or guide.numel() != rows * GUIDE_STRIDE or not guide.is_contiguous() or not guide.is_cuda):
+        raise ValueError(f"{name} must be the contiguous CUDA int16 (rows, {GUIDE_STRIDE}) tensor returned by igso3_cdf_guide")
+    return guide
+
+
 def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, rng_offset=None, row_offset=0,
-                 mean=None, want_angle=False, want_axis=False):
+                 mean=None, want_angle=False, want_axis=False, guide=None):
     """Draw rotations of batch shape `shape` from the CDF rows in `cdf` (rows, 999).
     row_idx: int64 tensor of shape `shape` (one table row per sample) or None -> all use `row`.
     u / axes: optional explicit draws.  -> R (*shape,3,3)[, angle (*shape)][, axis (*shape,3)]"""
@@ -329,7 +335,8 @@ def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, 
     R = torch.empty(*shape, 3, 3, dtype=torch.float32, device=dev)
     angle = torch.empty(shape, dtype=torch.float32, device=dev) if want_angle else None
     axis_out = torch.empty(*shape, 3, dtype=torch.float32, device=dev) if want_axis else None
-    call("so3d_igso3_sample_f32", ptr(cdf), ptr(trap_loc), cdf.numel() // CDF_POINTS, ptr(row_idx), int(row), ptr(u), ptr(axes),
+    _check_guide(guide, cdf.numel() // CDF_POINTS, "guide")
+    call("so3d_igso3_sample_f32", ptr(cdf), ptr(guide), ptr(trap_loc), cdf.numel() // CDF_POINTS, ptr(row_idx), int(row), ptr(u), ptr(axes),
          seed, rng_offset, int(row_offset), ptr(mean), mean_stride, ptr(R), ptr(angle), ptr(axis_out), n, device=dev)
     outs = [R]
     if want_angle:
@@ -343,7 +350,7 @@ def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, 
 # L2: fused diffusion steps
 # ---------------------------------------------------------------------------------------------
 def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, row_offset=0,
-                   want_target=True, want_noise=False, want_score=False):
+                   want_target=True, want_noise=False, want_score=False, guide=None):
     """-> dict(x_t, target, noise, score) (absent entries are None)."""
     x0, bs, n = _rows9(x0, "x_start")
     dev = x0.device
@@ -361,7 +368,8 @@ def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, 
     target = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_target else None
     noise = torch.empty_like(x0) if want_noise else None
     score = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_score else None
-    call("so3d_q_sample_f32", ptr(x0), ptr(t), ptr(sqrt_ac), ptr(sqrt_1m_ac), T, ptr(cdf), ptr(trap_loc), seed, rng_offset,
+    _check_guide(guide, T, "guide")
+    call("so3d_q_sample_f32", ptr(x0), ptr(t), ptr(sqrt_ac), ptr(sqrt_1m_ac), T, ptr(cdf), ptr(guide), ptr(trap_loc), seed, rng_offset,
          int(row_offset), ptr(x_t), ptr(target), ptr(noise), ptr(score), n, device=dev)
     return {"x_t": x_t, "target": target, "noise": noise, "score": score}
 
@@ -396,8 +404,7 @@ def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, se
         post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
         if post_cdf.numel() != T * CDF_POINTS:
             raise ValueError("posterior cdf table must have one row per timestep")
-        if post_guide is not None and (post_guide.dtype != torch.int16 or post_guide.numel() != T * GUIDE_STRIDE or not post_guide.is_contiguous()):
-            raise ValueError("posterior guide must be the contiguous int16 (T, 1026) tensor of igso3_cdf_guide")
+        _check_guide(post_guide, T, "post_guide")
         _, _, trap_loc = cdf_grid(dev)
         if seed is None or rng_offset is None:
             seed, rng_offset = rng.next()

@@ -44,7 +44,7 @@ extern "C" {
 /* evaluator for the IGSO(3) density (mode argument) */
 #define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms                    */
 #define SO3D_MODE_CLOSED 1          /* 3-image closed form, distributions.py:53-72, stable rewrite         */
-#define SO3D_MODE_AUTO 2            /* closed form for eps < 0.6, series (live terms only) otherwise       */
+#define SO3D_MODE_AUTO 2            /* closed form for eps <= 1, series (live terms only) above             */
 #define SO3D_MODE_SERIES_ADAPTIVE 3 /* series, skipping terms whose fp32 weight is exactly 0 (same result) */
 
 int so3d_version(void);
@@ -110,13 +110,14 @@ int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_l
  * identical index.  guide_out: rows x SO3D_GUIDE_STRIDE. */
 int so3d_igso3_cdf_guide_u16(const float* cdf, int64_t rows, uint16_t* guide_out, void* stream);
 /* distributions.py:33-51 sample: R = mean @ rot(axis, angle(u)).
- *   cdf: table rows x 999;  loc: 999 grid angles;  row_idx: int64[n] row per sample, or NULL with
+ *   cdf: table rows x 999;  guide: so3d_igso3_cdf_guide_u16(cdf) or NULL (only used with row_idx; the shared-row
+ *   path builds its guide in shared memory);  loc: 999 grid angles;  row_idx: int64[n] row per sample, or NULL with
  *   `row` = the single shared row (scalar-eps path, staged in shared memory).
  *   u / axes3: optional explicit draws (u in [0,1), axes un-normalised like randn) -- when NULL
  *   they come from Philox(seed, row_offset + i, rng_offset).
  *   mean: optional 3x3 (mean_stride 0) or n x 9 (mean_stride 1) left factor.
  *   outputs: R (n x 9), and optionally the drawn angle[n] / unit axis3[n x 3]. */
-int so3d_igso3_sample_f32(const float* cdf, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+int so3d_igso3_sample_f32(const float* cdf, const uint16_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
                           const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset,
                           uint64_t row_offset, const float* mean, int mean_stride, float* R, float* angle,
                           float* axis3, int64_t n, void* stream);
@@ -125,10 +126,10 @@ int so3d_igso3_sample_f32(const float* cdf, const float* loc, int64_t rows, cons
 /* diffusion.py:339-346 q_sample + :348-355 p_losses target, fused:
  *   eps = sqrt_1m_ac[t], noise ~ IGSO3(eps) from cdf row t, x_t = so3_scale(x0, sqrt_ac[t]) @ noise,
  *   target = vee(log noise) / eps  (nullable), noise (nullable), score of the noise under
- *   IGSO3(eps) (nullable, auto evaluator).  t: int64[n] in [0, T). */
+ *   IGSO3(eps) (nullable, auto evaluator).  t: int64[n] in [0, T).  guide: so3d_igso3_cdf_guide_u16(cdf) or NULL. */
 int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
-                      const float* cdf, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
-                      float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream);
+                      const float* cdf, const uint16_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
+                      uint64_t row_offset, float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream);
 /* q_sample with the noise supplied by the caller (diffusion.py:339-346 with noise != None). */
 int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt_ac, int64_t T, const float* noise,
                             float* x_t, int64_t n, void* stream);
