@@ -118,6 +118,25 @@ class IsotropicGaussianSO3(Distribution):
         return score
 
     @torch.no_grad()
+    def log_prob_and_score_host(self, rotations, out_logp=None, out_score=None, chunk_rows=1 << 20, pipeline=None):
+        """Host-buffer entry point: `rotations` (n,3,3) is a (preferably pinned) HOST float32 tensor; returns HOST
+        tensors logp (n,1) and score (n,3).  H2D copy, kernel and D2H copy are overlapped chunk by chunk
+        (ops.HostScorePipeline).  If this distribution has per-row eps, a HOST copy of eps is streamed alongside."""
+        n = rotations.shape[0]
+        if rotations.is_cuda:
+            raise ValueError("log_prob_and_score_host takes HOST tensors; use log_prob_and_score for device tensors")
+        per_row = self.eps.numel() == n and n > 1
+        if pipeline is None:
+            pipeline = ops.HostScorePipeline(self.eps.device, chunk_rows=chunk_rows, per_row_eps=per_row)
+        if out_logp is None:
+            out_logp = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        if out_score is None:
+            out_score = torch.empty(n, 3, dtype=torch.float32, pin_memory=True)
+        heps = self._host_eps if per_row and getattr(self, "_host_eps", None) is not None else (self.eps.cpu() if per_row else self.eps)
+        pipeline.run(rotations.contiguous(), heps, out_logp.reshape(n), out_score, mode=self.eval_mode, L=self.series_terms)
+        return out_logp.reshape(n, 1), out_score
+
+    @torch.no_grad()
     def log_prob_and_score(self, rotations):
         logp, score, _ = ops.igso3_logp_score(rotations, self.eps, mode=self.eval_mode, L=self.series_terms, want_score=True)
         return logp[..., None], score

@@ -266,6 +266,76 @@ def igso3_logp_bwd(R, dlogf, gout):
     return out
 
 
+class HostScorePipeline:
+    """Streams HOST (pinned) rotations / eps through the fused log-density + score kernel and returns HOST
+    results, overlapping the three legs chunk by chunk on separate CUDA streams:
+
+        H2D copy of chunk k+1   ||   kernel on chunk k   ||   D2H copy of the results of chunk k-1
+
+    With 40 B in and 16 B out per evaluation the PCIe link (not the kernel) bounds the end-to-end rate, so the
+    pipeline runs at the speed of the slowest leg instead of their sum.  Device staging buffers are a ring of
+    `depth` chunks allocated once; nothing synchronises with the host until `run` returns (it waits for the
+    last D2H copy, because the caller is about to read host memory)."""
+
+    def __init__(self, device, chunk_rows=1 << 20, depth=3, per_row_eps=True):
+        self.device = torch.device(device)
+        self.chunk, self.depth = int(chunk_rows), int(depth)
+        d = self.device
+        self.dR = [torch.empty(self.chunk, 3, 3, device=d) for _ in range(depth)]
+        self.deps = [torch.empty(self.chunk, device=d) for _ in range(depth)] if per_row_eps else None
+        self.dlogp = [torch.empty(self.chunk, device=d) for _ in range(depth)]
+        self.dscore = [torch.empty(self.chunk, 3, device=d) for _ in range(depth)]
+        self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_k = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.launches = 0
+
+    def run(self, hR, heps, h_logp, h_score, mode="series", L=2000, wait=True):
+        """hR (n,3,3), heps (n,) or a scalar tensor/float, h_logp (n,), h_score (n,3): pinned host float32 tensors."""
+        for name, t in (("rotations", hR), ("logp", h_logp), ("score", h_score)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous float32 HOST tensor")
+        n = hR.shape[0]
+        per_row = isinstance(heps, torch.Tensor) and heps.numel() == n and n > 1
+        if per_row and self.deps is None:
+            raise ValueError("pipeline was created with per_row_eps=False")
+        eps_shared = None if per_row else torch.as_tensor(heps, dtype=torch.float32).reshape(1).to(self.device)
+        m = _mode(mode)
+        cur = torch.cuda.current_stream(self.device)
+        for st in (self.s_in, self.s_k, self.s_out):
+            st.wait_stream(cur)
+        for c, lo in enumerate(range(0, n, self.chunk)):
+            hi = min(n, lo + self.chunk)
+            rows, b = hi - lo, c % self.depth
+            with torch.cuda.stream(self.s_in):
+                if c >= self.depth:
+                    self.s_in.wait_event(self.ev_k[b])      # the kernel that read this staging slot is done
+                self.dR[b][:rows].copy_(hR[lo:hi], non_blocking=True)
+                if per_row:
+                    self.deps[b][:rows].copy_(heps[lo:hi], non_blocking=True)
+                self.ev_in[b].record(self.s_in)
+            with torch.cuda.stream(self.s_k):
+                self.s_k.wait_event(self.ev_in[b])
+                if c >= self.depth:
+                    self.s_k.wait_event(self.ev_out[b])     # the D2H copy that read this result slot is done
+                e = self.deps[b] if per_row else eps_shared
+                call("so3d_igso3_logp_score_f32", ptr(self.dR[b]), ptr(e), 1 if per_row else 0, ptr(self.dlogp[b]), ptr(self.dscore[b]), None,
+                     rows, m, int(L), device=self.device)
+                self.launches += 1
+                self.ev_k[b].record(self.s_k)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_k[b])
+                h_logp[lo:hi].copy_(self.dlogp[b][:rows], non_blocking=True)
+                h_score[lo:hi].copy_(self.dscore[b][:rows], non_blocking=True)
+                self.ev_out[b].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_k)
+        if wait:
+            self.s_out.synchronize()
+        return h_logp, h_score
+
+
 _grid_cache = {}
 
 

@@ -1,0 +1,158 @@
+"""Multi-GPU harness: one process per GPU, batch rows partitioned across ranks.
+
+Every op of the SO(3) hot path is row-independent, so the data path needs NO collective: each
+rank owns a contiguous shard of the global batch and runs the fused kernels on it.  What does cross ranks:
+
+  * the loss / statistics reductions (a handful of floats per step) -- `all_reduce_stats`, `global_mean`;
+  * the gradient all-reduce of the small denoiser network -- stock `DistributedDataParallel` (`wrap_denoiser`).
+
+Both go through `torch.distributed` (NCCL over NVLink on the GPU box; gloo in the CPU test tier).  The
+Philox counter of every random draw is the GLOBAL row index (`row_offset` of the shard + local row), so a
+sharded run draws exactly the numbers a single-GPU run would: results are bit-identical for any world size.
+
+The reference has no distributed code at all; this module is the B200-side addition behind the
+same `SO3Diffusion` API (`process.row_offset` is the only coupling).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+# ---------------------------------------------------------------------------------------------
+# process group
+# ---------------------------------------------------------------------------------------------
+def init_from_env(backend=None, device=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world).
+    With WORLD_SIZE unset or 1 nothing is initialised."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl" and device is not None:
+            kwargs["device_id"] = torch.device(device)
+        dist.init_process_group(backend, **kwargs)
+    return rank, world
+
+
+def world_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ---------------------------------------------------------------------------------------------
+# partitioning
+# ---------------------------------------------------------------------------------------------
+def shard_bounds(n, rank, world):
+    """Contiguous shard [lo, hi) of n rows for `rank`: the first n % world ranks get one extra row."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"invalid rank/world: {rank}/{world}")
+    base, extra = divmod(int(n), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_rows(x, rank=None, world=None):
+    """This rank's contiguous slice of a globally indexed tensor (dim 0) and its global row offset."""
+    if rank is None or world is None:
+        rank, world = world_info()
+    lo, hi = shard_bounds(x.shape[0], rank, world)
+    return x[lo:hi], lo
+
+
+def attach(process, n_global, rank=None, world=None):
+    """Point a SO3Diffusion at this rank's shard of an n_global-row batch: sets `process.row_offset` (the
+    global index of the shard's first row, which keys the Philox draws) and returns (lo, hi)."""
+    if rank is None or world is None:
+        rank, world = world_info()
+    lo, hi = shard_bounds(n_global, rank, world)
+    process.row_offset = lo
+    return lo, hi
+
+
+# ---------------------------------------------------------------------------------------------
+# reductions (the only collectives of the path)
+# ---------------------------------------------------------------------------------------------
+def all_reduce_stats(stats):
+    """Sum a small 1-D tensor of statistics over all ranks (in place; no-op for a single process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def global_mean(local_sum, local_count):
+    """Mean over the global batch from per-shard sums and counts: one all-reduce of two numbers.
+    `local_sum` is a 0-d tensor (kept on its device, no host sync), `local_count` an int."""
+    buf = torch.stack([local_sum.detach().to(torch.float32).reshape(()), torch.tensor(float(local_count), device=local_sum.device)])
+    all_reduce_stats(buf)
+    return buf[0] / buf[1]
+
+
+def global_loss(per_row_sq_err):
+    """The reference's `F.mse_loss(pred, target)` (diffusion.py:362) over the GLOBAL batch: shards may be
+    ragged, so the mean is sum / count reduced over ranks, not a mean of per-rank means."""
+    return global_mean(per_row_sq_err.sum(), per_row_sq_err.numel())
+
+
+def wrap_denoiser(module, device=None):
+    """DistributedDataParallel around the denoiser (gradient all-reduce, bucketed by DDP); identity for a
+    single process.  The SO(3) kernels themselves hold no parameters."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return module
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    if device is not None and torch.device(device).type == "cuda":
+        return DDP(module.to(device), device_ids=[torch.device(device).index])
+    return DDP(module)
+
+
+def rotation_statistics(x):
+    """Per-shard sufficient statistics of a batch of rotations for global reporting:
+    [count, sum of rotation angle, sum of angle^2, sum of the 9 matrix entries] -> all-reduced."""
+    tr = x[..., 0, 0] + x[..., 1, 1] + x[..., 2, 2]
+    ang = torch.acos(torch.clamp((tr - 1) * 0.5, -1.0, 1.0))
+    stats = torch.cat([torch.tensor([float(ang.numel())], device=x.device), ang.sum().reshape(1), (ang * ang).sum().reshape(1),
+                       x.reshape(-1, 9).sum(0)]).to(torch.float32)
+    all_reduce_stats(stats)
+    n = stats[0]
+    return {"count": n, "mean_angle": stats[1] / n, "std_angle": torch.sqrt(torch.clamp(stats[2] / n - (stats[1] / n) ** 2, min=0)),
+            "mean_matrix": (stats[3:] / n).reshape(3, 3)}
+
+
+# ---------------------------------------------------------------------------------------------
+# sharded drivers
+# ---------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_sharded(process, n_global, init="igso3_1", steps=None):
+    """BASELINE config 3: n_global particles partitioned over the ranks, each rank running the fused reverse
+    step on its shard for all timesteps.  No communication inside the loop.  Returns the local shard."""
+    lo, hi = attach(process, n_global)
+    if steps is None:
+        return process.p_sample_loop((hi - lo,), init=init)
+    from . import ops
+    from .distributions import IsotropicGaussianSO3
+
+    device = process.betas.device
+    x = IsotropicGaussianSO3(torch.ones([], device=device)).sample((hi - lo,), row_offset=lo)
+    _, _, t_range = process.tables()
+    for i in reversed(range(process.num_timesteps - steps, process.num_timesteps)):
+        x = process.p_sample(x, t_range[i:i + 1])
+    return x
+
+
+def train_step_sharded(process, x0_local, optimizer):
+    """One data-parallel training step on this rank's shard: fused noising + target, denoiser forward/backward
+    (DDP all-reduces the gradients), optimizer step; returns the GLOBAL mean loss (one 2-float all-reduce)."""
+    optimizer.zero_grad(set_to_none=True)
+    b = x0_local.shape[0]
+    t = torch.randint(0, process.num_timesteps, (b,), device=x0_local.device)
+    fused = process.noise_and_target(x0_local, t)
+    pred = process.denoise_fn(fused["x_t"], t)
+    sq = (pred - fused["target"]) ** 2
+    loss = sq.mean()  # DDP averages gradients over ranks: equal shard sizes give the global-mean gradient
+    loss.backward()
+    optimizer.step()
+    return global_loss(sq.detach())

@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # 2. full capture of the dominant kernel (series logp+score) at a reduced n so the ~40 replays stay short
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:LogpScoreOp -s 3 -c 1 -f -o gpurun_out/prof_series \
     python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-extra --n 4194304 > gpurun_out/ncu_series_stdout.log 2>&1
-# 3. full capture of the HBM-bound fused kernels (reverse step, forward noising, auto evaluator)
-ncu --set full --clock-control none --import-source on -k 'regex:p_sample_kernel|q_sample_kernel' -s 6 -c 2 -f -o gpurun_out/prof_steps \
+# 3. full capture of the HBM-bound fused kernels (reverse step, forward noising)
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:PStepOp|QSampleOp' -s 6 -c 2 -f -o gpurun_out/prof_steps \
     python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_steps_stdout.log 2>&1
 ls -la gpurun_out

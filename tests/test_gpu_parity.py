@@ -597,3 +597,74 @@ def test_full_size_properties(dx, cuda_device):
     g = (score * axis).sum(-1)
     assert torch.isfinite(logp).all() and (g <= 1e-6).all()   # density decreases with the angle
     assert ((score - g[:, None] * axis).norm(dim=-1)).max().item() < 1e-6 * g.abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------
+# sharding invariance, guide tables, host-buffer pipeline
+# ---------------------------------------------------------------------------------------------
+def test_shard_invariance_of_random_draws(dx, cuda_device):
+    """A batch split into shards (each passing its global row offset, as parallel.attach does) draws the
+    same noise as the unsplit batch: results are bit-identical for any number of GPUs."""
+    n = 5000
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    x0 = dev(rand_rots(n, 51)[0], cuda_device)
+    t = torch.randint(0, 1000, (n,), device=cuda_device)
+    fwd, post, _ = p.tables()
+    fg, pg = p.guides()
+    args = (p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd)
+    full = dx.ops.q_sample_fused(x0, t, *args, seed=77, rng_offset=5, row_offset=0, guide=fg)
+    cuts = [0, 1234, 1234 + 256 * 7, n]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        part = dx.ops.q_sample_fused(x0[lo:hi], t[lo:hi], *args, seed=77, rng_offset=5, row_offset=lo, guide=fg)
+        assert torch.equal(part["x_t"], full["x_t"][lo:hi]) and torch.equal(part["target"], full["target"][lo:hi])
+    pred = torch.randn(n, 3, device=cuda_device) * 0.3
+    sched = (p.sqrt_recip_alphas_cumprod, p.sqrt_recipm1_alphas_cumprod, p.posterior_mean_coef1, p.posterior_mean_coef2)
+    t1 = torch.tensor([500], device=cuda_device)
+    fullp = dx.ops.p_sample_fused(x0, pred, t1, *sched, post_cdf=post, seed=78, rng_offset=9, row_offset=0)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        part = dx.ops.p_sample_fused(x0[lo:hi], pred[lo:hi], t1, *sched, post_cdf=post, seed=78, rng_offset=9, row_offset=lo)
+        assert torch.equal(part, fullp[lo:hi])
+
+
+def test_guide_table_lookup_is_exact(dx, cuda_device):
+    """The guided inverse-CDF search returns exactly the index of the full search: sampling with and
+    without the guide table gives bit-identical rotations, for per-row table rows and for the shared row."""
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    fwd, post, _ = p.tables()
+    fg, pg = p.guides()
+    g = fg.cpu().numpy().astype(np.int64) & 0xFFFF
+    trap = fwd.cpu().numpy()
+    for row in (0, 17, 500, 999):
+        want = np.searchsorted(trap[row], np.arange(1025, dtype=np.float32) / np.float32(1024), side="right")
+        assert np.array_equal(g[row, :1025], want)
+    n = 1 << 16
+    rows = torch.randint(0, 1000, (n,), device=cuda_device)
+    u = torch.rand(n, device=cuda_device)
+    u[:4] = torch.tensor([0.0, 1.0 - 2 ** -24, 0.5, 2 ** -24])
+    a = dx.ops.igso3_sample(post, (n,), row_idx=rows, u=u, seed=1, rng_offset=0, want_angle=True)
+    b = dx.ops.igso3_sample(post, (n,), row_idx=rows, u=u, seed=1, rng_offset=0, want_angle=True, guide=pg)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # shared-row path (guide built in shared memory) against the per-row path pointed at the same row
+    c = dx.ops.igso3_sample(post, (n,), row=321, u=u, seed=1, rng_offset=0, want_angle=True)
+    d = dx.ops.igso3_sample(post, (n,), row_idx=torch.full((n,), 321, device=cuda_device), u=u, seed=1, rng_offset=0, want_angle=True)
+    assert torch.equal(c[1], d[1]) and torch.equal(c[0], d[0])
+
+
+def test_host_score_pipeline(dx, cuda_device):
+    """ops.HostScorePipeline (pinned host in -> host out, H2D / kernel / D2H overlapped) returns exactly
+    what the device-resident call returns, for ragged sizes and for repeated runs on the same staging ring."""
+    for n, chunk in ((100_003, 1 << 14), (1 << 15, 1 << 15), (5, 1 << 10)):
+        R, eps = eset(n, 61)
+        hR = torch.from_numpy(R).pin_memory()
+        heps = torch.from_numpy(eps).pin_memory()
+        hl = torch.empty(n).pin_memory()
+        hs = torch.empty(n, 3).pin_memory()
+        pipe = dx.ops.HostScorePipeline(cuda_device, chunk_rows=chunk, depth=3)
+        d = dx.IsotropicGaussianSO3(dev(eps, cuda_device), mode="auto")
+        logp, score = d.log_prob_and_score(dev(R, cuda_device))
+        for _ in range(2):
+            hl.zero_(); hs.zero_()
+            pipe.run(hR, heps, hl, hs, mode="auto")
+            assert torch.equal(hl, logp[:, 0].cpu()) and torch.equal(hs, score.cpu())
+        l2, s2 = d.log_prob_and_score_host(hR, chunk_rows=chunk)
+        assert torch.equal(l2, logp.cpu()) and torch.equal(s2, score.cpu())

@@ -1,0 +1,124 @@
+"""World-size-2 tests of the multi-GPU host logic (diffusion_extensions_b200/parallel.py) on the gloo
+backend, CPU only: partitioning, the loss / statistics reductions, DDP of the denoiser, and the
+shard-invariance of the counter-based draws (through the host build of the kernels' Philox code)."""
+import ctypes
+import os
+import socket
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffusion_extensions_b200 import parallel as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _host_math():
+    src = os.path.join(HERE, "host_math", "host_math.cpp")
+    lib = os.path.join(HERE, "host_math", "_host_math.so")
+    hdr = os.path.join(HERE, "..", "diffusion_extensions_b200", "csrc", "so3d_math.cuh")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-march=native", "-shared", "-fPIC", "-o", lib, src])
+    return ctypes.CDLL(lib)
+
+
+def _draw(hm, seed, row0, offset, n):
+    axis = np.empty((n, 3), np.float32)
+    u = np.empty(n, np.float32)
+    F = ctypes.POINTER(ctypes.c_float)
+    hm.hm_draw(ctypes.c_ulonglong(seed), ctypes.c_ulonglong(row0), ctypes.c_ulonglong(offset), axis.ctypes.data_as(F), u.ctypes.data_as(F), ctypes.c_long(n))
+    return axis, u
+
+
+def _worker(rank, world, port, n, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    r, w = P.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world) and P.world_info() == (rank, world)
+    torch.manual_seed(0)  # same global data on every rank
+    x = torch.randn(n, 3)
+    y = torch.randn(n, 3)
+    # ---- partitioning: contiguous, disjoint, covers [0, n)
+    xs, lo = P.shard_rows(x)
+    lo2, hi2 = P.shard_bounds(n, rank, world)
+    assert lo == lo2 and xs.shape[0] == hi2 - lo2
+    sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([xs.shape[0]]))
+    assert sum(int(s) for s in sizes) == n
+
+    # ---- global loss == single-process mse_loss even with ragged shards (diffusion.py:362)
+    ys, _ = P.shard_rows(y)
+    loss = P.global_loss((xs - ys) ** 2)
+    want = torch.nn.functional.mse_loss(x, y)
+    assert abs(float(loss) - float(want)) < 1e-6
+
+    # ---- rotation statistics over the global batch
+    q = torch.randn(n, 4)
+    q = q / q.norm(dim=-1, keepdim=True)
+    a, b, c, d = q.unbind(-1)
+    R = torch.stack([1 - 2 * (c * c + d * d), 2 * (b * c - d * a), 2 * (b * d + c * a),
+                     2 * (b * c + d * a), 1 - 2 * (b * b + d * d), 2 * (c * d - b * a),
+                     2 * (b * d - c * a), 2 * (c * d + b * a), 1 - 2 * (b * b + c * c)], -1).reshape(n, 3, 3)
+    st = P.rotation_statistics(P.shard_rows(R)[0])
+    ang = torch.acos(torch.clamp((R.diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2, -1, 1))
+    assert int(st["count"]) == n and abs(float(st["mean_angle"]) - float(ang.mean())) < 1e-5
+    assert torch.allclose(st["mean_matrix"], R.mean(0), atol=1e-5)
+
+    # ---- DDP on the denoiser: averaged shard gradients == full-batch gradient for equal shards
+    m = n - n % world
+    net = torch.nn.Sequential(torch.nn.Linear(3, 16), torch.nn.SiLU(), torch.nn.Linear(16, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(3, 16), torch.nn.SiLU(), torch.nn.Linear(16, 3))
+    ref.load_state_dict(net.state_dict())
+    ddp = P.wrap_denoiser(net)
+    lo3, hi3 = P.shard_bounds(m, rank, world)
+    ((ddp(x[lo3:hi3]) - y[lo3:hi3]) ** 2).mean().backward()
+    ((ref(x[:m]) - y[:m]) ** 2).mean().backward()
+    for pa, pb in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(pa.grad, pb.grad, atol=1e-6)
+
+    # ---- counter-based draws do not depend on the sharding: shard draws == rows [lo, hi) of the global draw
+    hm = _host_math()
+    full_axis, full_u = _draw(hm, 1234, 0, 7, n)
+    axis, u = _draw(hm, 1234, lo, 7, hi2 - lo2)
+    assert np.array_equal(axis, full_axis[lo2:hi2]) and np.array_equal(u, full_u[lo2:hi2])
+
+    # ---- attach(): row_offset bookkeeping on a stand-in process object
+    class Proc:
+        row_offset = 0
+
+    p = Proc()
+    assert P.attach(p, n) == (lo2, hi2) and p.row_offset == lo2
+    dist.barrier()
+    with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
+        f.write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1001, 64])
+def test_world2_gloo(tmp_path, n):
+    _host_math()  # build once, not concurrently in the workers
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_shard_bounds_properties():
+    for n in (0, 1, 7, 8, 1000, 2 ** 24):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = P.shard_bounds(n, r, world)
+                assert lo == prev and hi >= lo and hi - lo in (n // world, n // world + 1)
+                prev = hi
+            assert prev == n
+    with pytest.raises(ValueError):
+        P.shard_bounds(10, 2, 2)
