@@ -13,6 +13,7 @@
 // No library calls, no tensor cores (nothing here is GEMM shaped).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/so3d.h"
@@ -238,14 +239,19 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
   for (int a = 0; a < Op::kOut3; ++a) use_tma &= aligned16(op.out3[a]);
   constexpr size_t smem = OpLayout<Op>::kSmemBytes;
   static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
-    cudaFuncSetAttribute(rowwise_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+  // Persistent grid = exactly the CTAs that are resident at once (registers and shared memory both count): with
+  // a static partition of the tiles, a grid larger than one wave leaves the last, partial wave's SMs idle.
+  static int resident = 0;  // per Op instantiation
+  if (resident == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rowwise_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowwise_kernel<Op>, kTile, smem) != cudaSuccess || occ < 1) occ = 1;
+    resident = occ;
   }
-  if (ctas_per_sm <= 0) {  // as many CTAs as shared memory allows, at most 8 (2048 threads / SM)
-    ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    ctas_per_sm = ctas_per_sm > 8 ? 8 : (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+  if (ctas_per_sm <= 0 || ctas_per_sm > resident) ctas_per_sm = resident;
+  if (const char* e = getenv("SO3D_CTAS_PER_SM")) {  // tuning aid: cap the persistent grid (CTAs per SM)
+    const int v = atoi(e);
+    if (v > 0 && v < ctas_per_sm) ctas_per_sm = v;
   }
   rowwise_kernel<Op><<<grid_for(n, ctas_per_sm), kTile, smem, (cudaStream_t)stream>>>(op, n, use_tma);
   return check_launch(name);
@@ -424,6 +430,7 @@ struct ScaleBwdOp {
 // ------------------------------------------------------------------------------------------------
 // L1: IGSO(3)
 // ------------------------------------------------------------------------------------------------
+template <int kMode>
 struct LogpScoreOp {  // distributions.py:74-77 + score, fused with the axis-angle extraction
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
@@ -431,11 +438,11 @@ struct LogpScoreOp {  // distributions.py:74-77 + score, fused with 
   int eps_stride;
   float* logp;
   float* dlogf;
-  int mode, L;
+  int L;
   __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const {
     const AxisAngleF a = axis_angle_fast(a9[0]);
     float lf, g;
-    igso3_logf_g(a.theta, eps[i * eps_stride], mode, L, &lf, &g);
+    igso3_logf_g_t<kMode>(a.theta, eps[i * eps_stride], L, &lf, &g);
     logp[i] = lf;
     if (dlogf) dlogf[i] = g;
     o3[0] = Vec3{g * a.axis.x, g * a.axis.y, g * a.axis.z};
@@ -644,7 +651,7 @@ struct QSampleOp {
     o3[0] = Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z};
     if (kExtra && out3[kExtra ? 1 : 0]) {
       float lf, g;
-      igso3_logf_g(ang, eps, kAuto, 2000, &lf, &g);
+      igso3_logf_g_t<kAuto>(ang, eps, 2000, &lf, &g);
       o3[kExtra ? 1 : 0] = Vec3{g * d.axis.x, g * d.axis.y, g * d.axis.z};
     }
   }
@@ -847,6 +854,22 @@ int so3d_scale_bwd_f32(const float* R, const float* s, int s_stride, const float
   return launch_rowwise(op, n, stream, "so3d_scale_bwd_f32");
 }
 
+}  // extern "C"
+
+template <int kMode>
+static int launch_logp_score(const float* R, const float* eps, int eps_stride, float* logp, float* score3, float* dlogf, int64_t n, int L,
+                             void* stream) {
+  LogpScoreOp<kMode> op;
+  op.in9[0] = R; op.eps = eps; op.eps_stride = eps_stride; op.logp = logp; op.dlogf = dlogf; op.out3[0] = score3;
+  op.L = L;
+  // The series streams its constant table through the uniform datapath; measured on B200 it runs fastest with few
+  // resident warps (3 CTAs/SM: 1.54e9 evals/s, 8 CTAs/SM: 1.26e9): warps at fewer distinct table positions.
+  const int ctas = (kMode == kSeries || kMode == kSeriesAdaptive) ? 3 : 0;
+  return launch_rowwise(op, n, stream, "so3d_igso3_logp_score_f32", ctas);
+}
+
+extern "C" {
+
 static int check_mode(int mode, int L) {
   if (mode < 0 || mode > 3) return fail(SO3D_EINVAL, "mode must be SO3D_MODE_{SERIES,CLOSED,AUTO,SERIES_ADAPTIVE}");
   if (mode != SO3D_MODE_CLOSED && (L < 1 || L > 2896)) return fail(SO3D_EINVAL, "series truncation L must be in [1, 2896]");
@@ -871,10 +894,12 @@ int so3d_igso3_logp_score_f32(const float* R, const float* eps, int eps_stride, 
   SO3D_REQUIRE(n == 0 || (R && eps && logp), "so3d_igso3_logp_score_f32: null pointer");
   SO3D_REQUIRE(eps_stride == 0 || eps_stride == 1, "eps_stride must be 0 or 1");
   if (int rc = check_mode(mode, L)) return rc;
-  LogpScoreOp op;
-  op.in9[0] = R; op.eps = eps; op.eps_stride = eps_stride; op.logp = logp; op.dlogf = dlogf; op.out3[0] = score3;
-  op.mode = mode; op.L = L;
-  return launch_rowwise(op, n, stream, "so3d_igso3_logp_score_f32");
+  switch (mode) {
+    case SO3D_MODE_SERIES: return launch_logp_score<kSeries>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
+    case SO3D_MODE_CLOSED: return launch_logp_score<kClosed>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
+    case SO3D_MODE_AUTO: return launch_logp_score<kAuto>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
+    default: return launch_logp_score<kSeriesAdaptive>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
+  }
 }
 
 int so3d_igso3_logp_bwd_f32(const float* R, const float* dlogf, const float* gout, float* gR, int64_t n, void* stream) {

@@ -790,20 +790,36 @@ SO3D_HD int igso3_series_live_terms(float eps, int L) {
 enum IgsoMode { kSeries = 0, kClosed = 1, kAuto = 2, kSeriesAdaptive = 3 };
 constexpr float kAutoSeriesEps = 1.0f;  // auto: closed form up to eps = 1 (3 images: <= 1e-6 rel, measured), series (<= 12 live terms) above
 
-// log f_eps(w) and g = d log f / dw by the requested evaluator.
-SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, float* g_out) {
-  if (mode == kClosed || (mode == kAuto && eps <= kAutoSeriesEps)) {
+// log f_eps(w) and g = d log f / dw by the evaluator kMode (a template parameter, so that a kernel contains one
+// evaluator only and the exact-L series keeps a provably warp-uniform trip count: its table operands must stay
+// uniform-register loads).
+template <int kMode>
+SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g_out) {
+  if (kMode == kClosed || (kMode == kAuto && eps <= kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
   } else {
-    int terms = (mode == kSeries) ? L : igso3_series_live_terms(eps, L);
+    int terms = L;
+    if (kMode != kSeries) {
+      terms = igso3_series_live_terms(eps, L);
 #if defined(__CUDA_ARCH__)
-    // keep the trip count (and with it the constant-table index) warp-uniform: a lane-varying index would
-    // serialise the constant loads.  The extra terms have weight exactly 0, so the result is unchanged.
-    if (mode != kSeries) terms = __reduce_max_sync(__activemask(), terms);
+      // keep the trip count (and with it the constant-table index) the same across the warp: a lane-varying index
+      // would serialise the constant loads.  The extra terms have weight exactly 0, so the result is unchanged.
+      terms = __reduce_max_sync(__activemask(), terms);
 #endif
+    }
     const SeriesAcc a = igso3_series_terms(w, eps, terms);
     *logf_out = logf(2.0f * a.F);
     *g_out = a.dF / a.F;
+  }
+}
+
+// runtime-mode dispatch (host harness, non-critical call sites)
+SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, float* g_out) {
+  switch (mode) {
+    case kSeries: igso3_logf_g_t<kSeries>(w, eps, L, logf_out, g_out); break;
+    case kClosed: igso3_logf_g_t<kClosed>(w, eps, L, logf_out, g_out); break;
+    case kAuto: igso3_logf_g_t<kAuto>(w, eps, L, logf_out, g_out); break;
+    default: igso3_logf_g_t<kSeriesAdaptive>(w, eps, L, logf_out, g_out); break;
   }
 }
 
