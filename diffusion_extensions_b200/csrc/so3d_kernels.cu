@@ -13,6 +13,7 @@
 // No library calls, no tensor cores (nothing here is GEMM shaped).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -106,23 +107,58 @@ __device__ __forceinline__ void sm_put_vec(float* sm, int r, Vec3 v) {
   sm[r * 3 + 2] = v.z;
 }
 
+// Optional software pipeline for per-row scalars and table look-ups (latency-bound ops): an Op may define
+//   struct Pre1; struct Pre2;
+//   __device__ Pre1 prefetch1(int64_t i) const;               -- issued two tiles ahead (e.g. t[i], eps[i])
+//   __device__ Pre2 prefetch2(int64_t i, const Pre1&) const;  -- issued one tile ahead (loads that depend on Pre1)
+//   __device__ void row(int64_t i, const Pre2&, a9, a3, o9, o3, tab) const;
+// so that by the time a row is processed its dependent global/L2 loads have had a whole tile time to land.
+template <class Op, class = void>
+struct HasPre : std::false_type {};
+template <class Op>
+struct HasPre<Op, std::void_t<typename Op::Pre1, typename Op::Pre2>> : std::true_type {};
+struct NoPre {};
+template <class Op, bool = HasPre<Op>::value>
+struct PreTypes {
+  using P1 = NoPre;
+  using P2 = NoPre;
+};
+template <class Op>
+struct PreTypes<Op, true> {
+  using P1 = typename Op::Pre1;
+  using P2 = typename Op::Pre2;
+};
+
 template <class Op>
 struct OpLayout {
   static constexpr int kInWords = Op::kIn9 * 9 + Op::kIn3 * 3;     // per row
   static constexpr int kOutWords = Op::kOut9 * 9 + Op::kOut3 * 3;  // per row
-  static constexpr int kStageFloats = kTile * (kInWords + kOutWords);
+  static constexpr int kOutStages = Op::kOutStages;               // 2: output tile double-buffered; 1: single (more CTAs/SM)
+  static constexpr int kInFloats = kTile * kInWords;              // per stage
+  static constexpr int kOutFloats = kTile * kOutWords;            // per stage
   static constexpr int kTabFloats = (Op::kTab + 3) & ~3;
-  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kStageFloats + kTabFloats) + 2 * sizeof(uint64_t);
+  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kInFloats + kOutStages * kOutFloats + kTabFloats) + 2 * sizeof(uint64_t);
+};
+
+// register cap per op: minimum resident CTAs per SM promised to the compiler (0 = no cap)
+template <class Op, class = void>
+struct OpMinCtas {
+  static constexpr int value = 1;
+};
+template <class Op>
+struct OpMinCtas<Op, std::void_t<decltype(Op::kMinCtas)>> {
+  static constexpr int value = Op::kMinCtas;
 };
 
 template <class Op>
-__global__ void __launch_bounds__(kTile) rowwise_kernel(const Op op, const int64_t n, const int use_tma) {
+__global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(const Op op, const int64_t n, const int use_tma) {
   extern __shared__ float4 smem4[];
   constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
   using Lay = OpLayout<Op>;
   float* smem = reinterpret_cast<float*>(smem4);
-  // stage s: [in9 arrays][in3 arrays][out9 arrays][out3 arrays]; every array starts 16-byte aligned (1 KiB multiples)
-  float* s_tab = smem + 2 * Lay::kStageFloats;
+  // [in stage 0][in stage 1][out stage 0][out stage 1 if double-buffered]; every array starts 16-byte aligned
+  float* s_out = smem + 2 * Lay::kInFloats;
+  float* s_tab = s_out + Lay::kOutStages * Lay::kOutFloats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -144,7 +180,7 @@ __global__ void __launch_bounds__(kTile) rowwise_kernel(const Op op, const int64
     if (kI9 + kI3 == 0) return;
     const int64_t row0 = tile_row0(k);
     const int st = (int)(k & 1);
-    float* base = smem + st * Lay::kStageFloats;
+    float* base = smem + st * Lay::kInFloats;
     mbar_expect_tx(&bars[st], (uint32_t)(kTile * Lay::kInWords * sizeof(float)));
 #pragma unroll
     for (int a = 0; a < kI9; ++a) bulk_load(base + a * kTile * 9, op.in9[a] + row0 * 9, kTile * 9 * sizeof(float), &bars[st]);
@@ -156,14 +192,27 @@ __global__ void __launch_bounds__(kTile) rowwise_kernel(const Op op, const int64
     if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
   }
 
+  // software pipeline registers (empty structs for ops without prefetch hooks)
+  constexpr bool kPre = HasPre<Op>::value;
+  typename PreTypes<Op>::P1 p1_next{};   // Pre1 of tile k+1
+  typename PreTypes<Op>::P2 p2_cur{};    // Pre2 of tile k
+  auto pre_row = [&](int64_t k) -> int64_t {  // this thread's row of tile k, clamped into range (result unused if beyond)
+    const int64_t i = tile_row0(k) + tid;
+    return i < n ? i : n - 1;
+  };
+  if constexpr (kPre) {
+    if (my_tiles > 0) p2_cur = op.prefetch2(pre_row(0), op.prefetch1(pre_row(0)));
+    if (my_tiles > 1) p1_next = op.prefetch1(pre_row(1));
+  }
+
   for (int64_t k = 0; k < my_tiles; ++k) {
     const int st = (int)(k & 1);
     const int64_t row0 = tile_row0(k);
     const int rows = tile_rows(k);
     const bool tma = use_tma && rows == kTile;
-    float* s_i9 = smem + st * Lay::kStageFloats;
+    float* s_i9 = smem + st * Lay::kInFloats;
     float* s_i3 = s_i9 + kI9 * kTile * 9;
-    float* s_o9 = s_i3 + kI3 * kTile * 3;
+    float* s_o9 = s_out + (Lay::kOutStages == 2 ? st : 0) * Lay::kOutFloats;
     float* s_o3 = s_o9 + kO9 * kTile * 9;
     if (kI9 + kI3 > 0) {
       if (tma) {
@@ -182,14 +231,29 @@ __global__ void __launch_bounds__(kTile) rowwise_kernel(const Op op, const int64
     for (int a = 0; a < kI9; ++a) a9[a] = sm_mat(s_i9 + a * kTile * 9, tid);
 #pragma unroll
     for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, tid);
-    if (tid == 0) bulk_wait_read<1>();  // the stores that read out[st] two iterations ago have drained
-    __syncthreads();                    // A
+    if (Lay::kOutStages == 2 && tid == 0) bulk_wait_read<1>();  // the stores that read out[st] two iterations ago have drained
+    __syncthreads();                                            // A
     if (tid == 0 && use_tma && k + 2 < my_tiles && tile_rows(k + 2) == kTile) issue_load(k + 2);
 
+    Mat3 o9[kO9 > 0 ? kO9 : 1];
+    Vec3 o3[kO3 > 0 ? kO3 : 1];
+    if constexpr (kPre) {
+      typename PreTypes<Op>::P2 p2_next{};
+      typename PreTypes<Op>::P1 p1_next2{};
+      if (k + 1 < my_tiles) p2_next = op.prefetch2(pre_row(k + 1), p1_next);  // loads land during this tile's arithmetic
+      if (k + 2 < my_tiles) p1_next2 = op.prefetch1(pre_row(k + 2));
+      if (tid < rows) op.row(row0 + tid, p2_cur, a9, a3, o9, o3, s_tab);
+      p2_cur = p2_next;
+      p1_next = p1_next2;
+    } else {
+      if (tid < rows) op.row(row0 + tid, a9, a3, o9, o3, s_tab);
+    }
+    if (Lay::kOutStages == 1 && kO9 + kO3 > 0) {
+      // single output stage: the previous tile's stores had the whole arithmetic phase to drain
+      if (tid == 0) bulk_wait_read<0>();
+      __syncthreads();  // C
+    }
     if (tid < rows) {
-      Mat3 o9[kO9 > 0 ? kO9 : 1];
-      Vec3 o3[kO3 > 0 ? kO3 : 1];
-      op.row(row0 + tid, a9, a3, o9, o3, s_tab);
 #pragma unroll
       for (int a = 0; a < kO9; ++a) sm_put_mat(s_o9 + a * kTile * 9, tid, o9[a]);
 #pragma unroll
@@ -258,12 +322,15 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
 }
 
 // dummy arrays for ops without a given kind of operand (zero-length arrays are not allowed)
-#define SO3D_OP_ARRAYS(I9, I3, O9, O3)                                         \
+#define SO3D_OP_ARRAYS(I9, I3, O9, O3) SO3D_OP_ARRAYS_S(I9, I3, O9, O3, 2)
+// S = output stages: 2 (double-buffered) or 1 (less shared memory -> more resident CTAs, for latency-bound ops)
+#define SO3D_OP_ARRAYS_S(I9, I3, O9, O3, S)                                    \
   static constexpr int kIn9 = I9, kIn3 = I3, kOut9 = O9, kOut3 = O3;           \
   const float* in9[I9 > 0 ? I9 : 1];                                           \
   const float* in3[I3 > 0 ? I3 : 1];                                           \
   float* out9[O9 > 0 ? O9 : 1];                                                \
-  float* out3[O3 > 0 ? O3 : 1];
+  float* out3[O3 > 0 ? O3 : 1];                                                \
+  static constexpr int kOutStages = S;
 // ops without CTA-shared tables
 #define SO3D_OP_NO_TAB              \
   static constexpr int kTab = 0;    \
@@ -547,20 +614,27 @@ __device__ __forceinline__ void stage_cdf(float* tab, const float* __restrict__ 
 __device__ __forceinline__ float shared_row_angle(const float* tab, float u) {
   return igso3_angle_from_uniform_guided(tab + kTabTrap, tab + kTabLoc, reinterpret_cast<const uint16_t*>(tab + kTabGuide), u);
 }
-__device__ __forceinline__ float table_row_angle(const float* __restrict__ cdf, const uint16_t* __restrict__ guide, int64_t row,
+__device__ __forceinline__ float table_row_angle(const float* __restrict__ cdf, const uint32_t* __restrict__ guide, int64_t row,
                                                  const float* tab, float u) {
-  if (guide) return igso3_angle_from_uniform_guided(cdf + row * kCdf, tab + kTabLoc, guide + row * kGuideStride, u);
+  if (guide) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(guide) + row * kGuide + guide_bucket(u));  // one 16-byte record
+    const GuideRec rec{w.x, __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w)};
+    return igso3_angle_from_record(cdf + row * kCdf, tab + kTabLoc, rec, u);
+  }
   return igso3_angle_from_uniform(cdf + row * kCdf, tab + kTabLoc, u);
 }
 
-// distributions.py:15-30 companion: guide[row][k] = #{j : trap[row][j] <= k/1024} (so3d_math.cuh).
-__global__ void __launch_bounds__(kTile) cdf_guide_kernel(const float* __restrict__ cdf, uint16_t* __restrict__ guide) {
+// distributions.py:15-30 companion: the 1024 guide records of every CDF row (so3d_math.cuh).
+__global__ void __launch_bounds__(kTile) cdf_guide_kernel(const float* __restrict__ cdf, uint32_t* __restrict__ guide) {
   __shared__ float s_trap[kGrid];
   const int64_t row = blockIdx.x;
   for (int k = threadIdx.x; k < kCdf; k += kTile) s_trap[k] = cdf[row * kCdf + k];
   __syncthreads();
-  for (int k = threadIdx.x; k < kGuideStride; k += kTile)
-    guide[row * kGuideStride + k] = (k <= kGuide) ? (uint16_t)cdf_count_le(s_trap, (float)k * (1.0f / (float)kGuide), 0, kCdf) : (uint16_t)kCdf;
+  uint4* out = reinterpret_cast<uint4*>(guide) + row * kGuide;
+  for (int k = threadIdx.x; k < kGuide; k += kTile) {
+    const GuideRec r = make_guide_rec(s_trap, k);
+    out[k] = make_uint4(r.lohi, __float_as_uint(r.tm1), __float_as_uint(r.t0), __float_as_uint(r.tp1));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,7 +645,7 @@ struct SampleOp {
   SO3D_OP_ARRAYS(0, 0, 1, 1)
   static constexpr int kTab = kTabCdfFloats;
   const float* cdf;
-  const uint16_t* guide;
+  const uint32_t* guide;
   const float* loc;
   const int64_t* row_idx;
   int64_t shared_row, rows;
@@ -625,27 +699,55 @@ struct SampleOp {
 // target = vee(log noise)/eps = angle axis / eps (the noise is built from (axis, angle), so its log is known).
 template <bool kExtra>  // kExtra: the optional noise / score outputs are compiled in (more shared memory per stage)
 struct QSampleOp {
-  SO3D_OP_ARRAYS(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1))  // in: x0;  out9: x_t[, noise];  out3: target[, score]
-  static constexpr int kTab = kTabCdfFloats;
+  // per-row table rows are dependent L2 accesses: latency-bound, so favour resident CTAs over output double-buffering
+  SO3D_OP_ARRAYS_S(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1), 1)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
+  static constexpr int kTab = kGrid;  // loc only
+  static constexpr int kMinCtas = 5;  // cap registers at 51: the software pipeline must not cost occupancy
   const int64_t* t;
   const float* sqrt_ac;
   const float* sqrt_1m_ac;
   int64_t T;
   const float* cdf;
-  const uint16_t* guide;
+  const uint32_t* guide;
   const float* loc;
   uint64_t seed, rng_offset, row_offset;
   __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3* o3, const float* tab) const {
-    int64_t ti = t[i];
-    ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
-    const float eps = __ldg(sqrt_1m_ac + ti);
-    const float sc = __ldg(sqrt_ac + ti);
-    const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
-    const float ang = table_row_angle(cdf, guide, ti, tab, d.u);
+  // software pipeline: t two tiles ahead; the draw (a pure function of the global row index), the schedule
+  // scalars and the guide record one tile ahead -- the row itself then touches no dependent global memory
+  // except in the rare multi-point bucket.
+  struct Pre1 {
+    int64_t t;
+  };
+  struct Pre2 {
+    int ti;
+    float eps, sc;
+    NoiseDraw d;
+    uint4 rec;
+  };
+  __device__ Pre1 prefetch1(int64_t i) const { return Pre1{t[i]}; }
+  __device__ Pre2 prefetch2(int64_t i, const Pre1& p1) const {
+    Pre2 p;
+    const int64_t ti = p1.t < 0 ? 0 : (p1.t >= T ? T - 1 : p1.t);
+    p.ti = (int)ti;
+    p.eps = __ldg(sqrt_1m_ac + ti);
+    p.sc = __ldg(sqrt_ac + ti);
+    p.d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+    p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuide + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
+    return p;
+  }
+  __device__ void row(int64_t, const Pre2& p, const Mat3* a9, const Vec3*, Mat3* o9, Vec3* o3, const float* tab) const {
+    const float eps = p.eps;
+    const NoiseDraw d = p.d;
+    float ang;
+    if (guide) {
+      const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+      ang = igso3_angle_from_record(cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, d.u);
+    } else {
+      ang = igso3_angle_from_uniform(cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, d.u);
+    }
     const Quat qn = quat_axis_angle(d.axis, ang);
     const AxisAngleF ax = axis_angle_fast(a9[0]);
-    o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, sc * ax.theta), qn));  // diffusion.py:344-346
+    o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, p.sc * ax.theta), qn));  // diffusion.py:344-346
     if (kExtra && out9[kExtra ? 1 : 0]) o9[kExtra ? 1 : 0] = quat_to_mat_unit(qn);
     const float k = ang * rcp_approx(eps);                                          // diffusion.py:355
     o3[0] = Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z};
@@ -674,8 +776,8 @@ struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
 // its guide live in shared memory; otherwise per-row t with table rows (and the optional guide) read through L2.
 template <bool kSharedT, bool kX0>
 struct PStepOp {
-  SO3D_OP_ARRAYS(1, 1, (kX0 ? 2 : 1), 0)  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
-  static constexpr int kTab = kTabCdfFloats;
+  SO3D_OP_ARRAYS_S(1, 1, (kX0 ? 2 : 1), 0, (kSharedT ? 2 : 1))  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
+  static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
   const int64_t* t;
   const float* recip;
   const float* recipm1;
@@ -683,7 +785,7 @@ struct PStepOp {
   const float* coef2;
   int64_t T;
   const float* post_cdf;
-  const uint16_t* post_guide;
+  const uint32_t* post_guide;
   const float* loc;
   uint64_t seed, rng_offset, row_offset;
   __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
@@ -922,7 +1024,7 @@ int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_l
 }  // extern "C"
 
 template <bool kShared>
-static int launch_sample(const float* cdf, const uint16_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+static int launch_sample(const float* cdf, const uint32_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
                          const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, const float* mean,
                          int mean_stride, float* R, float* angle, float* axis3, int64_t n, void* stream) {
   SampleOp<kShared> op;
@@ -934,7 +1036,7 @@ static int launch_sample(const float* cdf, const uint16_t* guide, const float* l
 
 template <bool kExtra>
 static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T, const float* cdf,
-                           const uint16_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
+                           const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
                            float* target3, float* noise, float* score3, int64_t n, void* stream) {
   QSampleOp<kExtra> op;
   op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
@@ -946,7 +1048,7 @@ static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_
 
 template <bool kSharedT, bool kX0>
 static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
-                         const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint16_t* post_guide,
+                         const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint32_t* post_guide,
                          const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
                          int64_t n, void* stream) {
   PStepOp<kSharedT, kX0> op;
@@ -959,7 +1061,7 @@ static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t,
 
 extern "C" {
 
-int so3d_igso3_sample_f32(const float* cdf, const uint16_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+int so3d_igso3_sample_f32(const float* cdf, const uint32_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
                           const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                           const float* mean, int mean_stride, float* R, float* angle, float* axis3, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
@@ -974,7 +1076,7 @@ int so3d_igso3_sample_f32(const float* cdf, const uint16_t* guide, const float* 
 }
 
 int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
-                      const float* cdf, const uint16_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
+                      const float* cdf, const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
                       uint64_t row_offset, float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
   if (n == 0) return 0;
@@ -994,18 +1096,19 @@ int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt
   return launch_rowwise(op, n, stream, "so3d_q_sample_given_f32");
 }
 
-int so3d_igso3_cdf_guide_u16(const float* cdf, int64_t rows, uint16_t* guide_out, void* stream) {
+int so3d_igso3_cdf_guide(const float* cdf, int64_t rows, uint32_t* guide_out, void* stream) {
   SO3D_REQUIRE(rows >= 0, "negative rows");
   if (rows == 0) return 0;
-  SO3D_REQUIRE(cdf && guide_out, "so3d_igso3_cdf_guide_u16: null pointer");
-  SO3D_REQUIRE(rows <= 0x7fffffff, "so3d_igso3_cdf_guide_u16: too many rows");
+  SO3D_REQUIRE(cdf && guide_out, "so3d_igso3_cdf_guide: null pointer");
+  SO3D_REQUIRE(aligned16(guide_out), "so3d_igso3_cdf_guide: guide_out must be 16-byte aligned");
+  SO3D_REQUIRE(rows <= 0x7fffffff, "so3d_igso3_cdf_guide: too many rows");
   cdf_guide_kernel<<<(int)rows, kTile, 0, (cudaStream_t)stream>>>(cdf, guide_out);
-  return check_launch("so3d_igso3_cdf_guide_u16");
+  return check_launch("so3d_igso3_cdf_guide");
 }
 
 int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, int t_stride, const float* recip,
                       const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
-                      const uint16_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
+                      const uint32_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                       float* out, float* x0_hat_out, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
   if (n == 0) return 0;

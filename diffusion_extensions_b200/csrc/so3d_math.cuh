@@ -857,11 +857,17 @@ SO3D_HD float igso3_angle_from_uniform(const float* trap, const float* loc, floa
   return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, 0, kCdf));
 }
 
-// Guide table of a CDF row: guide[k] = #{j : trap[j] <= k / kGuide}, k = 0..kGuide.  k / 1024 and u * 1024 are
-// exact in fp32, so for u in [k/1024, (k+1)/1024) the count lies in [guide[k], guide[k+1]] and the search
-// returns exactly the index of the full binary search, in ~1 probe instead of 10.
+// Guide of a CDF row: guide[k] = #{j : trap[j] <= k / kGuide}, k = 0..kGuide.  k / 1024 and u * 1024 are exact in
+// fp32, so for u in [k/1024, (k+1)/1024) the count lies in [guide[k], guide[k+1]] and a search restricted to that
+// range returns exactly the index of the full binary search, in ~1 probe instead of 10.
+//   * shared-row kernels keep the guide as uint16 counts next to the row in shared memory;
+//   * per-row lookups through L2 use 16-byte RECORDS, one per bucket: {lo | hi << 16, trap[lo-1], trap[lo],
+//     trap[lo+1]} (indices clamped to [0, 998]).  When the bucket holds at most one grid point (hi - lo <= 1, the
+//     common case) ONE 16-byte load resolves the lookup: the count is lo + (trap[lo] <= u) and both CDF values of
+//     the interpolation are in the record -- a single dependent memory access instead of 4-5.
 constexpr int kGuide = 1024;
-constexpr int kGuideStride = kGuide + 2;  // entries per row (1025 used; even, so rows stay 4-byte aligned)
+constexpr int kGuideStride = kGuide + 2;  // uint16 entries per shared-memory guide (1025 used; even)
+constexpr int kGuideRecWords = 4;         // 32-bit words per record of the global guide (kGuide records per row)
 
 SO3D_HD float igso3_angle_from_uniform_guided(const float* trap, const float* loc, const uint16_t* guide, float u) {
   int k = (int)(u * (float)kGuide);
@@ -869,6 +875,41 @@ SO3D_HD float igso3_angle_from_uniform_guided(const float* trap, const float* lo
   const int lo = (u >= 0.f) ? (int)guide[k] : 0;
   const int hi = (u < 1.0f) ? (int)guide[k + 1] : kCdf;
   return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, lo, hi));
+}
+
+struct GuideRec {
+  uint32_t lohi;
+  float tm1, t0, tp1;
+};
+
+SO3D_HD GuideRec make_guide_rec(const float* trap, int k) {
+  const int lo = cdf_count_le(trap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
+  const int hi = cdf_count_le(trap, (float)(k + 1) * (1.0f / (float)kGuide), 0, kCdf);
+  auto at = [&](int j) { return trap[j < 0 ? 0 : (j > kCdf - 1 ? kCdf - 1 : j)]; };
+  return GuideRec{(uint32_t)lo | ((uint32_t)hi << 16), at(lo - 1), at(lo), at(lo + 1)};
+}
+
+// `rec` = the record of bucket floor(u * 1024) of this row (already loaded); trap = the row, for the rare fallback
+SO3D_HD float igso3_angle_from_record(const float* trap, const float* loc, const GuideRec& rec, float u) {
+  const int lo = (int)(rec.lohi & 0xffffu), hi = (int)(rec.lohi >> 16);
+  if (hi - lo <= 1 && lo < kCdf - 1 && u >= 0.f && u < 1.0f) {
+    const bool up = (hi > lo) && (rec.t0 <= u);  // count = lo + up;  i1 = count, i0 = max(count - 1, 0)
+    const int i1 = lo + (up ? 1 : 0);
+    const int i0 = i1 > 0 ? i1 - 1 : 0;
+    const float t0 = up ? rec.t0 : rec.tm1, t1 = up ? rec.tp1 : rec.t0;
+    const float diff = fmaxf(t1 - t0, 1e-6f);
+    const float wgt = fminf(fmaxf((u - t0) / diff, 0.f), 1.f);
+    const float a0 = loc[i0], a1 = loc[i1];
+    const float d = a1 - a0;
+    return (wgt < 0.5f) ? fmaf(wgt, d, a0) : fmaf(-d, 1.0f - wgt, a1);
+  }
+  const bool in01 = (u >= 0.f) && (u < 1.0f);
+  return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, in01 ? lo : 0, in01 ? hi : kCdf));
+}
+
+SO3D_HD int guide_bucket(float u) {
+  int k = (int)(u * (float)kGuide);
+  return k < 0 ? 0 : (k > kGuide - 1 ? kGuide - 1 : k);
 }
 
 // ------------------------------------------------------------------------------------------------

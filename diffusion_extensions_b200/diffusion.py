@@ -109,7 +109,7 @@ class SO3Diffusion(nn.Module):
         return self._tables[key]
 
     def guides(self):
-        """(fwd_guide, post_guide): the (T, 1026) search accelerators of the two CDF tables."""
+        """(fwd_guide, post_guide): the (T, 1024, 4) search records of the two CDF tables."""
         self.tables()
         return self._guides[str(self.betas.device)]
 

@@ -13,7 +13,7 @@ from ._lib import call, check_f32, ptr
 
 CDF_POINTS = 999
 GRID_POINTS = 1000
-GUIDE_STRIDE = 1026  # uint16 entries per guide row (include/so3d.h SO3D_GUIDE_STRIDE)
+GUIDE_BUCKETS = 1024  # 16-byte records per guide row (include/so3d.h SO3D_GUIDE_BUCKETS)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -362,17 +362,17 @@ def igso3_cdf_table(eps, reference_quirks=False):
 
 
 def igso3_cdf_guide(cdf):
-    """cdf (rows, 999) -> guide (rows, 1026) int16 storage of uint16 counts (search accelerator)."""
+    """cdf (rows, 999) -> guide (rows, 1024, 4) int32: the 16-byte search records of include/so3d.h."""
     cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
     rows = cdf.numel() // CDF_POINTS
-    out = torch.empty(rows, GUIDE_STRIDE, dtype=torch.int16, device=cdf.device)
-    call("so3d_igso3_cdf_guide_u16", ptr(cdf), rows, ptr(out), device=cdf.device)
+    out = torch.empty(rows, GUIDE_BUCKETS, 4, dtype=torch.int32, device=cdf.device)
+    call("so3d_igso3_cdf_guide", ptr(cdf), rows, ptr(out), device=cdf.device)
     return out
 
 
 def _check_guide(guide, rows, name):
-    if guide is not None and (guide.dtype != torch.int16 or guide.numel() != rows * GUIDE_STRIDE or not guide.is_contiguous() or not guide.is_cuda):
-        raise ValueError(f"{name} must be the contiguous CUDA int16 (rows, {GUIDE_STRIDE}) tensor returned by igso3_cdf_guide")
+    if guide is not None and (guide.dtype != torch.int32 or guide.numel() != rows * GUIDE_BUCKETS * 4 or not guide.is_contiguous() or not guide.is_cuda):
+        raise ValueError(f"{name} must be the contiguous CUDA int32 (rows, {GUIDE_BUCKETS}, 4) tensor returned by igso3_cdf_guide")
     return guide
 
 

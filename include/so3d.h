@@ -39,7 +39,7 @@ extern "C" {
 
 #define SO3D_CDF_POINTS 999  /* entries per CDF row (distributions.py:15,30: 1000-point grid) */
 #define SO3D_GRID_POINTS 1000
-#define SO3D_GUIDE_STRIDE 1026 /* uint16 entries per guide row (1025 used) */
+#define SO3D_GUIDE_BUCKETS 1024 /* 16-byte records per guide row */
 
 /* evaluator for the IGSO(3) density (mode argument) */
 #define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms                    */
@@ -104,20 +104,22 @@ int so3d_igso3_logp_bwd_f32(const float* R, const float* dlogf, const float* gou
  * reference's (999, *E) layout).  quirks != 0 reproduces the reference's overflow behaviour (D5). */
 int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_loc, const float* haar_w,
                              float* trap_out, int quirks, void* stream);
-/* Search accelerator for the inverse-CDF lookup of distributions.py:38-43 (`(trap <= u).sum()`): for every
- * CDF row, guide[k] = #{j : trap[j] <= k/1024}, k = 0..1024, stored as uint16 with a row stride of
- * SO3D_GUIDE_STRIDE entries.  A lookup then needs ~1 probe instead of a 10-step binary search and returns the
- * identical index.  guide_out: rows x SO3D_GUIDE_STRIDE. */
-int so3d_igso3_cdf_guide_u16(const float* cdf, int64_t rows, uint16_t* guide_out, void* stream);
+/* Search accelerator for the inverse-CDF lookup of distributions.py:38-43 (`(trap <= u).sum()`): for every CDF
+ * row, SO3D_GUIDE_BUCKETS records of 16 bytes, record k = {lo | hi << 16, trap[lo-1], trap[lo], trap[lo+1]} with
+ * lo = #{j : trap[j] <= k/1024}, hi = #{j : trap[j] <= (k+1)/1024} (trap indices clamped to [0, 998]).  For
+ * u in [k/1024, (k+1)/1024) the count lies in [lo, hi]; when hi - lo <= 1 one 16-byte load resolves the lookup,
+ * otherwise a binary search restricted to [lo, hi] does: either way the index is IDENTICAL to the full search.
+ * guide_out: rows x SO3D_GUIDE_BUCKETS x 4 words, 16-byte aligned. */
+int so3d_igso3_cdf_guide(const float* cdf, int64_t rows, uint32_t* guide_out, void* stream);
 /* distributions.py:33-51 sample: R = mean @ rot(axis, angle(u)).
- *   cdf: table rows x 999;  guide: so3d_igso3_cdf_guide_u16(cdf) or NULL (only used with row_idx; the shared-row
+ *   cdf: table rows x 999;  guide: so3d_igso3_cdf_guide(cdf) or NULL (only used with row_idx; the shared-row
  *   path builds its guide in shared memory);  loc: 999 grid angles;  row_idx: int64[n] row per sample, or NULL with
  *   `row` = the single shared row (scalar-eps path, staged in shared memory).
  *   u / axes3: optional explicit draws (u in [0,1), axes un-normalised like randn) -- when NULL
  *   they come from Philox(seed, row_offset + i, rng_offset).
  *   mean: optional 3x3 (mean_stride 0) or n x 9 (mean_stride 1) left factor.
  *   outputs: R (n x 9), and optionally the drawn angle[n] / unit axis3[n x 3]. */
-int so3d_igso3_sample_f32(const float* cdf, const uint16_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
+int so3d_igso3_sample_f32(const float* cdf, const uint32_t* guide, const float* loc, int64_t rows, const int64_t* row_idx, int64_t row,
                           const float* u, const float* axes3, uint64_t seed, uint64_t rng_offset,
                           uint64_t row_offset, const float* mean, int mean_stride, float* R, float* angle,
                           float* axis3, int64_t n, void* stream);
@@ -126,9 +128,9 @@ int so3d_igso3_sample_f32(const float* cdf, const uint16_t* guide, const float* 
 /* diffusion.py:339-346 q_sample + :348-355 p_losses target, fused:
  *   eps = sqrt_1m_ac[t], noise ~ IGSO3(eps) from cdf row t, x_t = so3_scale(x0, sqrt_ac[t]) @ noise,
  *   target = vee(log noise) / eps  (nullable), noise (nullable), score of the noise under
- *   IGSO3(eps) (nullable, auto evaluator).  t: int64[n] in [0, T).  guide: so3d_igso3_cdf_guide_u16(cdf) or NULL. */
+ *   IGSO3(eps) (nullable, auto evaluator).  t: int64[n] in [0, T).  guide: so3d_igso3_cdf_guide(cdf) or NULL. */
 int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
-                      const float* cdf, const uint16_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
+                      const float* cdf, const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
                       uint64_t row_offset, float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream);
 /* q_sample with the noise supplied by the caller (diffusion.py:339-346 with noise != None). */
 int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt_ac, int64_t T, const float* noise,
@@ -138,11 +140,11 @@ int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt
  *   mean   = so3_scale(x0_hat, coef1[t]) @ so3_scale(x_t, coef2[t])            (:299-302)
  *   out    = t == 0 ? mean : mean @ noise,  noise ~ IGSO3(sigma_t) from post_cdf row t   (:315-326)
  *   t: int64[n] per row (t_stride 1) or a single shared step (t_stride 0: CDF row and guide staged in
- *   shared memory).  post_guide: so3d_igso3_cdf_guide_u16 of post_cdf (nullable; used with per-row t).
+ *   shared memory).  post_guide: so3d_igso3_cdf_guide of post_cdf (nullable; used with per-row t).
  *   post_cdf == NULL returns the mean only (p_mean_variance).  x0_hat_out nullable. */
 int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, int t_stride, const float* recip,
                       const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
-                      const uint16_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
+                      const uint32_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                       float* out, float* x0_hat_out, int64_t n, void* stream);
 
 #ifdef __cplusplus

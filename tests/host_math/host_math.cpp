@@ -62,6 +62,13 @@ void hm_series(const float* w, const float* eps, float* F, float* Fp, long n, in
 void hm_angle_from_uniform(const float* trap, const float* loc, const float* u, float* ang, long n) {
   for (long i = 0; i < n; ++i) ang[i] = igso3_angle_from_uniform(trap, loc, u[i]);
 }
+// inverse CDF through the 16-byte guide records (built here from the same row) -- must equal the full search
+void hm_angle_from_record(const float* trap, const float* loc, const float* u, float* ang, long n) {
+  for (long i = 0; i < n; ++i) {
+    const GuideRec rec = make_guide_rec(trap, guide_bucket(u[i]));
+    ang[i] = igso3_angle_from_record(trap, loc, rec, u[i]);
+  }
+}
 void hm_philox(unsigned long long seed, unsigned long long row0, unsigned long long offset, unsigned* out, long n) {
   for (long i = 0; i < n; ++i) { U4 r = philox4x32_10(seed, row0 + i, offset); out[4*i]=r.x; out[4*i+1]=r.y; out[4*i+2]=r.z; out[4*i+3]=r.w; }
 }

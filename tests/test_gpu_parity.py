@@ -632,11 +632,16 @@ def test_guide_table_lookup_is_exact(dx, cuda_device):
     p = dx.SO3Diffusion(None).to(cuda_device)
     fwd, post, _ = p.tables()
     fg, pg = p.guides()
-    g = fg.cpu().numpy().astype(np.int64) & 0xFFFF
+    g = fg.cpu().numpy()                                   # (T, 1024, 4) int32 records
     trap = fwd.cpu().numpy()
+    edges = np.arange(1025, dtype=np.float32) / np.float32(1024)
     for row in (0, 17, 500, 999):
-        want = np.searchsorted(trap[row], np.arange(1025, dtype=np.float32) / np.float32(1024), side="right")
-        assert np.array_equal(g[row, :1025], want)
+        cnt = np.searchsorted(trap[row], edges, side="right")
+        lohi = g[row, :, 0].astype(np.int64) & 0xFFFFFFFF
+        assert np.array_equal(lohi & 0xFFFF, cnt[:-1]) and np.array_equal(lohi >> 16, cnt[1:])
+        vals = g[row, :, 1:].view(np.float32)
+        for j, off in enumerate((-1, 0, 1)):
+            assert np.array_equal(vals[:, j], trap[row][np.clip(cnt[:-1] + off, 0, 998)])
     n = 1 << 16
     rows = torch.randint(0, 1000, (n,), device=cuda_device)
     u = torch.rand(n, device=cuda_device)

@@ -223,6 +223,25 @@ def test_inverse_cdf_lookup(hm, golden):
     assert np.max(np.abs(ang[:-1] - want)) <= 1e-7 and np.isfinite(ang[-1])
 
 
+def test_inverse_cdf_guide_records(hm, golden):
+    """The 16-byte guide records resolve the lookup to exactly the index (hence the angle) of the full search,
+    for random uniforms, bucket edges, CDF values themselves and their float neighbours."""
+    g = golden("igso3")
+    loc = f32(g["trap_loc"])
+    rng = np.random.default_rng(33)
+    for k in range(len(g["eps_list"])):
+        trap = f32(g["trap"][k])
+        edges = np.arange(1024, dtype=np.float32) / np.float32(1024)
+        u = np.concatenate([rng.random(20000, dtype=np.float32), edges, np.nextafter(edges[1:], np.float32(0)), trap[:-1],
+                            np.nextafter(trap[:-1], np.float32(0)), np.nextafter(trap[:-1], np.float32(1)),
+                            f32([0.0, np.nextafter(np.float32(1), np.float32(0))])]).astype(np.float32)
+        u = np.ascontiguousarray(u[(u >= 0) & (u < 1)])
+        a = np.empty(u.shape[0], np.float32); b = np.empty(u.shape[0], np.float32)
+        hm.hm_angle_from_uniform(fp(trap), fp(loc), fp(u), fp(a), ctypes.c_long(u.shape[0]))
+        hm.hm_angle_from_record(fp(trap), fp(loc), fp(u), fp(b), ctypes.c_long(u.shape[0]))
+        assert np.array_equal(a, b)
+
+
 def test_philox_known_answer_and_draws(hm):
     # Random123 known-answer test for philox4x32-10: counter = key = 0 and the "pi" vector
     out = np.empty(4, np.uint32)
