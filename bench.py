@@ -46,6 +46,11 @@ FLOP_PER_TERM = 11
 BYTES_PER_EVAL = 56          # 36 R + 4 eps in, 4 logp + 12 score out
 BYTES_PER_PARTICLE_STEP = 84 # 36 x_t + 12 pred in, 36 out
 BYTES_PER_QSAMPLE = 92       # 36 x0 + 8 t in, 36 x_t + 12 target out
+# DRAM traffic of the series kernel per evaluation from the ncu --set full capture (profiles/r01d_series_full.md:
+# 169.10 MB read + 43.55 MB written for 4 194 304 evaluations; the rest of the 16 B/eval of results is still in L2
+# when the kernel ends) -- equal to the algorithmic 40 B/eval of inputs: nothing is re-read.
+NCU_DRAM_BYTES_PER_EVAL = (169.095680e6 + 43.554304e6) / 4194304
+MMD_LANE_INSTR_PER_PAIR = 41  # executed FP32-pipe instructions per pair of the all-pairs kernel (SASS count)
 
 
 def peaks():
@@ -320,6 +325,52 @@ def main():
         extra["noised_rotations_per_sec"] = {"value": v, "ms_per_step": m, "note": "fused q_sample + skewvec target, per-row t",
                                              "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}}
 
+        # BASELINE configs[2]: the whole reverse process, 1000 fused steps over this GPU's share of 2^24 particles
+        # (pred = 0: the denoiser is excluded); x ping-pongs between two buffers, t and the Philox offset
+        # change every step, nothing synchronises with the host inside the loop.
+        n_loop = max(1, (1 << 24) // world)
+        la, lb = R[:n_loop].clone(), torch.empty_like(R[:n_loop])
+        pz = pred[:n_loop]
+
+        def reverse_loop():
+            a, b = la, lb
+            for i in reversed(range(1000)):
+                lib_call("so3d_p_sample_f32", ptr(a), ptr(pz), ptr(t_range[i:i + 1]), 0, ptr(proc.sqrt_recip_alphas_cumprod),
+                         ptr(proc.sqrt_recipm1_alphas_cumprod), ptr(proc.posterior_mean_coef1), ptr(proc.posterior_mean_coef2), 1000, ptr(post),
+                         None, ptr(dx.ops.cdf_grid(device)[2]), SEED, 1000 + i, rank * n_loop, ptr(b), None, n_loop, device=device)
+                a, b = b, a
+
+        m = time_loop(reverse_loop, 1, 1, dist_on)
+        v = world * n_loop * 1000 / (m * 1e-3)
+        gbs = v / world * BYTES_PER_PARTICLE_STEP / 1e9
+        extra["reverse_loop_1000_steps"] = {"value": v, "unit": "particle-steps/s", "seconds": m * 1e-3, "particles": world * n_loop, "steps": 1000,
+                                            "note": "BASELINE configs[2]: 1000 fused reverse steps x 2^24 particles (split over the GPUs), pred = 0",
+                                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}}
+        del la, lb
+
+        # MMD two-sample statistic at bingham_test.py:29's size (20 000 vs 20 000 rotations), one fused
+        # all-pairs launch; multi-GPU: tile pairs dealt round-robin, three doubles all-reduced.
+        nm = 20000
+        mx, my = R[:nm].contiguous(), xb[:nm].contiguous()
+        sums = torch.zeros(3, dtype=torch.float64, device=device)
+
+        def step_mmd():
+            sums.copy_(dx.ops.pair_kernel_sums(mx, my, "gaussian", shard=rank, nshards=world))
+            if dist_on:
+                torch.distributed.all_reduce(sums)
+
+        mm = time_loop(step_mmd, 5, 3, dist_on) / 5
+        pairs_logical = 3 * nm * nm                      # k(X,X), k(Y,Y), k(X,Y) as the reference evaluates them
+        tiles = (nm + 255) // 256
+        pairs_computed = (tiles * (tiles + 1) + tiles * tiles) * 65536   # lower-triangular tile pairs for the two self sums
+        sm_ = torch.cuda.get_device_properties(device).multi_processor_count
+        lane_peak = world * sm_ * 128 * pk["sm_max_mhz"] * 1e6
+        extra["mmd_pairs_per_sec"] = {"value": pairs_logical / (mm * 1e-3), "unit": "kernel evaluations/s (as the reference counts them)", "ms_per_mmd": mm,
+                                      "n": [nm, nm], "note": "util.MMD with rmat_gaussian_kernel, fused all-pairs kernel (bingham_test.py:29 size)",
+                                      "roofline": {"bound": "fp32", "achieved": pairs_computed * MMD_LANE_INSTR_PER_PAIR / (mm * 1e-3) * 1e-12,
+                                                   "peak": lane_peak * 1e-12, "unit": "T lane-instr/s",
+                                                   "frac": pairs_computed * MMD_LANE_INSTR_PER_PAIR / (mm * 1e-3) / lane_peak}}
+
     if rank == 0:
         sm = torch.cuda.get_device_properties(device).multi_processor_count
         ghz = pk["sm_max_mhz"] * 1e-3
@@ -333,7 +384,7 @@ def main():
         clk_per_term = sm * 4 * ghz * 1e9 * 32 / (per_gpu * L)
         roofline = {
             "bound": "fp32", "achieved": ach * 1e-12, "peak": issue_peak * 1e-12, "unit": "T lane-instr/s", "frac": ach / issue_peak,
-            "traffic": None,
+            "traffic": NCU_DRAM_BYTES_PER_EVAL * n, "traffic_source": "ncu --set full, profiles/r01d_series_full.md (bytes/eval x rows per launch)",
             "definition": "SURVEY 8(d): FP32-issue bound with 10 lane-instr/term (1.86e9 evals/s/GPU); executed mix below",
             "executed_per_term": {"fp32_instr": FP32_INSTR_PER_TERM, "mufu": MUFU_PER_TERM, "uniform_ldc": UNIFORM_PER_TERM, "flop": FLOP_PER_TERM},
             "clk_per_warp_term": clk_per_term, "clk_floor_issue": 9.0, "clk_floor_xu": 8.0, "clk_floor_fp32_operands": 8.8,

@@ -42,10 +42,14 @@ SIGNATURES = {
     "so3d_q_sample_given_f32": [_c_f, _c_f, _c_f, _i64, _c_f, _c_f, _i64, _c_f],
     "so3d_p_sample_f32": [_c_f, _c_f, _c_f, _int, _c_f, _c_f, _c_f, _c_f, _i64, _c_f, _c_f, _c_f, _u64, _u64, _u64, _c_f, _c_f, _i64, _c_f],
     "so3d_igso3_cdf_guide": [_c_f, _i64, _c_f, _c_f],
+    "so3d_bingham_sample_f32": [_c_f, _c_f, _u64, _u64, _u64, _c_f, _c_f, _i64, _c_f],
+    "so3d_pair_kernel_sums_f32": [_c_f, _i64, _c_f, _i64, _int, _i64, _i64, _c_f, _i64, _c_f, _c_f],
 }
 
 MODE_SERIES, MODE_CLOSED, MODE_AUTO, MODE_SERIES_ADAPTIVE = 0, 1, 2, 3
 MODES = {"series": MODE_SERIES, "closed": MODE_CLOSED, "auto": MODE_AUTO, "series_adaptive": MODE_SERIES_ADAPTIVE}
+
+PAIR_GAUSSIAN, PAIR_COSINE = 0, 1
 
 _lib = None
 

@@ -10,8 +10,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "so3d_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "so3d_math.cuh"), os.path.join(HERE, "..", "include", "so3d.h")]
+CSRC = os.path.join(HERE, "csrc")
+SRCS = [os.path.join(CSRC, f) for f in ("so3d_kernels.cu", "so3d_pairwise.cu")]
+DEPS = SRCS + [os.path.join(CSRC, f) for f in ("so3d_math.cuh", "so3d_tma.cuh", "so3d_common.cuh")] + [os.path.join(HERE, "..", "include", "so3d.h")]
 LIB = os.path.join(HERE, "libso3d.so")
 
 NVCC_FLAGS = [
@@ -37,7 +38,7 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, SRC]
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, *SRCS]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -692,6 +692,36 @@ struct SampleOp {
   }
 };
 
+// distributions.py:113-127 Bingham.rsample: unit quaternion = normalise(L z), z ~ N(0, I4), L = scale_tril of the
+// covariance; fused with util.py:222-252 quat_to_rmat (bingham_train.py:88-90 feeds the samples straight into it).
+struct BinghamOp {
+  SO3D_OP_ARRAYS(0, 0, 1, 0)
+  SO3D_OP_NO_TAB
+  const float* tril;  // 4x4 row-major, lower triangle used
+  const float* z_in;  // optional explicit normals (n x 4)
+  bool z_vec;
+  float* q_out;       // optional (n x 4, 16-byte aligned)
+  uint64_t seed, rng_offset, row_offset;
+  __device__ void row(int64_t i, const Mat3*, const Vec3*, Mat3* o9, Vec3*, const float*) const {
+    Normal4 z;
+    if (z_in) {
+      const float4 v = z_vec ? __ldcs(reinterpret_cast<const float4*>(z_in) + i)
+                             : make_float4(z_in[4 * i], z_in[4 * i + 1], z_in[4 * i + 2], z_in[4 * i + 3]);
+      z = Normal4{v.x, v.y, v.z, v.w};
+    } else {
+      z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset));
+    }
+    const float v0 = __ldg(tril + 0) * z.a;
+    const float v1 = fmaf(__ldg(tril + 4), z.a, __ldg(tril + 5) * z.b);
+    const float v2 = fmaf(__ldg(tril + 8), z.a, fmaf(__ldg(tril + 9), z.b, __ldg(tril + 10) * z.c));
+    const float v3 = fmaf(__ldg(tril + 12), z.a, fmaf(__ldg(tril + 13), z.b, fmaf(__ldg(tril + 14), z.c, __ldg(tril + 15) * z.d)));
+    const float inv = rsqrt_f(fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, v3 * v3))));  // distributions.py:125
+    const float qw = v0 * inv, qx = v1 * inv, qy = v2 * inv, qz = v3 * inv;
+    if (q_out) __stcs(reinterpret_cast<float4*>(q_out) + i, make_float4(qw, qx, qy, qz));
+    o9[0] = quat_to_rmat(qw, qx, qy, qz);
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // L2: fused forward noising (diffusion.py:339-355) and reverse step (diffusion.py:291-326)
 // ------------------------------------------------------------------------------------------------
@@ -809,6 +839,13 @@ struct PStepOp {
 };
 
 }  // namespace
+
+// error / device helpers shared with the other translation units of the library (so3d_common.cuh)
+namespace so3d_host {
+int fail(int code, const char* what) { return ::fail(code, what); }
+int check_launch(const char* name) { return ::check_launch(name); }
+int sm_count() { return ::sm_count(); }
+}  // namespace so3d_host
 
 // ================================================================================================
 // C ABI
@@ -1094,6 +1131,18 @@ int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt
   QSampleGivenOp op;
   op.in9[0] = x0; op.in9[1] = noise; op.out9[0] = x_t; op.t = t; op.sqrt_ac = sqrt_ac; op.T = T;
   return launch_rowwise(op, n, stream, "so3d_q_sample_given_f32");
+}
+
+int so3d_bingham_sample_f32(const float* scale_tril16, const float* z4, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
+                            float* q4, float* R, int64_t n, void* stream) {
+  SO3D_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return 0;
+  SO3D_REQUIRE(scale_tril16 && (q4 || R), "so3d_bingham_sample_f32: scale_tril16 and at least one output are required");
+  SO3D_REQUIRE(!q4 || aligned16(q4), "so3d_bingham_sample_f32: q4 must be 16-byte aligned");
+  BinghamOp op;
+  op.out9[0] = R; op.tril = scale_tril16; op.z_in = z4; op.z_vec = aligned16(z4); op.q_out = q4;
+  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  return launch_rowwise(op, n, stream, "so3d_bingham_sample_f32");
 }
 
 int so3d_igso3_cdf_guide(const float* cdf, int64_t rows, uint32_t* guide_out, void* stream) {

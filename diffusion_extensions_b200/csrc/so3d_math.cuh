@@ -956,6 +956,22 @@ SO3D_HD Vec3 sphere_from_uniforms(float ua, float ub) {
   return Vec3{r * cp, r * sp, z};
 }
 
+// Four independent standard normals from one Philox block (Box-Muller on two pairs of 24-bit uniforms; the radius
+// uniforms live in (0, 1], so the logarithm is finite: |z| <= sqrt(2 * 24 ln 2) = 5.77).
+struct Normal4 {
+  float a, b, c, d;
+};
+SO3D_HD Normal4 normal4_from_u4(const U4& r) {
+  const float ua = (float)((r.x >> 8) + 1u) * (1.0f / 16777216.0f);
+  const float ub = (float)((r.z >> 8) + 1u) * (1.0f / 16777216.0f);
+  const float ta = -2.0f * logf(ua), tb = -2.0f * logf(ub);
+  const float ra = ta * rsqrt_approx(fmaxf(ta, 1e-30f)), rb = tb * rsqrt_approx(fmaxf(tb, 1e-30f));
+  float sa, ca, sb, cb;
+  sincos_fast(kTwoPi * u01(r.y), &sa, &ca);
+  sincos_fast(kTwoPi * u01(r.w), &sb, &cb);
+  return Normal4{ra * ca, ra * sa, rb * cb, rb * sb};
+}
+
 struct NoiseDraw {
   Vec3 axis;
   float u;

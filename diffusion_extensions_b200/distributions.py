@@ -22,7 +22,7 @@ above; <= 1e-5 relative everywhere), "series_adaptive".
 tiny eps too.  Quirk Q1 (column-0 gather with batched eps) is a plain bug and is not reproduced.
 """
 import torch
-from torch.distributions import Distribution, constraints
+from torch.distributions import Distribution, MultivariateNormal, constraints
 
 from . import ops
 
@@ -142,4 +142,44 @@ class IsotropicGaussianSO3(Distribution):
         return logp[..., None], score
 
 
-__all__ = ["IsotropicGaussianSO3"]
+class Bingham(MultivariateNormal):
+    """distributions.py:113-127: zero-mean Gaussian in R^4 pushed onto the unit quaternions (real part first).
+
+    Same constructor as the reference (a MultivariateNormal whose `loc` is replaced by zeros).  On a CUDA device
+    with a single (4,4) covariance, `rsample` / `sample` are ONE fused kernel (device Philox normals, L z,
+    normalisation), and `sample_rmat` additionally fuses the `quat_to_rmat` the reference applies to every batch
+    (bingham_train.py:88-90).  `z=` reproduces given standard-normal draws (parity tests).  Gradients w.r.t. the
+    covariance take the stock torch route."""
+
+    arg_constraints = {"covariance_matrix": constraints.positive_definite, "precision_matrix": constraints.positive_definite,
+                       "scale_tril": constraints.lower_cholesky}
+    support = constraints.real_vector
+
+    def __init__(self, loc, covariance_matrix=None, precision_matrix=None, scale_tril=None, validate_args=None):
+        loc = torch.zeros_like(loc)  # distributions.py:120: always zero-mean (antipodally symmetric)
+        super().__init__(loc, covariance_matrix, precision_matrix, scale_tril, validate_args)
+        self.row_offset = 0
+
+    def _fused(self):
+        st = self._unbroadcasted_scale_tril
+        return st.is_cuda and st.dtype == torch.float32 and st.shape == (4, 4) and not (torch.is_grad_enabled() and st.requires_grad)
+
+    def rsample(self, sample_shape=torch.Size(), *, z=None):
+        if self._fused():
+            shape = tuple(sample_shape) + tuple(self.batch_shape)
+            return ops.bingham_sample(self._unbroadcasted_scale_tril, shape, z=z, row_offset=self.row_offset)
+        vals = super().rsample(sample_shape)
+        return vals / vals.norm(dim=-1, keepdim=True)
+
+    @torch.no_grad()
+    def sample_rmat(self, sample_shape=torch.Size(), *, z=None):
+        """quat_to_rmat(self.sample(sample_shape)) in one launch: (*sample_shape, 3, 3)."""
+        if not self._fused():
+            from .util import quat_to_rmat
+
+            return quat_to_rmat(self.rsample(sample_shape))
+        shape = tuple(sample_shape) + tuple(self.batch_shape)
+        return ops.bingham_sample(self._unbroadcasted_scale_tril, shape, z=z, row_offset=self.row_offset, want_quat=False, want_rmat=True)
+
+
+__all__ = ["IsotropicGaussianSO3", "Bingham"]

@@ -417,6 +417,61 @@ def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, 
 
 
 # ---------------------------------------------------------------------------------------------
+# data side: Bingham quaternions (distributions.py:113-127), optionally straight to rotation matrices
+# ---------------------------------------------------------------------------------------------
+def bingham_sample(scale_tril, shape, z=None, seed=None, rng_offset=None, row_offset=0, want_quat=True, want_rmat=False):
+    """scale_tril (4,4) CUDA float32 -> unit quaternions (*shape,4) and/or rotation matrices (*shape,3,3) in ONE
+    launch.  z: optional explicit standard normals (*shape,4)."""
+    scale_tril = check_f32(scale_tril, "scale_tril", (4, 4))
+    if scale_tril.numel() != 16:
+        raise ValueError("the fused Bingham sampler takes a single (4,4) scale_tril (no batch of covariances)")
+    dev = scale_tril.device
+    shape = tuple(int(d) for d in shape)
+    n = 1
+    for d in shape:
+        n *= d
+    if z is not None:
+        z = check_f32(z, "z", (4,)).expand(*shape, 4).contiguous()
+    if seed is None or rng_offset is None:
+        seed, rng_offset = rng.next()
+    if not (want_quat or want_rmat):
+        raise ValueError("nothing to compute")
+    q = torch.empty(*shape, 4, dtype=torch.float32, device=dev) if want_quat else None
+    R = torch.empty(*shape, 3, 3, dtype=torch.float32, device=dev) if want_rmat else None
+    call("so3d_bingham_sample_f32", ptr(scale_tril), ptr(z), seed, rng_offset, int(row_offset), ptr(q), ptr(R), n, device=dev)
+    if want_quat and want_rmat:
+        return q, R
+    return q if want_quat else R
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluation: all-pairs kernel sums (util.py:254-285 MMD)
+# ---------------------------------------------------------------------------------------------
+PAIR_KERNELS = {"gaussian": _lib.PAIR_GAUSSIAN, "cosine": _lib.PAIR_COSINE}
+_pair_ws = {}
+
+
+def pair_kernel_sums(X, Y=None, kernel="gaussian", shard=0, nshards=1):
+    """X (nx,3,3), Y (ny,3,3) or None -> float64 (3,) = [sum_ij k(X_i,X_j), sum_ij k(Y_i,Y_j), sum_ij k(X_i,Y_j)]
+    in one fused launch (nothing of size nx*ny is materialised).  With nshards > 1 only this shard's share of the
+    256x256 tile pairs is summed (add the results of all shards)."""
+    X = check_f32(X, "X", (3, 3)).reshape(-1, 3, 3)
+    dev = X.device
+    Y = check_f32(Y, "Y", (3, 3)).reshape(-1, 3, 3) if Y is not None else None
+    if kernel not in PAIR_KERNELS:
+        raise ValueError(f"kernel must be one of {sorted(PAIR_KERNELS)}")
+    key = str(dev)
+    if key not in _pair_ws:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        _pair_ws[key] = torch.empty(3 * 8 * sms, dtype=torch.float64, device=dev)
+    ws = _pair_ws[key]
+    out = torch.empty(3, dtype=torch.float64, device=dev)
+    call("so3d_pair_kernel_sums_f32", ptr(X), X.shape[0], ptr(Y), 0 if Y is None else Y.shape[0], PAIR_KERNELS[kernel],
+         int(shard), int(nshards), ptr(ws), ws.numel(), ptr(out), device=dev)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # L2: fused diffusion steps
 # ---------------------------------------------------------------------------------------------
 def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, row_offset=0,

@@ -11,6 +11,8 @@ Deliberate deviations from the reference:
   * log_rmat / rmat_to_aa are accurate up to and at a rotation by pi (Q4) and return the axis
     (0,0,1) with angle 0 at the identity instead of NaN (Q10).
 """
+from itertools import product
+from math import log
 from typing import Tuple
 
 import torch
@@ -202,7 +204,73 @@ def compose(a, b, trans_a=False, trans_b=False):
     return ops.compose(a, b, trans_a, trans_b)
 
 
+# ---------------------------------------------------------------------------------------------
+# kernels on SO(3) and the MMD two-sample statistic  (util.py:108-150, 254-313)
+# ---------------------------------------------------------------------------------------------
+def rmat_cosine_dist(m1: torch.Tensor, m2: torch.Tensor) -> torch.Tensor:
+    """util.py:108-124: 1 - cos(angle of m2^T m1), broadcasting over batch dims."""
+    return 1 - rmat_cosine_kernel(m1, m2)
+
+
+def rmat_gaussian_kernel(m1: torch.Tensor, m2: torch.Tensor) -> torch.Tensor:
+    """util.py:128-134: exp(-rmat_dist(m1, m2)), broadcasting over batch dims (one fused distance kernel)."""
+    return torch.exp(-rmat_dist(m1, m2))
+
+
+def rmat_cosine_kernel(m1: torch.Tensor, m2: torch.Tensor) -> torch.Tensor:
+    """util.py:136-150: (tr(m2^T m1) - 1) / 2 = cos(angle)."""
+    return ((m1 * m2).sum(dim=(-1, -2)) - 1) / 2
+
+
+_FUSED_PAIR_KERNELS = {rmat_gaussian_kernel: "gaussian", rmat_cosine_kernel: "cosine"}
+
+
+def MMD(X: torch.Tensor, Y: torch.Tensor, kernel, chunksize=None):
+    """util.py:254-285: maximum mean discrepancy between two sets of rotations (biased V-statistic).
+
+    With `rmat_gaussian_kernel` / `rmat_cosine_kernel` the three all-pairs sums run as ONE fused sm_100a launch that
+    never materialises a pair matrix (so `chunksize`, the reference's memory workaround, is not needed and is
+    ignored); any other callable takes the reference's chunked outer-product route through torch ops."""
+    l_X, l_Y = len(X), len(Y)
+    fused = _FUSED_PAIR_KERNELS.get(kernel)
+    if fused is not None and X.is_cuda and X.dim() == 3 and Y.dim() == 3 and not _needs_grad(X, Y):
+        sums = ops.pair_kernel_sums(X, Y, fused)
+        mmd = sums[0] / (l_X ** 2) + sums[1] / (l_Y ** 2) - sums[2] * (2 / (l_X * l_Y))
+        return mmd.to(torch.float32)
+    maxlen = max(l_X, l_Y)
+    if chunksize is None or chunksize >= maxlen:
+        X_sum = kernel(X.unsqueeze(0), X.unsqueeze(1)).sum(dim=(0, 1))
+        Y_sum = kernel(Y.unsqueeze(0), Y.unsqueeze(1)).sum(dim=(0, 1))
+        XY_sum = kernel(X.unsqueeze(0), Y.unsqueeze(1)).sum(dim=(0, 1))
+    else:
+        splits = list(range(chunksize, maxlen, chunksize))
+        X_split = torch.tensor_split(X, splits)
+        Y_split = torch.tensor_split(Y, splits)
+        X_sum = sum(kernel(x1.unsqueeze(0), x2.unsqueeze(1)).sum(dim=(0, 1)) for x1, x2 in product(X_split, X_split))
+        Y_sum = sum(kernel(y1.unsqueeze(0), y2.unsqueeze(1)).sum(dim=(0, 1)) for y1, y2 in product(Y_split, Y_split))
+        XY_sum = sum(kernel(x.unsqueeze(0), y.unsqueeze(1)).sum(dim=(0, 1)) for x, y in product(X_split, Y_split))
+    return (1 / (l_X ** 2)) * X_sum + (1 / (l_Y ** 2)) * Y_sum - (2 / (l_X * l_Y)) * XY_sum
+
+
+def Ker_2samp_test(X, Y, kernel, alpha=0.05, max_ker=1, chunksize=None):
+    """util.py:287-298: kernel two-sample test (True = same distribution not rejected)."""
+    m, n = len(X), len(Y)
+    assert m == n, "Requires equal amount of samples from X and Y"
+    mmd = MMD(X, Y, kernel, chunksize=chunksize).item()
+    test_val = (2 * max_ker / m) ** 0.5 * (1 + (2 * log(1 / alpha)) ** 0.5)
+    return mmd < test_val
+
+
+def Ker_2samp_log_prob(X, Y, kernel, max_ker=1, chunksize=None):
+    """util.py:300-312: log-probability of a type I error."""
+    m, n = len(X), len(Y)
+    assert m == n, "Requires equal amount of samples from X and Y"
+    mmd = MMD(X, Y, kernel, chunksize=chunksize).item()
+    return -((((mmd / ((2 * max_ker / m) ** 0.5)) - 1) ** 2) / 2)
+
+
 __all__ = [
     "skew2vec", "vec2skew", "orthogonalise", "log_rmat", "log_vec", "aa_to_rmat", "exp_vec", "rmat_to_aa",
     "quat_to_rmat", "rmat_to_quat", "rmat_dist", "so3_lerp", "so3_scale", "compose",
+    "rmat_cosine_dist", "rmat_gaussian_kernel", "rmat_cosine_kernel", "MMD", "Ker_2samp_test", "Ker_2samp_log_prob",
 ]

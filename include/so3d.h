@@ -147,6 +147,29 @@ int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, in
                       const uint32_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                       float* out, float* x0_hat_out, int64_t n, void* stream);
 
+/* ---- data side: distributions.py Bingham ------------------------------------------- */
+/* distributions.py:113-127 Bingham.rsample (zero-mean MultivariateNormal in R^4, normalised to a unit quaternion,
+ * real part first) fused with util.py:222-252 quat_to_rmat (bingham_train.py:88-90):
+ *   q = L z / |L z|,  L = scale_tril16 (DEVICE pointer, 4x4 row-major, lower triangle used),
+ *   z = z4[n x 4] when given (parity with explicit draws), else 4 Box-Muller normals from
+ *   Philox(seed, row_offset + i, rng_offset).   Outputs (each nullable, not both): q4 (n x 4, 16-byte aligned),
+ *   R (n x 9). */
+int so3d_bingham_sample_f32(const float* scale_tril16, const float* z4, uint64_t seed, uint64_t rng_offset,
+                            uint64_t row_offset, float* q4, float* R, int64_t n, void* stream);
+
+/* ---- evaluation: util.py MMD ---------------------------------------------------- */
+#define SO3D_PAIR_GAUSSIAN 0 /* util.py:128-134 rmat_gaussian_kernel: exp(-rmat_dist) = exp(-sqrt(2) theta(A^T B)) */
+#define SO3D_PAIR_COSINE 1   /* util.py:136-150 rmat_cosine_kernel: (tr(B^T A) - 1)/2 = cos theta                 */
+/* util.py:254-285 MMD: the three all-pairs kernel sums it needs, in one launch and without materialising the
+ * pair matrices:   out3[0] = sum_{i,j < nx} k(X_i, X_j),  out3[1] = sum_{i,j < ny} k(Y_i, Y_j),
+ *                  out3[2] = sum_{i < nx, j < ny} k(X_i, Y_j)            (doubles; Y may be NULL with ny = 0).
+ * MMD = out3[0]/nx^2 + out3[1]/ny^2 - 2 out3[2]/(nx ny).  The work is a flat list of 256 x 256 tile pairs dealt
+ * round-robin to `nshards` shards; this call computes shard `shard` only (multi-GPU: every rank calls with its
+ * own shard and the caller adds the out3 of all ranks).  ws: scratch of ws_len doubles (>= 3; three per resident
+ * CTA, 3 * 8 * #SMs lets the launch fill the device).  Deterministic for fixed (shard, nshards, ws_len). */
+int so3d_pair_kernel_sums_f32(const float* X, int64_t nx, const float* Y, int64_t ny, int kernel, int64_t shard,
+                              int64_t nshards, double* ws, int64_t ws_len, double* out3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,5 +157,40 @@ def main():
     )
 
 
+def main_eval():
+    """Evaluation / data-side fixtures: Bingham.rsample with its normals recorded, and the
+    reference's MMD (util.py:254-285) with both SO(3) kernels, un-chunked and chunked."""
+    cov3 = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0.9, 0.9], [0, 0.9, 1.0, 0.9], [0, 0.9, 0.9, 1.0]])  # bingham_train.py:66-71
+    cov1 = torch.diag(torch.tensor([1000.0, 0.1, 0.1, 0.1]))                                            # bingham_train.py:55
+    loc = torch.zeros(4)
+    out = {}
+    for name, cov, n in (("c3", cov3, 300), ("c1", cov1, 333)):
+        d = rdist.Bingham(loc, covariance_matrix=cov)
+        torch.manual_seed(2024)
+        q = d.sample((n,))
+        torch.manual_seed(2024)
+        z = torch.empty(n, 4).normal_()  # what MultivariateNormal.rsample draws (_standard_normal)
+        chk = z @ d.scale_tril.T
+        chk = chk / chk.norm(dim=-1, keepdim=True)
+        assert torch.allclose(chk, q, atol=1e-6), "normals do not reproduce the reference's Bingham draw"
+        out.update({f"{name}_cov": cov, f"{name}_tril": d.scale_tril, f"{name}_z": z, f"{name}_q": q, f"{name}_R": rutil.quat_to_rmat(q)})
+    X, Y = out["c3_R"], out["c1_R"]
+    out["mmd_gauss"] = rutil.MMD(X, Y, rutil.rmat_gaussian_kernel)
+    out["mmd_gauss_chunk128"] = rutil.MMD(X, Y, rutil.rmat_gaussian_kernel, chunksize=128)
+    out["mmd_cos"] = rutil.MMD(X, Y, rutil.rmat_cosine_kernel)
+    out["mmd_gauss_same"] = rutil.MMD(X[:150], X[150:], rutil.rmat_gaussian_kernel)
+    out["ker_gauss_xy"] = rutil.rmat_gaussian_kernel(X[:64].unsqueeze(0), Y[:48].unsqueeze(1))
+    out["ker_cos_xy"] = rutil.rmat_cosine_kernel(X[:64].unsqueeze(0), Y[:48].unsqueeze(1))
+    out["cos_dist"] = rutil.rmat_cosine_dist(X[:64], Y[:64])
+    out["test_same"] = np.array(rutil.Ker_2samp_test(X[:150], X[150:], rutil.rmat_gaussian_kernel))
+    out["test_diff"] = np.array(rutil.Ker_2samp_test(X, Y[:300], rutil.rmat_gaussian_kernel))
+    out["logp_same"] = np.array(rutil.Ker_2samp_log_prob(X[:150], X[150:], rutil.rmat_gaussian_kernel))
+    save("evaluation", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "eval" in sys.argv[1:]:
+        main_eval()
+    else:
+        main()
+        main_eval()

@@ -174,6 +174,48 @@ def rmat_dist(a, b):
     return math.sqrt(2.0) * np.linalg.norm(v, axis=-1)
 
 
+def rmat_gaussian_kernel(a, b):
+    """util.py:128-134: exp(-rmat_dist(a, b)), broadcasting over batch dims."""
+    return np.exp(-rmat_dist(a, b))
+
+
+def rmat_cosine_kernel(a, b):
+    """util.py:136-150: (tr(b^T a) - 1) / 2."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return ((a * b).sum(axis=(-1, -2)) - 1.0) / 2.0
+
+
+def pair_kernel_sums(x, y, kernel=rmat_gaussian_kernel, chunk=512):
+    """The three outer-product sums of util.py:254-285: sum k(X,X), sum k(Y,Y), sum k(X,Y) (float64), evaluated in
+    chunk x chunk blocks like the reference's chunked branch (util.py:265-278)."""
+    def total(p, q):
+        acc = 0.0
+        for i in range(0, len(p), chunk):
+            for j in range(0, len(q), chunk):
+                acc += float(kernel(p[None, i:i + chunk], q[j:j + chunk, None]).sum())
+        return acc
+
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    return np.array([total(x, x), total(y, y), total(x, y)])
+
+
+def mmd(x, y, kernel=rmat_gaussian_kernel, chunk=512):
+    """util.py:254-285 MMD (biased V-statistic): mean k(X,X) + mean k(Y,Y) - 2 mean k(X,Y)."""
+    sxx, syy, sxy = pair_kernel_sums(x, y, kernel, chunk)
+    lx, ly = len(x), len(y)
+    return sxx / lx ** 2 + syy / ly ** 2 - 2.0 * sxy / (lx * ly)
+
+
+def bingham_sample_given(z, scale_tril):
+    """distributions.py:113-127 Bingham.rsample with the standard-normal draws z (...,4) given:
+    vals = L z (MultivariateNormal.rsample with loc = 0), out = vals / |vals|  (unit quaternions, real first)."""
+    z = np.asarray(z, dtype=np.float64)
+    vals = z @ np.asarray(scale_tril, dtype=np.float64).T
+    return vals / np.linalg.norm(vals, axis=-1, keepdims=True)
+
+
 def quat_to_rmat(q):
     """util.py:222-252: real-first (r,i,j,k), un-normalised input allowed (two_s = 2/|q|^2)."""
     q = np.asarray(q, dtype=np.float64)

@@ -236,3 +236,31 @@ def test_diffusion_algebra(golden):
                          s["posterior_mean_coef1"][tr], s["posterior_mean_coef2"][tr])
     assert np.max(np.abs(mm - g["mean_pm"])[ok2]) < 3e-5
     assert np.array_equal(s["posterior_variance"][tr], g["post_var"])
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluation / data side: MMD with the SO(3) kernels, Bingham draws
+# ---------------------------------------------------------------------------------------------
+def test_pair_kernels_and_mmd(golden):
+    g = golden("evaluation")
+    X, Y = g["c3_R"], g["c1_R"]
+    kg = O.rmat_gaussian_kernel(X[:64][None], Y[:48][:, None])
+    assert np.max(np.abs(kg - g["ker_gauss_xy"])) < 2e-6          # reference fp32 atan2 / exp
+    kc = O.rmat_cosine_kernel(X[:64][None], Y[:48][:, None])
+    assert np.max(np.abs(kc - g["ker_cos_xy"])) < 1e-6
+    assert np.max(np.abs((1 - O.rmat_cosine_kernel(X[:64], Y[:64])) - g["cos_dist"])) < 1e-6
+    # MMD: the reference sums ~1e5 fp32 kernel values per term, so agreement is ~1e-6 absolute
+    assert abs(O.mmd(X, Y) - float(g["mmd_gauss"])) < 3e-6
+    assert abs(O.mmd(X, Y, chunk=128) - float(g["mmd_gauss_chunk128"])) < 3e-6
+    assert abs(O.mmd(X, Y, O.rmat_cosine_kernel) - float(g["mmd_cos"])) < 3e-6
+    assert abs(O.mmd(X[:150], X[150:]) - float(g["mmd_gauss_same"])) < 3e-6
+    assert float(g["mmd_gauss"]) > 0.1 > float(g["mmd_gauss_same"]) > 0.0
+    assert bool(g["test_same"]) and not bool(g["test_diff"])
+
+
+def test_bingham_given_normals(golden):
+    g = golden("evaluation")
+    for name in ("c3", "c1"):
+        q = O.bingham_sample_given(g[name + "_z"], g[name + "_tril"])
+        assert np.max(np.abs(q - g[name + "_q"])) < 1e-6
+        assert np.max(np.abs(O.quat_to_rmat(q) - g[name + "_R"])) < 2e-6
