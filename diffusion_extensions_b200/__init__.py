@@ -8,7 +8,8 @@ CUDA float32 only -- there is no CPU fallback.
 from . import _lib, ops  # noqa: F401
 from .ops import manual_seed  # noqa: F401
 from . import util, distributions, diffusion  # noqa: F401
-from .distributions import IsotropicGaussianSO3  # noqa: F401
-from .diffusion import SO3Diffusion, ProjectedSO3Diffusion  # noqa: F401
+from .distributions import IsotropicGaussianSO3, IGSO3xR3, Bingham  # noqa: F401
+from .diffusion import SO3Diffusion, ProjectedSO3Diffusion, SE3Diffusion, ProjectedSE3Diffusion  # noqa: F401
+from .util import AffineT, AffineGrad  # noqa: F401
 
 __version__ = "0.1.0"

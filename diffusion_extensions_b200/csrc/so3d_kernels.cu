@@ -838,6 +838,96 @@ struct PStepOp {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// SE(3) arm: diffusion.py:432-573 SE3Diffusion / distributions.py:84-110 IGSO3xR3.  The rotation
+// half is the SO(3) arithmetic above; the translation half is a scalar DDPM in R^3 with noise scale
+// eps * shift_scale, carried by the same launch (three more 12-byte arrays per row).
+// The translation normals come from a second Philox block of the same row: counter (row, rng_offset | 2^63), so the
+// rotation draws are bit-identical to the SO(3)-only kernels at the same (seed, rng_offset).
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kShiftStream = 0x8000000000000000ull;
+
+// q_sample + p_losses targets: diffusion.py:498-516
+//   rot_t = so3_scale(rot0, a_t) @ noise_rot;  target_rot = vee(log noise_rot)/eps_t
+//   shift_t = a_t shift0 + eps_t shift_scale z;  target_shift = noise_shift/(eps_t shift_scale) = z
+struct SE3QSampleOp {
+  SO3D_OP_ARRAYS_S(1, 1, 1, 3, 1)  // in: rot0 | shift0;  out: rot_t | target_rot, shift_t, target_shift
+  static constexpr int kTab = kGrid;
+  const int64_t* t;
+  const float* sqrt_ac;
+  const float* sqrt_1m_ac;
+  int64_t T;
+  const float* cdf;
+  const uint32_t* guide;
+  const float* loc;
+  float shift_scale;
+  uint64_t seed, rng_offset, row_offset;
+  __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
+    int64_t ti = t[i];
+    ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
+    const float eps = __ldg(sqrt_1m_ac + ti), sc = __ldg(sqrt_ac + ti);
+    const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+    const float ang = table_row_angle(cdf, guide, ti, tab, d.u);
+    const Quat qn = quat_axis_angle(d.axis, ang);
+    const AxisAngleF ax = axis_angle_fast(a9[0]);
+    o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, sc * ax.theta), qn));
+    const float k = ang * rcp_approx(eps);
+    o3[0] = Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z};
+    const Normal4 z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset | kShiftStream));
+    const float ns = eps * shift_scale;
+    o3[1] = Vec3{fmaf(sc, a3[0].x, ns * z.a), fmaf(sc, a3[0].y, ns * z.b), fmaf(sc, a3[0].z, ns * z.c)};
+    o3[2] = Vec3{z.a, z.b, z.c};
+  }
+};
+
+// reverse step: diffusion.py:446-485
+//   rot as PStepOp;  shift0_hat = recip_t shift_t - recipm1_t pred_shift;  mean = c1 shift0_hat + c2 shift_t;
+//   out = t == 0 ? mean : mean + sigma_t shift_scale z
+template <bool kSharedT>
+struct SE3PStepOp {
+  SO3D_OP_ARRAYS_S(1, 3, 1, 1, 1)  // in: rot_t | pred_rot, shift_t, pred_shift;  out: rot | shift
+  static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
+  const int64_t* t;
+  const float* recip;
+  const float* recipm1;
+  const float* coef1;
+  const float* coef2;
+  const float* sigma;
+  int64_t T;
+  const float* post_cdf;
+  const uint32_t* post_guide;
+  const float* loc;
+  float shift_scale;
+  uint64_t seed, rng_offset, row_offset;
+  __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
+  __device__ void setup(float* tab) const {
+    if (post_cdf) stage_cdf(tab, kSharedT ? post_cdf + clamp_t(t[0]) * kCdf : nullptr, loc);
+  }
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
+    const int64_t ti = clamp_t(kSharedT ? t[0] : t[i]);
+    const float k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti);
+    const float k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti);
+    Quat qh;
+    Quat qm = p_mean_quat(a9[0], a3[0], k_recip, k_recipm1, k_c1, k_c2, &qh);
+    const Vec3 st = a3[1], ps = a3[2];
+    Vec3 m;
+    m.x = fmaf(k_c1, fmaf(k_recip, st.x, -k_recipm1 * ps.x), k_c2 * st.x);
+    m.y = fmaf(k_c1, fmaf(k_recip, st.y, -k_recipm1 * ps.y), k_c2 * st.y);
+    m.z = fmaf(k_c1, fmaf(k_recip, st.z, -k_recipm1 * ps.z), k_c2 * st.z);
+    if (post_cdf && ti != 0) {
+      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+      const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
+      qm = qmul(qm, quat_axis_angle(d.axis, ang));
+      const Normal4 z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset | kShiftStream));
+      const float ns = __ldg(sigma + ti) * shift_scale;
+      m = Vec3{fmaf(ns, z.a, m.x), fmaf(ns, z.b, m.y), fmaf(ns, z.c, m.z)};
+    }
+    o9[0] = quat_to_mat_unit(qm);
+    o3[0] = m;
+  }
+};
+
 }  // namespace
 
 // error / device helpers shared with the other translation units of the library (so3d_common.cuh)
@@ -1170,6 +1260,59 @@ int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, in
   if (t_stride == 0) return x0_hat_out ? SO3D_PSTEP(true, true) : SO3D_PSTEP(true, false);
   return x0_hat_out ? SO3D_PSTEP(false, true) : SO3D_PSTEP(false, false);
 #undef SO3D_PSTEP
+}
+
+}  // extern "C"
+
+template <bool kSharedT>
+static int launch_se3_p_step(const float* rot_t, const float* shift_t, const float* pred_rot3, const float* pred_shift3, const int64_t* t,
+                             const float* recip, const float* recipm1, const float* coef1, const float* coef2, const float* sigma, int64_t T,
+                             const float* post_cdf, const uint32_t* post_guide, const float* loc, float shift_scale, uint64_t seed,
+                             uint64_t rng_offset, uint64_t row_offset, float* rot_out, float* shift_out, int64_t n, void* stream) {
+  SE3PStepOp<kSharedT> op;
+  op.in9[0] = rot_t; op.in3[0] = pred_rot3; op.in3[1] = shift_t; op.in3[2] = pred_shift3; op.out9[0] = rot_out; op.out3[0] = shift_out;
+  op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.sigma = sigma; op.T = T;
+  op.post_cdf = post_cdf; op.post_guide = post_guide; op.loc = loc; op.shift_scale = shift_scale;
+  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  return launch_rowwise(op, n, stream, "so3d_se3_p_sample_f32");
+}
+
+extern "C" {
+
+int so3d_se3_q_sample_f32(const float* rot0, const float* shift0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac,
+                          int64_t T, const float* cdf, const uint32_t* guide, const float* loc, float shift_scale, uint64_t seed,
+                          uint64_t rng_offset, uint64_t row_offset, float* rot_t, float* shift_t, float* target_rot3,
+                          float* target_shift3, int64_t n, void* stream) {
+  SO3D_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return 0;
+  SO3D_REQUIRE(rot0 && shift0 && t && sqrt_ac && sqrt_1m_ac && cdf && loc && rot_t && shift_t, "so3d_se3_q_sample_f32: null pointer");
+  SO3D_REQUIRE(T > 0, "so3d_se3_q_sample_f32: T must be positive");
+  SO3D_REQUIRE(rng_offset < kShiftStream, "so3d_se3_q_sample_f32: rng_offset must be below 2^63");
+  SE3QSampleOp op;
+  op.in9[0] = rot0; op.in3[0] = shift0; op.out9[0] = rot_t; op.out3[0] = target_rot3; op.out3[1] = shift_t; op.out3[2] = target_shift3;
+  op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
+  op.shift_scale = shift_scale; op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  return launch_rowwise(op, n, stream, "so3d_se3_q_sample_f32");
+}
+
+int so3d_se3_p_sample_f32(const float* rot_t, const float* shift_t, const float* pred_rot3, const float* pred_shift3, const int64_t* t,
+                          int t_stride, const float* recip, const float* recipm1, const float* coef1, const float* coef2,
+                          const float* sigma, int64_t T, const float* post_cdf, const uint32_t* post_guide, const float* loc,
+                          float shift_scale, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* rot_out, float* shift_out,
+                          int64_t n, void* stream) {
+  SO3D_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return 0;
+  SO3D_REQUIRE(rot_t && shift_t && pred_rot3 && pred_shift3 && t && recip && recipm1 && coef1 && coef2 && rot_out && shift_out,
+               "so3d_se3_p_sample_f32: null pointer");
+  SO3D_REQUIRE(T > 0, "so3d_se3_p_sample_f32: T must be positive");
+  SO3D_REQUIRE(t_stride == 0 || t_stride == 1, "t_stride must be 0 or 1");
+  SO3D_REQUIRE(!post_cdf || (loc && sigma), "so3d_se3_p_sample_f32: loc and sigma required with post_cdf");
+  SO3D_REQUIRE(rng_offset < kShiftStream, "so3d_se3_p_sample_f32: rng_offset must be below 2^63");
+  if (t_stride == 0)
+    return launch_se3_p_step<true>(rot_t, shift_t, pred_rot3, pred_shift3, t, recip, recipm1, coef1, coef2, sigma, T, post_cdf, post_guide, loc,
+                                   shift_scale, seed, rng_offset, row_offset, rot_out, shift_out, n, stream);
+  return launch_se3_p_step<false>(rot_t, shift_t, pred_rot3, pred_shift3, t, recip, recipm1, coef1, coef2, sigma, T, post_cdf, post_guide, loc,
+                                  shift_scale, seed, rng_offset, row_offset, rot_out, shift_out, n, stream);
 }
 
 }  // extern "C"

@@ -463,6 +463,36 @@ SO3D_HD void quat_axis_halfangle(const Quat& q, Vec3* n, float* half) {
   *n = Vec3{q.x * k, q.y * k, fsel(v2 > 0.f, q.z * k, 1.0f)};
 }
 
+// Kernel values on SO(3) for a pair of unit quaternions a, b (real part first), util.py:128-150:
+//   gaussian: exp(-rmat_dist) = exp(-sqrt(2) theta),   cosine: cos(theta),   theta = angle of R(a)^T R(b).
+// conj(a) (x) b has scalar part d = cos(theta/2) (up to sign) and a vector part v with |v| = sin(theta/2): both are
+// computed directly (no 1 - d^2 cancellation), so theta/2 = atan2(|v|, |d|) is accurate to ~1e-7 rad from 0 to pi.
+template <bool kGaussian>
+SO3D_HD float so3_pair_kernel(const Quat& a, const Quat& b) {
+  const float d = fmaf(a.w, b.w, fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)));
+  const float vx = fmaf(a.w, b.x, fmaf(-b.w, a.x, fmaf(a.z, b.y, -(a.y * b.z))));
+  const float vy = fmaf(a.w, b.y, fmaf(-b.w, a.y, fmaf(a.x, b.z, -(a.z * b.x))));
+  const float vz = fmaf(a.w, b.z, fmaf(-b.w, a.z, fmaf(a.y, b.x, -(a.x * b.y))));
+  const float s2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+  if (!kGaussian) return fmaf(d, d, -s2);  // cos(theta) = cos^2(theta/2) - sin^2(theta/2)
+  const float s = s2 * rsqrt_approx(fmaxf(s2, 1e-37f));
+  const float ad = fabsf(d);
+  // s^2 + d^2 = 1, so max(s, |d|) >= 0.707: the quotient needs no zero guard
+  const float hi = fmaxf(ad, s), lo = fminf(ad, s);
+  const float t = lo * rcp_approx(hi);
+  const float z = t * t;
+  float p = fmaf(0.0028662257f, z, -0.0161657367f);  // Abramowitz-Stegun 4.4.49, |err| <= 2e-8 on [0, 1]
+  p = fmaf(p, z, 0.0429096138f);
+  p = fmaf(p, z, -0.0752896400f);
+  p = fmaf(p, z, 0.1065626393f);
+  p = fmaf(p, z, -0.1420889944f);
+  p = fmaf(p, z, 0.1999355085f);
+  p = fmaf(p, z, -0.3333314528f);
+  float h = fmaf(p * z, t, t);
+  h = fsel(s > ad, 1.57079632679f - h, h);
+  return fast_ex2(-4.08055779f * h);  // exp(-sqrt(2) * 2h) = 2^(-2 sqrt(2) log2(e) h)
+}
+
 // The reverse step of diffusion.py:291-326 on quaternions (one atan2 per log, one sincos per exp):
 //   x0_hat = so3_scale(x_t, a) @ exp(hat(b pred))^T ;  mean = so3_scale(x0_hat, c1) @ so3_scale(x_t, c2)
 // Returns the mean as a quaternion; *x0h receives x0_hat.

@@ -40,33 +40,10 @@ __device__ __forceinline__ float4 load_quat(const float* __restrict__ R, int64_t
   return make_float4(q[0], q[1], q[2], q[3]);
 }
 
-// value of the kernel for the pair of unit quaternions (real part in .x)
+// value of the kernel for the pair of unit quaternions (real part in .x); arithmetic in so3d_math.cuh
 template <int kKernel>
 __device__ __forceinline__ float pair_value(const float4 a, const float4 b) {
-  // conj(a) (x) b:  scalar d = cos(theta/2) (up to sign), vector v with |v| = sin(theta/2)
-  const float d = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
-  const float vx = fmaf(a.x, b.y, fmaf(-b.x, a.y, fmaf(a.w, b.z, -(a.z * b.w))));
-  const float vy = fmaf(a.x, b.z, fmaf(-b.x, a.z, fmaf(a.y, b.w, -(a.w * b.y))));
-  const float vz = fmaf(a.x, b.w, fmaf(-b.x, a.w, fmaf(a.z, b.y, -(a.y * b.z))));
-  const float s2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
-  if (kKernel == SO3D_PAIR_COSINE) return fmaf(d, d, -s2);  // cos(theta) = d^2 - s^2   (util.py:136-150)
-  const float s = s2 * rsqrt_approx(fmaxf(s2, 1e-37f));
-  const float ad = fabsf(d);
-  // theta/2 = atan2(s, |d|) in [0, pi/2]; s^2 + d^2 = 1 so max(s, |d|) >= 0.707: no zero guard needed
-  const float hi = fmaxf(ad, s), lo = fminf(ad, s);
-  const float t = lo * rcp_approx(hi);
-  const float z = t * t;
-  float p = fmaf(0.0028662257f, z, -0.0161657367f);  // Abramowitz-Stegun 4.4.49, |err| <= 2e-8 on [0, 1]
-  p = fmaf(p, z, 0.0429096138f);
-  p = fmaf(p, z, -0.0752896400f);
-  p = fmaf(p, z, 0.1065626393f);
-  p = fmaf(p, z, -0.1420889944f);
-  p = fmaf(p, z, 0.1999355085f);
-  p = fmaf(p, z, -0.3333314528f);
-  float h = fmaf(p * z, t, t);
-  h = fsel(s > ad, 1.57079632679f - h, h);
-  // exp(-sqrt(2) theta) = 2^(-2 sqrt(2) log2(e) h)                                      (util.py:128-134, 315-322)
-  return fast_ex2(-4.08062774f * h);
+  return so3_pair_kernel<kKernel == SO3D_PAIR_GAUSSIAN>(Quat{a.x, a.y, a.z, a.w}, Quat{b.x, b.y, b.z, b.w});
 }
 
 struct PairArgs {

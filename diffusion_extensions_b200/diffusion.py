@@ -23,8 +23,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .distributions import IsotropicGaussianSO3
-from .util import compose, rmat_dist, so3_scale
+from .distributions import IGSO3xR3, IsotropicGaussianSO3
+from .util import AffineGrad, AffineT, compose, rmat_dist, se3_scale, so3_scale
 
 
 def exists(x):
@@ -260,4 +260,150 @@ class ProjectedSO3Diffusion(SO3Diffusion):
         return super().forward(x, *args, **kwargs)
 
 
-__all__ = ["SO3Diffusion", "ProjectedSO3Diffusion", "extract", "cosine_beta_schedule", "exists", "default"]
+class SE3Diffusion(SO3Diffusion):
+    """diffusion.py:432-523: diffusion on SE(3) elements (`AffineT`): IGSO(3) noise on the rotation, Gaussian noise of
+    scale eps * shift_scale on the translation, both halves of every step in ONE fused kernel
+    (`so3d_se3_q_sample_f32` / `so3d_se3_p_sample_f32`).  Batches may carry extra frame dims, e.g. (B, N_res) protein
+    backbone frames with a (B,) step index (prot_train.py): t broadcasts over the trailing batch dims.
+    Same schedule buffers as the reference (it derives from GaussianDiffusion; state-dict compatible)."""
+
+    def __init__(self, denoise_fn, timesteps=1000, loss_type="grad_mse", betas=None, shift_scale=75.0, reference_quirks=False):
+        super().__init__(denoise_fn, timesteps=timesteps, loss_type=loss_type, betas=betas, reference_quirks=reference_quirks)
+        self.shift_scale = shift_scale
+
+    def _sigma(self):
+        key = str(self.betas.device)
+        if getattr(self, "_sigma_cache", None) is None or self._sigma_cache[0] != key:
+            self._sigma_cache = (key, (0.5 * self.posterior_log_variance_clipped).exp().contiguous())  # diffusion.py:481
+        return self._sigma_cache[1]
+
+    def _sched(self):
+        return (self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.posterior_mean_coef1, self.posterior_mean_coef2)
+
+    # ---- forward process ----------------------------------------------------------------------
+    def q_mean_variance(self, x_start, t):
+        """diffusion.py:438-442."""
+        mean = se3_scale(x_start, extract(self.sqrt_alphas_cumprod, t, t.shape))
+        variance = extract(1.0 - self.alphas_cumprod, t, x_start.shape)
+        log_variance = extract(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
+
+    def noise_and_target(self, x_start: AffineT, t):
+        """One fused launch: noise ~ IGSO3xR3(eps_t, shift_scale), x_t, and both 'grad_mse' targets
+        (diffusion.py:508-516).  -> (x_t: AffineT, target: AffineGrad)"""
+        fwd, _, _ = self.tables()
+        out = ops.se3_q_sample_fused(x_start.rot, x_start.shift, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, fwd,
+                                     self.shift_scale, row_offset=self.row_offset, guide=self.guides()[0])
+        return AffineT(out["rot"], out["shift"]), AffineGrad(out["target_rot"], out["target_shift"])
+
+    def q_sample(self, x_start: AffineT, t, noise: AffineT = None):
+        """diffusion.py:498-506."""
+        if noise is None:
+            return self.noise_and_target(x_start, t)[0]
+        rot = ops.q_sample_given(x_start.rot, ops._rows_t(t, x_start.rot.shape[:-2], x_start.rot.device), self.sqrt_alphas_cumprod, noise.rot)
+        scale = self.sqrt_alphas_cumprod[t].reshape(tuple(t.shape) + (1,) * (x_start.shift.dim() - t.dim()))
+        return AffineT(rot, x_start.shift * scale + noise.shift)
+
+    # ---- reverse process ----------------------------------------------------------------------
+    def _step(self, x: AffineT, predict: AffineGrad, t, noise: bool):
+        _, post, _ = self.tables()
+        rot, shift = ops.se3_p_sample_fused(x.rot, x.shift, predict.rot_g, predict.shift_g, t, *self._sched(), self._sigma(), self.shift_scale,
+                                            post_cdf=post if noise else None, post_guide=self.guides()[1] if noise else None,
+                                            row_offset=self.row_offset)
+        return AffineT(rot, shift)
+
+    def predict_start_from_noise(self, x_t: AffineT, t, noise: AffineGrad):
+        """diffusion.py:444-455."""
+        rot = SO3Diffusion.predict_start_from_noise(self, x_t.rot, t, noise.rot_g)
+        tb = t.reshape(tuple(t.shape) + (1,) * (x_t.shift.dim() - t.dim()))
+        return AffineT(rot, x_t.shift * self.sqrt_recip_alphas_cumprod[tb] - noise.shift_g * self.sqrt_recipm1_alphas_cumprod[tb])
+
+    def q_posterior(self, x_start: AffineT, x_t: AffineT, t):
+        """diffusion.py:457-464."""
+        c_1 = se3_scale(x_start, self.posterior_mean_coef1[t])
+        c_2 = se3_scale(x_t, self.posterior_mean_coef2[t])
+        posterior_mean = AffineT(compose(c_1.rot, c_2.rot), c_1.shift + c_2.shift)
+        return posterior_mean, extract(self.posterior_variance, t, t.shape), extract(self.posterior_log_variance_clipped, t, t.shape)
+
+    def _denoise(self, x: AffineT, t):
+        return self.denoise_fn(x, t)
+
+    def p_mean_variance(self, x: AffineT, t, clip_denoised: bool = False):
+        """diffusion.py:466-471 (posterior mean of both halves in one launch)."""
+        predict = self._denoise(x, t)
+        mean = self._step(x, predict, t, noise=False)
+        return mean, extract(self.posterior_variance, t, t.shape), extract(self.posterior_log_variance_clipped, t, t.shape)
+
+    @torch.no_grad()
+    def p_sample(self, x: AffineT, t, clip_denoised=False, repeat_noise=False):
+        """diffusion.py:473-485: one fused kernel after the denoiser; rows with t == 0 get no noise (device-side check)."""
+        return self._step(x, self._denoise(x, t), t, noise=True)
+
+    @torch.no_grad()
+    def p_sample_loop(self, shape, init="haar", progress=False):
+        """diffusion.py:487-496 (the reference starts from rotations only; here the translation starts at
+        N(0, shift_scale^2 I), the forward process's terminal law, like ProjectedSE3Diffusion does with N(0, I))."""
+        device = self.betas.device
+        shape = tuple(shape)
+        x = AffineT(self._init_rot(shape, init), torch.randn(*shape, 3, device=device) * self.shift_scale)
+        for i in self._steps(progress):
+            x = self.p_sample(x, torch.full(shape[:1], i, device=device, dtype=torch.long))
+        return x
+
+    def _init_rot(self, shape, init):
+        device = self.betas.device
+        if init == "haar":
+            return ops.quat_to_rmat(torch.randn(*shape, 4, device=device))
+        if init == "igso3_1":
+            return IsotropicGaussianSO3(torch.ones([], device=device)).sample(shape, row_offset=self.row_offset)
+        raise ValueError("init must be 'igso3_1' or 'haar'")
+
+    def _steps(self, progress):
+        steps = reversed(range(0, self.num_timesteps))
+        if progress:
+            from tqdm import tqdm
+
+            steps = tqdm(steps, desc="sampling loop time step", total=self.num_timesteps)
+        return steps
+
+    # ---- training loss ------------------------------------------------------------------------
+    def p_losses(self, x_start: AffineT, t, noise=None):
+        """diffusion.py:508-520."""
+        x_noisy, target = self.noise_and_target(x_start, t)
+        x_recon = self._denoise(x_noisy, t)
+        if self.loss_type != "grad_mse":
+            raise RuntimeError(f"Unexpected loss_type: {self.loss_type}")  # the reference forgets to raise (Q9)
+        rot_g = x_recon.rot_g if hasattr(x_recon, "rot_g") else x_recon.rot
+        shift_g = x_recon.shift_g if hasattr(x_recon, "shift_g") else x_recon.shift
+        return F.mse_loss(shift_g, target.shift_g) + F.mse_loss(rot_g, target.rot_g)
+
+    def forward(self, x: AffineT, *args, **kwargs):
+        b, device = len(x), x.device
+        t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
+        return self.p_losses(x, t, *args, **kwargs)
+
+
+class ProjectedSE3Diffusion(SE3Diffusion):
+    """diffusion.py:526-573: the denoiser sees projection(x)."""
+
+    def _denoise(self, x: AffineT, t):
+        return self.denoise_fn(self.projection(x), t)
+
+    @torch.no_grad()
+    def p_sample_loop(self, shape, projection, init="haar", progress=False):
+        """diffusion.py:541-552: translation starts from N(0, I) as in the reference."""
+        self.projection = projection
+        device = self.betas.device
+        shape = tuple(shape)
+        x = AffineT(self._init_rot(shape, init), torch.randn(*shape, 3, device=device))
+        for i in self._steps(progress):
+            x = self.p_sample(x, torch.full(shape[:1], i, device=device, dtype=torch.long))
+        return x
+
+    def forward(self, x: AffineT, projection, *args, **kwargs):
+        self.projection = projection
+        return super().forward(x, *args, **kwargs)
+
+
+__all__ = ["SO3Diffusion", "ProjectedSO3Diffusion", "SE3Diffusion", "ProjectedSE3Diffusion", "extract", "cosine_beta_schedule",
+           "exists", "default"]

@@ -22,9 +22,10 @@ above; <= 1e-5 relative everywhere), "series_adaptive".
 tiny eps too.  Quirk Q1 (column-0 gather with batched eps) is a plain bug and is not reproduced.
 """
 import torch
-from torch.distributions import Distribution, MultivariateNormal, constraints
+from torch.distributions import Distribution, MultivariateNormal, Normal, constraints
 
 from . import ops
+from .util import AffineT
 
 
 class _LogProb(torch.autograd.Function):
@@ -142,6 +143,40 @@ class IsotropicGaussianSO3(Distribution):
         return logp[..., None], score
 
 
+class IGSO3xR3(Distribution):
+    """distributions.py:84-110: product of IGSO3(eps) on the rotation and N(shift, (eps * shift_scale)^2 I) on the
+    translation of an SE(3) element (`AffineT`).  `sample` draws both halves on the device."""
+
+    arg_constraints = {"eps": constraints.positive}
+
+    def __init__(self, eps: torch.Tensor, mean: AffineT = None, shift_scale=1.0, mode: str = "auto"):
+        self.eps = eps
+        if mean is None:
+            rot = torch.eye(3, device=eps.device).unsqueeze(0)
+            shift = torch.zeros(*eps.shape, 3).to(eps)
+            mean = AffineT(shift=shift, rot=rot)
+        self._mean = mean.to(eps.device)
+        self.shift_scale = shift_scale
+        self.igso3 = IsotropicGaussianSO3(eps=eps, mean=self._mean.rot, mode=mode)
+        self.r3 = Normal(loc=self._mean.shift, scale=eps[..., None] * shift_scale)
+        super().__init__(validate_args=False)
+
+    @torch.no_grad()
+    def sample(self, sample_shape=torch.Size()):
+        rot = self.igso3.sample(sample_shape)
+        shift = self.r3.sample(sample_shape)
+        return AffineT(rot, shift)
+
+    def log_prob(self, value):
+        rot_prob = self.igso3.log_prob(value.rot)      # (..., 1)
+        shift_prob = self.r3.log_prob(value.shift)     # (..., 3)
+        return rot_prob + shift_prob
+
+    @property
+    def mean(self):
+        return self._mean
+
+
 class Bingham(MultivariateNormal):
     """distributions.py:113-127: zero-mean Gaussian in R^4 pushed onto the unit quaternions (real part first).
 
@@ -182,4 +217,4 @@ class Bingham(MultivariateNormal):
         return ops.bingham_sample(self._unbroadcasted_scale_tril, shape, z=z, row_offset=self.row_offset, want_quat=False, want_rmat=True)
 
 
-__all__ = ["IsotropicGaussianSO3", "Bingham"]
+__all__ = ["IsotropicGaussianSO3", "IGSO3xR3", "Bingham"]

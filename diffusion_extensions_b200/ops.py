@@ -417,6 +417,77 @@ def igso3_sample(cdf, shape, row_idx=None, row=0, u=None, axes=None, seed=None, 
 
 
 # ---------------------------------------------------------------------------------------------
+# SE(3) arm: fused forward noising / reverse step on (rotation, translation) pairs (diffusion.py:432-573)
+# ---------------------------------------------------------------------------------------------
+def _rows_t(t, bs, dev):
+    """t (int64) broadcast against the batch shape `bs`: leading dims are matched first, like the reference's
+    extract(a, t, t.shape)[..., None] broadcasting of a (B,) step index over (B, N_res, ...) frames."""
+    t = t.to(device=dev, dtype=torch.int64)
+    if tuple(t.shape) != tuple(bs):
+        t = t.reshape(tuple(t.shape) + (1,) * (len(bs) - t.dim())).expand(bs)
+    return t.contiguous()
+
+
+def se3_q_sample_fused(rot0, shift0, t, sqrt_ac, sqrt_1m_ac, cdf, shift_scale, seed=None, rng_offset=None, row_offset=0,
+                       want_target=True, guide=None):
+    """-> dict(rot, shift, target_rot, target_shift)."""
+    rot0, bs, n = _rows9(rot0, "x_start.rot")
+    dev = rot0.device
+    shift0 = check_f32(shift0, "x_start.shift", (3,)).expand(*bs, 3).contiguous()
+    t = _rows_t(t, bs, dev)
+    sqrt_ac = check_f32(sqrt_ac, "sqrt_alphas_cumprod")
+    sqrt_1m_ac = check_f32(sqrt_1m_ac, "sqrt_one_minus_alphas_cumprod")
+    cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
+    T = sqrt_ac.numel()
+    if cdf.numel() != T * CDF_POINTS:
+        raise ValueError("cdf table must have one row per timestep")
+    _check_guide(guide, T, "guide")
+    _, _, trap_loc = cdf_grid(dev)
+    if seed is None or rng_offset is None:
+        seed, rng_offset = rng.next()
+    rot_t, shift_t = torch.empty_like(rot0), torch.empty_like(shift0)
+    tr = torch.empty_like(shift0) if want_target else None
+    ts = torch.empty_like(shift0) if want_target else None
+    call("so3d_se3_q_sample_f32", ptr(rot0), ptr(shift0), ptr(t), ptr(sqrt_ac), ptr(sqrt_1m_ac), T, ptr(cdf), ptr(guide), ptr(trap_loc),
+         float(shift_scale), seed, rng_offset, int(row_offset), ptr(rot_t), ptr(shift_t), ptr(tr), ptr(ts), n, device=dev)
+    return {"rot": rot_t, "shift": shift_t, "target_rot": tr, "target_shift": ts}
+
+
+def se3_p_sample_fused(rot_t, shift_t, pred_rot, pred_shift, t, recip, recipm1, coef1, coef2, sigma, shift_scale, post_cdf=None,
+                       seed=None, rng_offset=None, row_offset=0, post_guide=None):
+    """Fused SE(3) reverse step; t with one element = shared step.  post_cdf None -> posterior mean only.
+    -> (rot (...,3,3), shift (...,3))"""
+    rot_t, bs, n = _rows9(rot_t, "x.rot")
+    dev = rot_t.device
+    shift_t = check_f32(shift_t, "x.shift", (3,)).expand(*bs, 3).contiguous()
+    pred_rot = check_f32(pred_rot, "predict.rot_g", (3,)).expand(*bs, 3).contiguous()
+    pred_shift = check_f32(pred_shift, "predict.shift_g", (3,)).expand(*bs, 3).contiguous()
+    t = t.to(device=dev, dtype=torch.int64)
+    if t.numel() == 1:
+        t, t_stride = t.reshape(1).contiguous(), 0
+    else:
+        t, t_stride = _rows_t(t, bs, dev), 1
+    recip, recipm1 = check_f32(recip, "sqrt_recip_alphas_cumprod"), check_f32(recipm1, "sqrt_recipm1_alphas_cumprod")
+    coef1, coef2 = check_f32(coef1, "posterior_mean_coef1"), check_f32(coef2, "posterior_mean_coef2")
+    sigma = check_f32(sigma, "sigma")
+    T = recip.numel()
+    trap_loc = None
+    if post_cdf is not None:
+        post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
+        if post_cdf.numel() != T * CDF_POINTS:
+            raise ValueError("posterior cdf table must have one row per timestep")
+        _check_guide(post_guide, T, "post_guide")
+        _, _, trap_loc = cdf_grid(dev)
+        if seed is None or rng_offset is None:
+            seed, rng_offset = rng.next()
+    rot_out, shift_out = torch.empty_like(rot_t), torch.empty_like(shift_t)
+    call("so3d_se3_p_sample_f32", ptr(rot_t), ptr(shift_t), ptr(pred_rot), ptr(pred_shift), ptr(t), t_stride, ptr(recip), ptr(recipm1),
+         ptr(coef1), ptr(coef2), ptr(sigma), T, ptr(post_cdf), ptr(post_guide), ptr(trap_loc), float(shift_scale), seed or 0, rng_offset or 0,
+         int(row_offset), ptr(rot_out), ptr(shift_out), n, device=dev)
+    return rot_out, shift_out
+
+
+# ---------------------------------------------------------------------------------------------
 # data side: Bingham quaternions (distributions.py:113-127), optionally straight to rotation matrices
 # ---------------------------------------------------------------------------------------------
 def bingham_sample(scale_tril, shape, z=None, seed=None, rng_offset=None, row_offset=0, want_quat=True, want_rmat=False):
@@ -479,7 +550,7 @@ def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, 
     """-> dict(x_t, target, noise, score) (absent entries are None)."""
     x0, bs, n = _rows9(x0, "x_start")
     dev = x0.device
-    t = t.to(device=dev, dtype=torch.int64).expand(bs).contiguous()
+    t = _rows_t(t, bs, dev)
     sqrt_ac = check_f32(sqrt_ac, "sqrt_alphas_cumprod")
     sqrt_1m_ac = check_f32(sqrt_1m_ac, "sqrt_one_minus_alphas_cumprod")
     cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
@@ -502,7 +573,7 @@ def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, 
 def q_sample_given(x0, t, sqrt_ac, noise):
     x0, bs, n = _rows9(x0, "x_start")
     noise = check_f32(noise, "noise", (3, 3)).expand_as(x0).contiguous()
-    t = t.to(device=x0.device, dtype=torch.int64).expand(bs).contiguous()
+    t = _rows_t(t, bs, x0.device)
     sqrt_ac = check_f32(sqrt_ac, "sqrt_alphas_cumprod")
     out = torch.empty_like(x0)
     call("so3d_q_sample_given_f32", ptr(x0), ptr(t), ptr(sqrt_ac), sqrt_ac.numel(), ptr(noise), ptr(out), n, device=x0.device)
@@ -520,7 +591,7 @@ def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, se
     if t.numel() == 1:
         t, t_stride = t.reshape(1).contiguous(), 0
     else:
-        t, t_stride = t.expand(bs).contiguous(), 1
+        t, t_stride = _rows_t(t, bs, dev), 1
     recip, recipm1 = check_f32(recip, "sqrt_recip_alphas_cumprod"), check_f32(recipm1, "sqrt_recipm1_alphas_cumprod")
     coef1, coef2 = check_f32(coef1, "posterior_mean_coef1"), check_f32(coef2, "posterior_mean_coef2")
     T = recip.numel()

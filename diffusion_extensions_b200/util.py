@@ -21,6 +21,73 @@ from . import ops
 
 
 # ---------------------------------------------------------------------------------------------
+# SE(3) containers (util.py:10-56): a rotation (...,3,3) with a translation (...,3), and the matching
+# tangent-space pair the SE(3) denoisers return
+# ---------------------------------------------------------------------------------------------
+class AffineT(object):
+    def __init__(self, rot: torch.Tensor, shift: torch.Tensor):
+        super().__init__()
+        self.rot = rot
+        self.shift = shift
+
+    def __len__(self):
+        return max(len(self.rot), len(self.shift))
+
+    def __getitem__(self, item):
+        return AffineT(self.rot[item], self.shift[item])
+
+    @property
+    def device(self):
+        return self.rot.device
+
+    @property
+    def shape(self):
+        return self.shift.shape
+
+    def to(self, device):
+        return AffineT(self.rot.to(device), self.shift.to(device))
+
+    @classmethod
+    def from_euler(cls, euls: torch.Tensor, shift: torch.Tensor):
+        return cls(euler_to_rmat(*torch.unbind(euls, dim=-1)), shift)
+
+    def detach(self):
+        return AffineT(self.rot.detach(), self.shift.detach())
+
+
+class AffineGrad(object):
+    def __init__(self, rot_g, shift_g):
+        super().__init__()
+        self.rot_g = rot_g
+        self.shift_g = shift_g
+
+    def __len__(self):
+        return max(len(self.rot_g), len(self.shift_g))
+
+    def __getitem__(self, item):
+        return AffineGrad(self.rot_g[item], self.shift_g[item])
+
+
+def euler_to_rmat(x, y, z):
+    """util.py:396-422: R = R_z R_y R_x from the three Euler angles, with the reference's sign convention for
+    R_y (its [2,0] entry is +sin y).  Plain torch: data preparation only."""
+    cx, sx, cy, sy, cz, sz = torch.cos(x), torch.sin(x), torch.cos(y), -torch.sin(y), torch.cos(z), torch.sin(z)
+    rows = (cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx,
+            sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx,
+            -sy, cy * sx, cy * cx)
+    return torch.stack(rows, dim=-1).reshape(x.shape + (3, 3))
+
+
+def rmat_to_euler(rmat: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """util.py:388-393."""
+    sy = torch.sqrt(rmat[..., 0, 0] * rmat[..., 0, 0] + rmat[..., 1, 0] * rmat[..., 1, 0])
+    x = torch.atan2(rmat[..., 2, 1], rmat[..., 2, 2])
+    y = torch.atan2(rmat[..., 2, 0], sy)
+    z = torch.atan2(rmat[..., 1, 0], rmat[..., 0, 0])
+    return x, y, z
+
+
+# ---------------------------------------------------------------------------------------------
 # hat / vee  (util.py:79-92) -- pure data movement, kept as torch indexing (fused away inside the
 # kernels wherever they sit on the hot path)
 # ---------------------------------------------------------------------------------------------
@@ -199,6 +266,16 @@ def so3_scale(rmat, scalars):
     return ops.so3_scale(rmat, scalars)
 
 
+def se3_lerp(transf_a: AffineT, transf_b: AffineT, weight: torch.Tensor) -> AffineT:
+    """util.py:364-379: so3_lerp on the rotations, torch.lerp on the translations."""
+    return AffineT(so3_lerp(transf_a.rot, transf_b.rot, weight), torch.lerp(transf_a.shift, transf_b.shift, weight))
+
+
+def se3_scale(transf: AffineT, scalars) -> AffineT:
+    """util.py:382-385: so3_scale on the rotation, plain scaling of the translation."""
+    return AffineT(so3_scale(transf.rot, scalars), transf.shift * scalars[..., None])
+
+
 def compose(a, b, trans_a=False, trans_b=False):
     """Batched 3x3 product op(a) @ op(b) as one kernel (no autograd; use `@` when gradients are needed)."""
     return ops.compose(a, b, trans_a, trans_b)
@@ -272,5 +349,6 @@ def Ker_2samp_log_prob(X, Y, kernel, max_ker=1, chunksize=None):
 __all__ = [
     "skew2vec", "vec2skew", "orthogonalise", "log_rmat", "log_vec", "aa_to_rmat", "exp_vec", "rmat_to_aa",
     "quat_to_rmat", "rmat_to_quat", "rmat_dist", "so3_lerp", "so3_scale", "compose",
+    "AffineT", "AffineGrad", "euler_to_rmat", "rmat_to_euler", "se3_lerp", "se3_scale",
     "rmat_cosine_dist", "rmat_gaussian_kernel", "rmat_cosine_kernel", "MMD", "Ker_2samp_test", "Ker_2samp_log_prob",
 ]

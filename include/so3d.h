@@ -147,6 +147,27 @@ int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, in
                       const uint32_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                       float* out, float* x0_hat_out, int64_t n, void* stream);
 
+/* ---- SE(3) arm: diffusion.py SE3Diffusion / distributions.py IGSO3xR3 --------------- */
+/* diffusion.py:498-516 (SE3Diffusion.q_sample + p_losses targets), fused.  Rotation half exactly as
+ * so3d_q_sample_f32 (same Philox block: identical rotation draws at the same seed / rng_offset); translation half
+ *   shift_t = sqrt_ac[t] shift0 + sqrt_1m_ac[t] shift_scale z,   target_shift3 = z = noise_shift / (eps_t shift_scale)
+ * with z ~ N(0, I3) from Philox(seed, row_offset + i, rng_offset | 2^63)  (distributions.py:84-110 IGSO3xR3.sample).
+ * target_rot3 / target_shift3 nullable.  rng_offset < 2^63. */
+int so3d_se3_q_sample_f32(const float* rot0, const float* shift0, const int64_t* t, const float* sqrt_ac,
+                          const float* sqrt_1m_ac, int64_t T, const float* cdf, const uint32_t* guide, const float* loc,
+                          float shift_scale, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* rot_t,
+                          float* shift_t, float* target_rot3, float* target_shift3, int64_t n, void* stream);
+/* diffusion.py:446-485 (SE3Diffusion.predict_start_from_noise, q_posterior, p_sample), fused.  Rotation half as
+ * so3d_p_sample_f32; translation half
+ *   shift0_hat = recip[t] shift_t - recipm1[t] pred_shift;  mean = coef1[t] shift0_hat + coef2[t] shift_t;
+ *   shift_out = t == 0 ? mean : mean + sigma[t] shift_scale z      (sigma[t] = exp(posterior_log_variance_clipped[t]/2))
+ * post_cdf == NULL returns the posterior mean only (p_mean_variance). */
+int so3d_se3_p_sample_f32(const float* rot_t, const float* shift_t, const float* pred_rot3, const float* pred_shift3,
+                          const int64_t* t, int t_stride, const float* recip, const float* recipm1, const float* coef1,
+                          const float* coef2, const float* sigma, int64_t T, const float* post_cdf,
+                          const uint32_t* post_guide, const float* loc, float shift_scale, uint64_t seed, uint64_t rng_offset,
+                          uint64_t row_offset, float* rot_out, float* shift_out, int64_t n, void* stream);
+
 /* ---- data side: distributions.py Bingham ------------------------------------------- */
 /* distributions.py:113-127 Bingham.rsample (zero-mean MultivariateNormal in R^4, normalised to a unit quaternion,
  * real part first) fused with util.py:222-252 quat_to_rmat (bingham_train.py:88-90):

@@ -188,9 +188,56 @@ def main_eval():
     save("evaluation", **out)
 
 
+def main_se3():
+    """SE(3) arm fixtures: the reference's SE3Diffusion forward / reverse algebra on AffineT batches
+    with explicit noise, IGSO3xR3 draws with the underlying normals recorded, se3_scale and the Euler helpers."""
+    g = torch.Generator().manual_seed(4321)
+    proc = rdiff.SE3Diffusion(None)
+    bufs = {k: v for k, v in proc.named_buffers()}
+    B, ss = 96, proc.shift_scale
+    rot0, _, _ = rand_rot(B, g)
+    x0 = rutil.AffineT(rot0, torch.randn(B, 3, generator=g) * 10.0)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    t[:4] = torch.tensor([0, 1, 998, 999])
+    eps_t = bufs["sqrt_one_minus_alphas_cumprod"][t]
+    noise_rot = torch.stack([rdist.IsotropicGaussianSO3(e).sample()[0] for e in eps_t])
+    z = torch.randn(B, 3, generator=g)
+    noise = rutil.AffineT(noise_rot, z * (eps_t * ss)[:, None])
+    x_t = proc.q_sample(x0, t, noise=noise)
+    tgt_shift = noise.shift * (1 / (eps_t * ss))[..., None]                               # diffusion.py:514
+    tgt_rot = rutil.skew2vec(rutil.log_rmat(noise.rot)) * (1 / eps_t)[..., None]          # diffusion.py:515
+    pred = rutil.AffineGrad(torch.randn(B, 3, generator=g) * 0.5, torch.randn(B, 3, generator=g))
+    t_rev = torch.randint(0, 600, (B,), generator=g)
+    t_rev[:2] = torch.tensor([0, 1])
+    x_recon = proc.predict_start_from_noise(x_t, t_rev, pred)
+    post_mean, post_var, post_logvar = proc.q_posterior(x_recon, x_t, t_rev)
+    proc.denoise_fn = lambda x, tt: pred
+    mean_pm, _, _ = proc.p_mean_variance(x_t, t_rev, clip_denoised=False)
+    # IGSO3xR3 with a scalar eps and a batched mean (what SE3Diffusion.p_sample builds, diffusion.py:482): the
+    # rotation noise is ONE draw shared by the whole batch (axes = randn((3,)), quirk Q12), the shift noise is per row
+    sig = torch.tensor(0.25)
+    d = rdist.IGSO3xR3(eps=sig, mean=post_mean, shift_scale=ss)
+    torch.manual_seed(55)
+    smp = d.sample()
+    torch.manual_seed(55)
+    ax = torch.randn((3,)); u = torch.rand(()); zz = torch.empty(B, 3).normal_()
+    assert torch.allclose(smp.shift, post_mean.shift + zz * sig * ss, atol=1e-4), "normals do not reproduce the reference's shift draw"
+    scal = torch.rand(B, generator=g) * 1.5 + 0.1
+    sc = rutil.se3_scale(x0, scal)
+    eul = torch.rand(B, 3, generator=g) * 2 - 1
+    R_e = rutil.euler_to_rmat(*eul.unbind(-1))
+    save(
+        "se3",
+        shift_scale=np.float32(ss), rot0=x0.rot, shift0=x0.shift, t=t, eps_t=eps_t, noise_rot=noise.rot, noise_shift=noise.shift, z=z,
+        xt_rot=x_t.rot, xt_shift=x_t.shift, tgt_rot=tgt_rot, tgt_shift=tgt_shift, pred_rot=pred.rot_g, pred_shift=pred.shift_g, t_rev=t_rev,
+        recon_rot=x_recon.rot, recon_shift=x_recon.shift, post_rot=post_mean.rot, post_shift=post_mean.shift, post_var=post_var,
+        post_logvar=post_logvar, pm_rot=mean_pm.rot, pm_shift=mean_pm.shift,
+        smp_sigma=sig, smp_rot=smp.rot, smp_shift=smp.shift, smp_axis=ax, smp_u=u, smp_z=zz,
+        scal=scal, scaled_rot=sc.rot, scaled_shift=sc.shift, eul=eul, eul_rmat=R_e, eul_back=torch.stack(rutil.rmat_to_euler(R_e), -1),
+    )
+
+
 if __name__ == "__main__":
-    if "eval" in sys.argv[1:]:
-        main_eval()
-    else:
-        main()
-        main_eval()
+    todo = [a for a in sys.argv[1:] if a in ("core", "eval", "se3")] or ["core", "eval", "se3"]
+    for name in todo:
+        {"core": main, "eval": main_eval, "se3": main_se3}[name]()

@@ -506,6 +506,48 @@ def p_sample(x_t, pred, sqrt_recip_ac, sqrt_recipm1_ac, coef1, coef2, noise=None
 # ----------------------------------------------------------------------------------------------
 # helpers for tests / benchmarks
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# SE(3) arm (diffusion.py:432-523, util.py:382-385, distributions.py:84-110): (rotation, translation) pairs
+# ----------------------------------------------------------------------------------------------
+def se3_scale(rot, shift, scalars):
+    """util.py:382-385: so3_scale on the rotation, shift * scalars[..., None]."""
+    scalars = np.asarray(scalars, dtype=np.float64)
+    return so3_scale(rot, scalars), np.asarray(shift, dtype=np.float64) * scalars[..., None]
+
+
+def se3_q_sample(rot0, shift0, scale, noise_rot, noise_shift):
+    """diffusion.py:498-506: (so3_scale(rot0, a) @ noise_rot, a shift0 + noise_shift)."""
+    r, s = se3_scale(rot0, shift0, scale)
+    return r @ np.asarray(noise_rot, dtype=np.float64), s + np.asarray(noise_shift, dtype=np.float64)
+
+
+def se3_targets(noise_rot, noise_shift, eps, shift_scale):
+    """diffusion.py:514-515: (vee(log noise_rot)/eps, noise_shift/(eps shift_scale))."""
+    eps = np.asarray(eps, dtype=np.float64)
+    return skewvec_target(noise_rot, eps), np.asarray(noise_shift, dtype=np.float64) / (eps * shift_scale)[..., None]
+
+
+def se3_predict_start(rot_t, shift_t, pred_rot, pred_shift, sqrt_recip_ac, sqrt_recipm1_ac):
+    """diffusion.py:444-455."""
+    rot = predict_start_from_noise(rot_t, pred_rot, sqrt_recip_ac, sqrt_recipm1_ac)
+    a = np.asarray(sqrt_recip_ac, dtype=np.float64)[..., None]
+    b = np.asarray(sqrt_recipm1_ac, dtype=np.float64)[..., None]
+    return rot, np.asarray(shift_t, dtype=np.float64) * a - np.asarray(pred_shift, dtype=np.float64) * b
+
+
+def se3_posterior_mean(rot0, shift0, rot_t, shift_t, coef1, coef2):
+    """diffusion.py:457-460."""
+    c1 = np.asarray(coef1, dtype=np.float64)[..., None]
+    c2 = np.asarray(coef2, dtype=np.float64)[..., None]
+    return q_posterior_mean(rot0, rot_t, coef1, coef2), c1 * np.asarray(shift0, dtype=np.float64) + c2 * np.asarray(shift_t, dtype=np.float64)
+
+
+def se3_p_mean(rot_t, shift_t, pred_rot, pred_shift, sqrt_recip_ac, sqrt_recipm1_ac, coef1, coef2):
+    """diffusion.py:466-471: posterior mean given the denoiser output."""
+    r0, s0 = se3_predict_start(rot_t, shift_t, pred_rot, pred_shift, sqrt_recip_ac, sqrt_recipm1_ac)
+    return se3_posterior_mean(r0, s0, rot_t, shift_t, coef1, coef2)
+
+
 def random_rotations(n, rng, max_angle=PI):
     axis = rng.standard_normal((n, 3))
     axis /= np.linalg.norm(axis, axis=-1, keepdims=True)

@@ -85,6 +85,21 @@ void hm_expvec_bwd(const float* w, const float* G, float* gw, long n) {
   for (long i = 0; i < n; ++i) { Vec3 v{w[3*i], w[3*i+1], w[3*i+2]}; Vec3 g = exp_vec_bwd(v, exp_vec(v), ld(G + 9 * i)); gw[3*i]=g.x; gw[3*i+1]=g.y; gw[3*i+2]=g.z; }
 }
 }
+extern "C" void hm_pair_kernel(const float* A, const float* B, float* out, long n, int gaussian) {
+  for (long i = 0; i < n; ++i) {
+    float qa[4], qb[4];
+    rmat_to_quat(ld(A + 9 * i), qa);
+    rmat_to_quat(ld(B + 9 * i), qb);
+    const Quat a{qa[0], qa[1], qa[2], qa[3]}, b{qb[0], qb[1], qb[2], qb[3]};
+    out[i] = gaussian ? so3_pair_kernel<true>(a, b) : so3_pair_kernel<false>(a, b);
+  }
+}
+extern "C" void hm_normal4(unsigned long long seed, unsigned long long row0, unsigned long long offset, float* out, long n) {
+  for (long i = 0; i < n; ++i) {
+    const Normal4 z = normal4_from_u4(philox4x32_10(seed, row0 + i, offset));
+    out[4*i] = z.a; out[4*i+1] = z.b; out[4*i+2] = z.c; out[4*i+3] = z.d;
+  }
+}
 extern "C" void hm_logf_g(const float* w, const float* eps, float* logf, float* g, long n, int mode, int L) {
   for (long i = 0; i < n; ++i) igso3_logf_g(w[i], eps[i], mode, L, logf + i, g + i);
 }

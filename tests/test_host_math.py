@@ -357,3 +357,38 @@ def test_p_mean_quat_against_oracle(hm):
     want = O.p_sample_mean(x, pred, a.astype(np.float64), b.astype(np.float64), c1.astype(np.float64), c2.astype(np.float64))
     assert np.max(O.geodesic_angle(mean, want)) < 5e-6
     assert np.max(np.abs(mean.astype(np.float64) @ np.swapaxes(mean, -1, -2) - np.eye(3))) < 2e-6
+
+
+def test_pair_kernels(hm):
+    """util.py:128-150 kernel values through the quaternion formulation of the all-pairs MMD kernel, against the
+    oracle's matrix-log formulation: <= 1e-6 absolute, including angles at 0, near 0 and near / at pi."""
+    n = 20000
+    A, _, _ = rand_rots(n, 31)
+    B, _, _ = rand_rots(n, 32)
+    rng = np.random.default_rng(33)
+    axis = rng.standard_normal((64, 3)); axis /= np.linalg.norm(axis, axis=-1, keepdims=True)
+    special = np.concatenate([[0.0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3], math.pi - np.array([0.0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3]), rng.uniform(0, math.pi, 52)])
+    B[:64] = f32(A[:64].astype(np.float64) @ O.rodrigues(axis, special))
+    out = np.empty(n, np.float32)
+    hm.hm_pair_kernel(fp(A), fp(B), fp(out), n, 1)
+    want = O.rmat_gaussian_kernel(A, B)
+    assert np.max(np.abs(out - want)) < 1e-6
+    assert np.max(np.abs(out[:64] - np.exp(-math.sqrt(2.0) * special))) < 1e-6
+    hm.hm_pair_kernel(fp(A), fp(B), fp(out), n, 0)
+    assert np.max(np.abs(out - O.rmat_cosine_kernel(A, B))) < 1e-6
+
+
+def test_box_muller_normals(hm):
+    """The four normals per Philox block (Bingham / SE(3) translation noise): finite, standard moments, independent
+    components, and a tail that reaches beyond 4 sigma."""
+    n = 1 << 20
+    z = np.empty((n, 4), np.float32)
+    hm.hm_normal4(ctypes.c_ulonglong(99), ctypes.c_ulonglong(0), ctypes.c_ulonglong(3), fp(z), n)
+    assert np.isfinite(z).all() and np.abs(z).max() < 5.8
+    z = z.astype(np.float64)
+    assert np.max(np.abs(z.mean(0))) < 4e-3 and np.max(np.abs(z.var(0) - 1)) < 6e-3
+    assert np.max(np.abs(np.corrcoef(z.T) - np.eye(4))) < 4e-3
+    assert np.max(np.abs((z ** 4).mean(0) - 3)) < 0.05 and np.abs(z).max() > 4.0
+    # Kolmogorov distance to the normal CDF
+    from scipy.stats import kstest
+    assert kstest(z[:200000, 2], "norm").statistic < 4e-3

@@ -264,3 +264,40 @@ def test_bingham_given_normals(golden):
         q = O.bingham_sample_given(g[name + "_z"], g[name + "_tril"])
         assert np.max(np.abs(q - g[name + "_q"])) < 1e-6
         assert np.max(np.abs(O.quat_to_rmat(q) - g[name + "_R"])) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# SE(3) arm
+# ---------------------------------------------------------------------------------------------
+def test_se3_diffusion_algebra(golden):
+    g = golden("se3")
+    s = golden("schedule")
+    t, tr, ss = g["t"], g["t_rev"], float(g["shift_scale"])
+    assert ss == 75.0
+    rot, shift = O.se3_q_sample(g["rot0"], g["shift0"], s["sqrt_alphas_cumprod"][t], g["noise_rot"], g["noise_shift"])
+    assert np.max(np.abs(rot - g["xt_rot"])) < 5e-6
+    assert np.max(np.abs(shift - g["xt_shift"])) < 1e-5 * max(1.0, np.abs(g["xt_shift"]).max())
+    tgt_rot, tgt_shift = O.se3_targets(g["noise_rot"], g["noise_shift"], g["eps_t"], ss)
+    assert np.max(np.abs(tgt_rot - g["tgt_rot"]) / np.maximum(np.abs(g["tgt_rot"]), 1.0)) < 2e-5
+    assert np.max(np.abs(tgt_shift - g["tgt_shift"])) < 2e-6 and np.max(np.abs(g["tgt_shift"] - g["z"])) < 2e-6
+    ok = O.rmat_to_aa(g["xt_rot"])[1][:, 0] < 3.0
+    r0, s0 = O.se3_predict_start(g["xt_rot"], g["xt_shift"], g["pred_rot"], g["pred_shift"], s["sqrt_recip_alphas_cumprod"][tr],
+                                 s["sqrt_recipm1_alphas_cumprod"][tr])
+    assert np.max(np.abs(r0 - g["recon_rot"])[ok]) < 2e-5
+    assert np.max(np.abs(s0 - g["recon_shift"]) / np.maximum(np.abs(g["recon_shift"]), 1.0)) < 1e-5
+    ok2 = ok & (O.rmat_to_aa(g["recon_rot"])[1][:, 0] < 3.0)
+    pr, ps = O.se3_posterior_mean(g["recon_rot"], g["recon_shift"], g["xt_rot"], g["xt_shift"], s["posterior_mean_coef1"][tr],
+                                  s["posterior_mean_coef2"][tr])
+    assert np.max(np.abs(pr - g["post_rot"])[ok2]) < 2e-5
+    assert np.max(np.abs(ps - g["post_shift"]) / np.maximum(np.abs(g["post_shift"]), 1.0)) < 1e-5
+    mr, ms = O.se3_p_mean(g["xt_rot"], g["xt_shift"], g["pred_rot"], g["pred_shift"], s["sqrt_recip_alphas_cumprod"][tr],
+                          s["sqrt_recipm1_alphas_cumprod"][tr], s["posterior_mean_coef1"][tr], s["posterior_mean_coef2"][tr])
+    assert np.max(np.abs(mr - g["pm_rot"])[ok2]) < 3e-5
+    assert np.max(np.abs(ms - g["pm_shift"]) / np.maximum(np.abs(g["pm_shift"]), 1.0)) < 1e-5
+    # IGSO3xR3 draw (distributions.py:84-110): shift = mean.shift + sigma shift_scale z with the recorded normals
+    assert np.max(np.abs(g["post_shift"] + g["smp_z"] * float(g["smp_sigma"]) * ss - g["smp_shift"])) < 1e-4
+    # se3_scale (util.py:382-385)
+    sr, sh = O.se3_scale(g["rot0"], g["shift0"], g["scal"])
+    assert np.max(np.abs(sh - g["scaled_shift"])) < 1e-5
+    ok3 = O.rmat_to_aa(g["rot0"])[1][:, 0] < 3.0
+    assert np.max(np.abs(sr - g["scaled_rot"])[ok3]) < 1e-5
