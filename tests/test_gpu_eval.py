@@ -114,7 +114,7 @@ def test_mmd_full_size_properties(dx, cuda_device):
     D = dx.distributions
     loc = torch.zeros(4, device=cuda_device)
     cov3 = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0.9, 0.9], [0, 0.9, 1.0, 0.9], [0, 0.9, 0.9, 1.0]], device=cuda_device)
-    torch.manual_seed(7)
+    dx.manual_seed(7)
     A = D.Bingham(loc, covariance_matrix=cov3).sample_rmat((20_000,))
     B = D.Bingham(loc, covariance_matrix=cov3).sample_rmat((20_000,))
     C = D.Bingham(loc, covariance_matrix=torch.eye(4, device=cuda_device)).sample_rmat((20_000,))
@@ -156,9 +156,9 @@ def test_bingham_device_draws(dx, cuda_device):
     cov = np.array([[1.0, 0, 0, 0], [0, 1.0, 0.9, 0.9], [0, 0.9, 1.0, 0.9], [0, 0.9, 0.9, 1.0]])
     d = D.Bingham(torch.zeros(4, device=cuda_device), covariance_matrix=dev(cov, cuda_device))
     n = 1 << 20
-    torch.manual_seed(11)
+    dx.manual_seed(11)
     q = d.sample((n,))
-    torch.manual_seed(11)
+    dx.manual_seed(11)
     q2 = d.sample((n,))
     assert torch.equal(q, q2) and torch.isfinite(q).all()
     assert float((q.norm(dim=-1) - 1).abs().max()) < 1e-6
