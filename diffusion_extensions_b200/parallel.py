@@ -123,6 +123,41 @@ def rotation_statistics(x):
 
 
 # ---------------------------------------------------------------------------------------------
+# MMD two-sample statistic over the ranks (util.py:254-285)
+# ---------------------------------------------------------------------------------------------
+PAIR_TILE = 256  # rows per tile of the all-pairs kernel (csrc/so3d_pairwise.cu)
+
+
+def pair_tiles_of_shard(nx, ny, shard, nshards):
+    """The 256 x 256 tile pairs shard `shard` of `nshards` sums, in the kernel's order: the flat list
+    [X-X lower triangle | Y-Y lower triangle | X-Y all] dealt round-robin.  -> list of (section, bi, bj, weight),
+    section 0/1/2 = XX/YY/XY, weight 2 for the off-diagonal tiles of the symmetric sections."""
+    tx, ty = -(-nx // PAIR_TILE), -(-ny // PAIR_TILE)
+    flat = [(0, i, j, 1 if i == j else 2) for i in range(tx) for j in range(i + 1)]
+    flat += [(1, i, j, 1 if i == j else 2) for i in range(ty) for j in range(i + 1)]
+    flat += [(2, i, j, 1) for i in range(tx) for j in range(ty)]
+    return flat[shard::nshards]
+
+
+def mmd_from_sums(sums, nx, ny):
+    """util.py:281-285: mean k(X,X) + mean k(Y,Y) - 2 mean k(X,Y) from the three all-pairs sums."""
+    return sums[0] / (nx ** 2) + sums[1] / (ny ** 2) - sums[2] * (2 / (nx * ny))
+
+
+def mmd_sharded(X, Y, kernel="gaussian", pair_sums=None):
+    """MMD(X, Y) with every rank holding the full sample sets and summing its round-robin share of the tile pairs;
+    one all-reduce of three doubles.  `pair_sums(X, Y, kernel, shard=, nshards=)` defaults to the fused kernel."""
+    rank, world = world_info()
+    if pair_sums is None:
+        from . import ops
+
+        pair_sums = ops.pair_kernel_sums
+    sums = pair_sums(X, Y, kernel, shard=rank, nshards=world)
+    all_reduce_stats(sums)
+    return mmd_from_sums(sums, len(X), len(Y))
+
+
+# ---------------------------------------------------------------------------------------------
 # sharded drivers
 # ---------------------------------------------------------------------------------------------
 @torch.no_grad()

@@ -91,6 +91,28 @@ def _worker(rank, world, port, n, tmp):
     axis, u = _draw(hm, 1234, lo, 7, hi2 - lo2)
     assert np.array_equal(axis, full_axis[lo2:hi2]) and np.array_equal(u, full_u[lo2:hi2])
 
+    # ---- MMD over the ranks: round-robin tile pairs + one all-reduce of three doubles == single-process MMD.
+    # (The per-shard sums come from the fp64 oracle here; on the GPU box the fused kernel takes its place.)
+    from oracle import so3_oracle as O
+
+    rng = np.random.default_rng(5)
+    A = O.random_rotations(300 + n % 7, rng)[0]
+    B = O.random_rotations(515, rng, 1.0)[0]
+
+    def oracle_pair_sums(Xs, Ys, kernel, shard, nshards):
+        out = np.zeros(3)
+        T = P.PAIR_TILE
+        for sec, bi, bj, w in P.pair_tiles_of_shard(len(Xs), len(Ys), shard, nshards):
+            a = (Ys if sec == 1 else Xs)[bi * T:(bi + 1) * T]
+            b = (Xs if sec == 0 else Ys)[bj * T:(bj + 1) * T]
+            out[sec] += w * O.rmat_gaussian_kernel(a[:, None], b[None]).sum()
+        return torch.from_numpy(out)
+
+    got = float(P.mmd_sharded(A, B, "gaussian", pair_sums=oracle_pair_sums))
+    assert abs(got - O.mmd(A, B)) < 1e-12
+    cover = sorted(tp for sh in range(world) for tp in P.pair_tiles_of_shard(len(A), len(B), sh, world))
+    assert cover == sorted(P.pair_tiles_of_shard(len(A), len(B), 0, 1))
+
     # ---- attach(): row_offset bookkeeping on a stand-in process object
     class Proc:
         row_offset = 0
