@@ -20,6 +20,7 @@
 #include "../../include/so3d.h"
 #include "so3d_math.cuh"
 #include "so3d_tma.cuh"
+#include "so3d_cdf_smem.cuh"
 
 using namespace so3d;
 
@@ -594,26 +595,6 @@ __global__ void __launch_bounds__(256) cdf_table_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // CDF tables in shared memory (shared-row fast paths) and the guide builder
 // ------------------------------------------------------------------------------------------------
-// tab layout: [loc kGrid][trap kGrid][guide kGuideStride u16 = kGuideStride/2 floats (+1)][5 scalars]
-constexpr int kTabLoc = 0, kTabTrap = kGrid, kTabGuide = 2 * kGrid, kTabScal = 2 * kGrid + kGuideStride / 2 + 1;
-constexpr int kTabCdfFloats = kTabScal + 8;
-
-// loc (and, for a shared row, the CDF row and its guide) staged by the whole CTA
-__device__ __forceinline__ void stage_cdf(float* tab, const float* __restrict__ cdf_row, const float* __restrict__ loc) {
-  for (int k = threadIdx.x; k < kCdf; k += kTile) {
-    tab[kTabLoc + k] = loc[k];
-    if (cdf_row) tab[kTabTrap + k] = cdf_row[k];
-  }
-  __syncthreads();
-  if (cdf_row) {
-    uint16_t* guide = reinterpret_cast<uint16_t*>(tab + kTabGuide);
-    for (int k = threadIdx.x; k <= kGuide; k += kTile)
-      guide[k] = (uint16_t)cdf_count_le(tab + kTabTrap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
-  }
-}
-__device__ __forceinline__ float shared_row_angle(const float* tab, float u) {
-  return igso3_angle_from_uniform_guided(tab + kTabTrap, tab + kTabLoc, reinterpret_cast<const uint16_t*>(tab + kTabGuide), u);
-}
 __device__ __forceinline__ float table_row_angle(const float* __restrict__ cdf, const uint32_t* __restrict__ guide, int64_t row,
                                                  const float* tab, float u) {
   if (guide) {

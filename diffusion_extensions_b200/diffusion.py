@@ -90,6 +90,7 @@ class SO3Diffusion(nn.Module):
         # global row index of this process's first batch row: makes the Philox draws of a sharded
         # batch independent of the number of GPUs (set by the multi-GPU harness)
         self.row_offset = 0
+        self.fuse_denoiser = True  # p_sample runs a RotPredict denoiser inside the reverse-step kernel when it can
         self._tables = {}  # device -> (fwd_cdf, post_cdf, t_range)
         self._guides = {}  # device -> (fwd_guide, post_guide)
 
@@ -158,6 +159,15 @@ class SO3Diffusion(nn.Module):
         t_full = t if t.numel() == b else t.expand(b)
         return self.denoise_fn(x, t_full)
 
+    def _fused_denoiser(self, x, t):
+        """(blob, c1_table) when `denoise_fn` is a RotPredict the fused kernel can run for this call, else None."""
+        from .denoiser import RotPredict
+
+        fn = self.denoise_fn
+        if self.fuse_denoiser and type(self) in (SO3Diffusion,) and isinstance(fn, RotPredict) and t.numel() == 1 and fn.fusable():
+            return fn.packed(self.num_timesteps)
+        return None
+
     def p_mean_variance(self, x, t, clip_denoised: bool = False):
         """diffusion.py:308-313."""
         predict = self._denoise(x, t)
@@ -170,8 +180,14 @@ class SO3Diffusion(nn.Module):
     def p_sample(self, x, t, clip_denoised=False, repeat_noise=False):
         """diffusion.py:315-326.  t: (B,) or (1,) int64.  One fused kernel after the denoiser; rows
         with t == 0 get no noise (checked on the device, no host sync)."""
-        predict = self._denoise(x, t)
         _, post, _ = self.tables()
+        fused = self._fused_denoiser(x, t)
+        if fused is not None:  # RotPredict + shared step: denoiser and reverse step in ONE tensor-core kernel
+            blob, c1 = fused
+            return ops.rotpredict_p_sample_fused(x, blob, c1, t, self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
+                                                 self.posterior_mean_coef1, self.posterior_mean_coef2, post_cdf=post,
+                                                 row_offset=self.row_offset)
+        predict = self._denoise(x, t)
         return ops.p_sample_fused(x, predict, t, self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
                                   self.posterior_mean_coef1, self.posterior_mean_coef2, post_cdf=post, post_guide=self.guides()[1],
                                   row_offset=self.row_offset)

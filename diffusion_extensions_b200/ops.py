@@ -609,3 +609,67 @@ def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, se
     call("so3d_p_sample_f32", ptr(x_t), ptr(pred), ptr(t), t_stride, ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T,
          ptr(post_cdf), ptr(post_guide), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(x0_hat), n, device=dev)
     return (out, x0_hat) if want_x0_hat else out
+
+
+# ---------------------------------------------------------------------------------------------
+# RotPredict denoiser fused with the reverse step
+# ---------------------------------------------------------------------------------------------
+ROTPREDICT_D = 65
+ROTPREDICT_BLOB_FLOATS = 39424  # include/so3d.h SO3D_ROTPREDICT_BLOB_FLOATS
+
+
+def rotpredict_pack(weights, biases):
+    """Five nn.Linear weight / bias tensors (so3_train.py:26-36) -> packed tf32 hi/lo blob for the fused kernel."""
+    if len(weights) != 5 or len(biases) != 5:
+        raise ValueError("RotPredict has five Linear layers")
+    ws = [check_f32(w.detach(), f"weight{i + 1}", (ROTPREDICT_D,)) for i, w in enumerate(weights)]
+    bs = [check_f32(b.detach(), f"bias{i + 1}") for i, b in enumerate(biases)]
+    shapes = [(ROTPREDICT_D, ROTPREDICT_D)] * 4 + [(3, ROTPREDICT_D)]
+    for w, b, s in zip(ws, bs, shapes):
+        if tuple(w.shape) != s or b.numel() != s[0]:
+            raise ValueError(f"unexpected layer shape {tuple(w.shape)} / {tuple(b.shape)}; RotPredict(d_model=65, out_type='skewvec') expected")
+    dev = ws[0].device
+    blob = torch.empty(ROTPREDICT_BLOB_FLOATS, dtype=torch.float32, device=dev)
+    args = []
+    for w, b in zip(ws, bs):
+        args += [ptr(w), ptr(b)]
+    call("so3d_rotpredict_pack_f32", *args, ptr(blob), device=dev)
+    return blob
+
+
+def rotpredict_p_sample_fused(x_t, blob, c1_table, t, recip, recipm1, coef1, coef2, post_cdf=None, seed=None, rng_offset=None,
+                              row_offset=0, want_out=True, want_pred=False):
+    """Denoiser + reverse step in one launch.  t: int64 tensor with ONE element (step shared by the batch).
+    post_cdf None -> posterior mean only.  -> out (...,3,3) and/or pred (...,3)"""
+    x_t, bs, n = _rows9(x_t, "x")
+    dev = x_t.device
+    t = t.to(device=dev, dtype=torch.int64)
+    if t.numel() != 1:
+        raise ValueError("the fused denoiser step takes a step index shared by the batch (t.numel() == 1)")
+    t = t.reshape(1).contiguous()
+    blob = check_f32(blob, "blob")
+    if blob.numel() != ROTPREDICT_BLOB_FLOATS:
+        raise ValueError("blob must come from rotpredict_pack")
+    recip, recipm1 = check_f32(recip, "sqrt_recip_alphas_cumprod"), check_f32(recipm1, "sqrt_recipm1_alphas_cumprod")
+    coef1, coef2 = check_f32(coef1, "posterior_mean_coef1"), check_f32(coef2, "posterior_mean_coef2")
+    T = recip.numel()
+    c1_table = check_f32(c1_table, "c1_table", (ROTPREDICT_D,))
+    if c1_table.numel() != T * ROTPREDICT_D:
+        raise ValueError("c1_table must have one row per timestep")
+    trap_loc = None
+    if post_cdf is not None:
+        post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
+        if post_cdf.numel() != T * CDF_POINTS:
+            raise ValueError("posterior cdf table must have one row per timestep")
+        _, _, trap_loc = cdf_grid(dev)
+        if seed is None or rng_offset is None:
+            seed, rng_offset = rng.next()
+    if not (want_out or want_pred):
+        raise ValueError("nothing requested")
+    out = torch.empty_like(x_t) if want_out else None
+    pred = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_pred else None
+    call("so3d_rotpredict_p_sample_f32", ptr(x_t), ptr(blob), ptr(c1_table), ptr(t), ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T,
+         ptr(post_cdf), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(pred), n, device=dev)
+    if want_out and want_pred:
+        return out, pred
+    return out if want_out else pred

@@ -147,6 +147,28 @@ int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, in
                       const uint32_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                       float* out, float* x0_hat_out, int64_t n, void* stream);
 
+/* ---- RotPredict denoiser fused with the reverse step ------------------------------------ */
+#define SO3D_ROTPREDICT_D 65              /* so3_train.py:12 d_model */
+#define SO3D_ROTPREDICT_BLOB_FLOATS 39424 /* packed tf32 hi/lo weights in the tensor-core (UMMA) shared-memory layout */
+/* so3_train.py:26-36 RotPredict.net (out_type "skewvec"): five nn.Linear layers, weights row-major (out x in):
+ * w1..w4: 65 x 65, w5: 3 x 65, b1..b4: 65, b5: 3 (b1 is not packed: it enters through c1_table below).
+ * Writes blob[SO3D_ROTPREDICT_BLOB_FLOATS] (16-byte aligned).  Re-run whenever the weights change. */
+int so3d_rotpredict_pack_f32(const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                             const float* b3, const float* w4, const float* b4, const float* w5, const float* b5,
+                             float* blob, void* stream);
+/* so3_test.py:26-31 / diffusion.py:315-337: one reverse step with the RotPredict denoiser inside the kernel,
+ *   pred = RotPredict(x_t, t)  (so3_train.py:39-49, models.py:13-25);   out = p_sample(x_t, pred, t) as so3d_p_sample_f32
+ * for a step index shared by the batch (t: int64[1] on the device).  The 65-wide MLP runs on the tensor cores
+ * (tcgen05.mma kind::tf32, 3-term hi/lo split: fp32-level accuracy), activations stay in tensor memory.
+ *   c1_table: T x 65, c1_table[t] = b1 + W1[:, 9:] @ SinusoidalPosEmb(56)(t)  -- the time embedding folded into
+ *   layer 1's bias (caller-computed once per weight set).  post_cdf NULL or t == 0: no noise (posterior mean).
+ *   out (n x 9) and pred_out (n x 3) are each nullable (not both).  Random draws are those of so3d_p_sample_f32
+ *   at the same (seed, rng_offset, row_offset). */
+int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const float* c1_table, const int64_t* t,
+                                 const float* recip, const float* recipm1, const float* coef1, const float* coef2, int64_t T,
+                                 const float* post_cdf, const float* loc, uint64_t seed, uint64_t rng_offset,
+                                 uint64_t row_offset, float* out, float* pred_out, int64_t n, void* stream);
+
 /* ---- SE(3) arm: diffusion.py SE3Diffusion / distributions.py IGSO3xR3 --------------- */
 /* diffusion.py:498-516 (SE3Diffusion.q_sample + p_losses targets), fused.  Rotation half exactly as
  * so3d_q_sample_f32 (same Philox block: identical rotation draws at the same seed / rng_offset); translation half
