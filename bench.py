@@ -348,6 +348,25 @@ def main():
                                             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}}
         del la, lb
 
+        # one reverse step WITH the reference's RotPredict denoiser (so3_train.py:11-49) inside the kernel
+        # (tcgen05 tf32 3-term split), against the two-kernel route (stock PyTorch MLP + fused step).
+        torch.manual_seed(SEED)
+        net = dx.RotPredict().to(device)
+        procn = dx.SO3Diffusion(net).to(device)
+        procn.row_offset = rank * n
+        procn.tables()
+        with torch.no_grad():
+            vd, md = rate(lambda: procn.p_sample(xa, t_step), n, 5)
+            procn.fuse_denoiser = False
+            nu = min(n, 1 << 22)  # the stock route materialises (n, 65) activations: bounded
+            vu, mu = rate(lambda: procn.p_sample(xa[:nu], t_step), nu, 3)
+        flop_ps = 2 * 65 * (65 * 4 + 3)                       # algorithmic MLP flops per particle-step (fp32 semantics)
+        extra["reverse_with_denoiser_particle_steps_per_sec"] = {
+            "value": vd, "ms_per_step": md, "note": "RotPredict (65-wide, 5 layers) + reverse step in ONE tcgen05 kernel, shared t = 500",
+            "stock_mlp_plus_fused_step": {"value": vu, "ms_per_step": mu, "rows": nu},
+            "mlp_tflops_algorithmic": vd / world * flop_ps * 1e-12}
+        del net, procn
+
         # MMD two-sample statistic at bingham_test.py:29's size (20 000 vs 20 000 rotations), one fused
         # all-pairs launch; multi-GPU: tile pairs dealt round-robin, three doubles all-reduced.
         nm = 20000

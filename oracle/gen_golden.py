@@ -237,7 +237,43 @@ def main_se3():
     )
 
 
+def main_denoiser():
+    """RotPredict denoiser fixtures: the reference's so3_train.RotPredict (out_type 'skewvec') with
+    seeded weights, evaluated for a shared step index (so3_test.py:31) and per-row steps, and the reference's
+    SO3Diffusion.p_mean_variance driven by it (diffusion.py:308-313).  models.py / prot_util.py import packages
+    that are not installed, so those imports are stubbed; the stubs are never called."""
+    import types
+
+    for name in ("se3_transformer_pytorch", "se3_transformer_pytorch.se3_transformer_pytorch", "Bio", "Bio.PDB", "wandb"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    m = sys.modules["se3_transformer_pytorch.se3_transformer_pytorch"]
+    m.LinearSE3 = m.Fiber = m.NormSE3 = object
+    sys.modules["se3_transformer_pytorch"].SE3Transformer = object
+    import so3_train as rtrain  # reference so3_train.py
+
+    torch.manual_seed(77)
+    net = rtrain.RotPredict(out_type="skewvec")
+    with torch.no_grad():  # trained-network-sized activations instead of the near-zero default init
+        for p_ in net.parameters():
+            p_.mul_(2.5)
+    g = torch.Generator().manual_seed(78)
+    n = 300
+    R, _, _ = rand_rot(n, g)
+    out = {k.replace(".", "_"): v for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        shared = [0, 1, 500, 999]
+        out["t_shared"] = np.array(shared)
+        out["pred_shared"] = torch.stack([net(R, torch.tensor([tv])) for tv in shared])
+        t_row = torch.randint(0, 1000, (n,), generator=g)
+        out["t_row"] = t_row
+        out["pred_row"] = net(R, t_row)
+        proc = rdiff.SO3Diffusion(net)
+        out["mean_shared"] = torch.stack([proc.p_mean_variance(R, torch.full((n,), tv, dtype=torch.long), clip_denoised=False)[0] for tv in (1, 300, 999)])
+        out["t_mean"] = np.array([1, 300, 999])
+    save("rotpredict", x=R, **out)
+
+
 if __name__ == "__main__":
-    todo = [a for a in sys.argv[1:] if a in ("core", "eval", "se3")] or ["core", "eval", "se3"]
+    todo = [a for a in sys.argv[1:] if a in ("core", "eval", "se3", "denoiser")] or ["core", "eval", "se3", "denoiser"]
     for name in todo:
-        {"core": main, "eval": main_eval, "se3": main_se3}[name]()
+        {"core": main, "eval": main_eval, "se3": main_se3, "denoiser": main_denoiser}[name]()

@@ -504,6 +504,37 @@ def p_sample(x_t, pred, sqrt_recip_ac, sqrt_recipm1_ac, coef1, coef2, noise=None
 
 
 # ----------------------------------------------------------------------------------------------
+# RotPredict denoiser (so3_train.py:11-49, models.py:13-25), SURVEY 8f-4
+# ----------------------------------------------------------------------------------------------
+def sinusoidal_pos_emb(t, dim):
+    """models.py:13-25: cat(sin(t f_j), cos(t f_j)), f_j = exp(-j log(1e4)/(dim/2 - 1)).  The reference builds
+    f_j and the products in float32 (torch.arange -> exp), which is reproduced here before the float64 sin/cos:
+    at t = 999 a float64 frequency would move the phase by 3e-5 rad."""
+    half = dim // 2
+    scale = np.float32(math.log(10000) / (half - 1))
+    freq = np.exp(np.arange(half, dtype=np.float32) * -scale).astype(np.float32)
+    arg = (np.asarray(t, np.float32)[:, None] * freq[None, :]).astype(np.float64)
+    return np.concatenate([np.sin(arg), np.cos(arg)], axis=-1)
+
+
+def rotpredict_forward(weights, biases, x, t):
+    """so3_train.py:39-49 with out_type 'skewvec': net(cat(flatten(x), time_embedding(t))), five Linear layers
+    (weights[i]: out x in) with SiLU between them (so3_train.py:26-36).  t: (n,) or (1,) (expanded, :42-43)."""
+    x = np.asarray(x, np.float64)
+    n = x.shape[0]
+    d_model = np.asarray(weights[0]).shape[1]
+    emb = sinusoidal_pos_emb(np.asarray(t).reshape(-1), d_model - 9)
+    if emb.shape[0] == 1:
+        emb = np.broadcast_to(emb, (n, emb.shape[1]))
+    h = np.concatenate([x.reshape(n, 9), emb], axis=-1)
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        h = h @ np.asarray(w, np.float64).T + np.asarray(b, np.float64)
+        if i + 1 < len(weights):
+            h = h / (1.0 + np.exp(-h))  # SiLU
+    return h
+
+
+# ----------------------------------------------------------------------------------------------
 # helpers for tests / benchmarks
 # ----------------------------------------------------------------------------------------------
 # ----------------------------------------------------------------------------------------------

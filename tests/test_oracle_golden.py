@@ -301,3 +301,39 @@ def test_se3_diffusion_algebra(golden):
     assert np.max(np.abs(sh - g["scaled_shift"])) < 1e-5
     ok3 = O.rmat_to_aa(g["rot0"])[1][:, 0] < 3.0
     assert np.max(np.abs(sr - g["scaled_rot"])[ok3]) < 1e-5
+
+
+def rotpredict_params(g):
+    return [g[f"net_{i}_weight"] for i in (0, 2, 4, 6, 8)], [g[f"net_{i}_bias"] for i in (0, 2, 4, 6, 8)]
+
+
+def test_rotpredict_forward(golden):
+    """RotPredict (so3_train.py:11-49) for shared and per-row step indices; the golden outputs are the reference's
+    fp32 forward (error ~1e-6 on outputs of size ~1).  The time features are sin/cos(t * f_j) with f_j an fp32
+    exp(): a 1-ulp difference between exp implementations (numpy / ATen CPU / CUDA) moves the phase by t * 6e-8,
+    so the pin is 5e-6 at small t and 1e-4 over the whole range -- a conditioning property of the reference's
+    embedding, not of this restatement."""
+    g = golden("rotpredict")
+    w, b = rotpredict_params(g)
+    for k, tv in enumerate(g["t_shared"]):
+        got = O.rotpredict_forward(w, b, g["x"], np.array([tv]))
+        assert np.max(np.abs(got - g["pred_shared"][k])) < (5e-6 if tv <= 1 else 1e-4)
+    got = O.rotpredict_forward(w, b, g["x"], g["t_row"])
+    assert np.max(np.abs(got - g["pred_row"])) < 1e-4
+    assert np.max(np.abs(g["pred_row"])) > 0.05  # the fixture is not a near-zero network
+
+
+def test_rotpredict_reverse_mean(golden):
+    """SO3Diffusion.p_mean_variance driven by RotPredict (diffusion.py:308-313): oracle denoiser + oracle step
+    algebra against the reference's model mean.  Tolerance: the reference's so3_scale error grows with the scale
+    (quirk Q5), so t = 999 (scale 20291) is compared loosely;
+    at t = 300 the bound is the time-embedding conditioning above times the step's gain."""
+    g = golden("rotpredict")
+    w, b = rotpredict_params(g)
+    s = O.schedule_buffers(1000)
+    for k, tv in enumerate(g["t_mean"]):
+        pred = O.rotpredict_forward(w, b, g["x"], np.array([tv]))
+        want = O.p_sample_mean(g["x"].astype(np.float64), pred, s["sqrt_recip_alphas_cumprod"][tv], s["sqrt_recipm1_alphas_cumprod"][tv],
+                               s["posterior_mean_coef1"][tv], s["posterior_mean_coef2"][tv])
+        err = O.geodesic_angle(want, g["mean_shared"][k].astype(np.float64))
+        assert np.max(err) < (1e-4 if tv <= 300 else 0.2), (tv, np.max(err))
