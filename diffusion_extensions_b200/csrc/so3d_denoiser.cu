@@ -59,7 +59,7 @@ static_assert(kBlobFloats == SO3D_ROTPREDICT_BLOB_FLOATS, "so3d.h out of sync");
 // TMEM columns of a group: accumulator, A hi, A lo
 constexpr uint32_t kColD = 0, kColAhi = 96, kColAlo = 176, kColsPerGroup = 256;
 
-constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kBlobFloats + ((kTabCdfFloats + 3) & ~3)) + 64;
+constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kBlobFloats + ((kTabCdfFloats + 3) & ~3)) + 2 * 2 * 128 * 16 /* noise quaternions */ + 64;
 
 __device__ __forceinline__ int canon_index(int n, int k, int N) { return (k >> 2) * (N * 4) + n * 4 + (k & 3); }
 
@@ -78,7 +78,6 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -115,13 +114,16 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
 #define SO3D_TMEM_ST8(taddr, v, o) \
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), SO3D_W8(v, o) : "memory")
 
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+// tf32 split with round-to-nearest: hi = x rounded to 10 mantissa bits (low 13 bits zero), lo = x - hi exactly, so
+// |lo| <= 2^-11 |x| with either sign; the tensor core then truncates lo to 10 bits (an UNBIASED 2^-21 |x| error --
+// truncating hi instead would leave lo >= 0 and bias every product low by ~2^-22).
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
 // x * sigmoid(x) (torch.nn.SiLU): one MUFU.EX2 and one MUFU.RCP
 __device__ __forceinline__ float silu(float x) {
   const float e = fast_ex2(-1.4426950408889634f * x);
-  return x * fast_rcp(1.0f + e);
+  return x * rcp_approx(1.0f + e);
 }
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -136,6 +138,9 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
         : "memory");
     if (!done && ++spins > (1u << 24)) __trap();  // a tensor-core op that never completes must not hang the device
   } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 struct DenoiseArgs {
@@ -156,7 +161,7 @@ struct DenoiseArgs {
   int64_t n;
 };
 
-// issue the MMAs of one layer for group `g` (one thread): D = A_hi B_hi + A_lo B_hi + A_hi B_lo over `ksteps` K-steps
+// issue the MMAs of one layer for a group (one thread): D = A_hi B_hi + A_lo B_hi + A_hi B_lo over `ksteps` K-steps
 __device__ __forceinline__ void issue_layer(uint32_t tmem_group, uint32_t b_hi_addr, uint32_t b_lo_addr, int N, int ksteps, uint64_t* bar) {
   const uint32_t lbo = (uint32_t)N * 16u, sbo = 128u;
   const uint32_t idesc = instr_desc(kM, N);
@@ -172,23 +177,63 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_group, uint32_t b_hi_a
   tc_commit(bar);
 }
 
-__global__ void __launch_bounds__(256, 1) rotpredict_p_sample_kernel(const DenoiseArgs a) {
+// SiLU epilogue of one hidden layer for the thread's particle (TMEM lane) and its half of the columns:
+// H = 0: accumulator columns 0..31 -> A columns 0..31;  H = 1: columns 32..64 -> A columns 32..71 (column 65 is the
+// constant 1 that carries the next layer's bias, 66..71 are zero padding).
+template <int H>
+__device__ __forceinline__ void silu_epilogue(uint32_t tmem_lane) {
+  constexpr int kC0 = H ? 4 : 0, kChunks = H ? 5 : 4;
+  uint32_t acc[40];
+  SO3D_TMEM_LD16(tmem_lane + kColD + kC0 * 8, acc, 0);
+  SO3D_TMEM_LD16(tmem_lane + kColD + kC0 * 8 + 16, acc, 16);
+  if (H) SO3D_TMEM_LD1(tmem_lane + kColD + 64, acc, 32);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int col = (kC0 + c) * 8 + k;
+      float v;
+      if (col < kD)
+        v = silu(__uint_as_float(acc[c * 8 + k]));
+      else
+        v = col == kD ? 1.0f : 0.0f;
+      hi[k] = tf32_hi(v);
+      lo[k] = tf32_lo(v, hi[k]);
+    }
+    SO3D_TMEM_ST8(tmem_lane + kColAhi + (kC0 + c) * 8, hi, 0);
+    SO3D_TMEM_ST8(tmem_lane + kColAlo + (kC0 + c) * 8, lo, 0);
+  }
+  tc_wait_st();
+}
+
+// Roles: warps 0..15 are two groups of 8 epilogue warps (group g = warp / 8 owns one 128-particle tile at a time);
+// inside a group warp w handles TMEM lanes 32 (w % 4) .. +31 (the hardware's lane-quarter rule) and column half
+// h = (w / 4) % 2 -- two threads per particle.  Warps 16 and 17 issue the MMAs of group 0 and 1.  Hand-offs are
+// mbarriers: bar_a[g] "A operand written" (8 warp arrivals) -> issuer -> tcgen05.commit -> bar_d[g] "accumulator ready".
+constexpr int kEpiWarps = 16, kThreads = (kEpiWarps + 2) * 32;
+
+__global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const DenoiseArgs a) {
   extern __shared__ float4 smem4[];
   float* s_blob = reinterpret_cast<float*>(smem4);
   float* s_tab = s_blob + kBlobFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + ((kTabCdfFloats + 3) & ~3));  // [0]: weights, [1], [2]: MMA completion per group
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int g = tid >> 7, r = tid & 127;
+  float4* s_noise = reinterpret_cast<float4*>(s_tab + ((kTabCdfFloats + 3) & ~3));   // [group][parity][particle]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_noise + 2 * 2 * kM);  // [0] weights, [1..2] bar_d, [3..4] bar_a
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   int64_t ti = a.t[0];
   ti = ti < 0 ? 0 : (ti >= a.T ? a.T - 1 : ti);
+  const bool noisy = a.post_cdf && ti != 0 && a.out;
 
   if (warp == 0) tmem_alloc(s_tmem, 512);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 8);
+    mbar_init(&bars[4], 8);
     fence_barrier_init();
   }
   __syncthreads();
@@ -200,7 +245,7 @@ __global__ void __launch_bounds__(256, 1) rotpredict_p_sample_kernel(const Denoi
       bulk_load(s_blob + off, a.blob + off, (uint32_t)(cnt * sizeof(float)), &bars[0]);
     }
   }
-  if (a.post_cdf && ti != 0) stage_cdf(s_tab, a.post_cdf + ti * kCdf, a.loc);  // posterior CDF row of this step + guide
+  if (noisy) stage_cdf(s_tab, a.post_cdf + ti * kCdf, a.loc);  // posterior CDF row of this step + guide
   mbar_wait(&bars[0], 0);
   // time embedding of this step folded into layer 1's bias column (k = 9): generic-proxy writes, ordered before the MMAs
   if (tid < kD) {
@@ -214,114 +259,131 @@ __global__ void __launch_bounds__(256, 1) rotpredict_p_sample_kernel(const Denoi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
-  const uint32_t tmem_lane = tmem_group + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes of the group's columns
   const uint32_t blob_addr = smem_u32(s_blob);
-  uint64_t* bar = &bars[1 + g];
-  uint32_t phase = 0;
-
-  const float k_recip = __ldg(a.recip + ti), k_recipm1 = __ldg(a.recipm1 + ti);
-  const float k_c1 = __ldg(a.coef1 + ti), k_c2 = __ldg(a.coef2 + ti);
-
   const int64_t tiles = (a.n + kM - 1) / kM;
-  for (int64_t tile = (int64_t)blockIdx.x * 2 + g; tile < tiles; tile += (int64_t)gridDim.x * 2) {
-    const int64_t i = tile * kM + r;
-    const bool live = i < a.n;
-    Mat3 x = identity();
-    if (live) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) x.m[k] = __ldcs(a.x_t + i * 9 + k);
-    }
-    // ---- layer 1 operand: [x(9), 1, 0 x 6] ----
-    __syncwarp();
-    {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float v = k < 9 ? x.m[k] : (k == 9 ? 1.0f : 0.0f);
-        hi[k] = tf32_hi(v);
-        lo[k] = tf32_lo(v, hi[k]);
-      }
-      SO3D_TMEM_ST8(tmem_lane + kColAhi, hi, 0);
-      SO3D_TMEM_ST8(tmem_lane + kColAhi + 8, hi, 8);
-      SO3D_TMEM_ST8(tmem_lane + kColAlo, lo, 0);
-      SO3D_TMEM_ST8(tmem_lane + kColAlo + 8, lo, 8);
-    }
-    tc_wait_st();
-    tc_fence_before();
-    group_sync(g);
-    if (r == 0) issue_layer(tmem_group, blob_addr + kOffL1 * 4, blob_addr + (kOffL1 + kL1Floats) * 4, kNPad, kK1 / 8, bar);
 
-    // ---- layers 2..5: epilogue of the previous layer (SiLU) -> next A operand -> MMAs ----
+  if (warp >= kEpiWarps) {
+    // ---- MMA issuer of group g: wait for the A operand, issue the layer, commit to the accumulator barrier ----
+    const int g = warp - kEpiWarps;
+    const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
+    uint32_t ph = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * 2 + g; tile < tiles; tile += (int64_t)gridDim.x * 2) {
+      if (lane == 0) {
 #pragma unroll 1
-    for (int layer = 2; layer <= 5; ++layer) {
-      mbar_wait_bounded(bar, phase);
-      phase ^= 1;
+        for (int layer = 1; layer <= 5; ++layer) {
+          mbar_wait_bounded(&bars[3 + g], ph);
+          ph ^= 1;
+          if (layer == 1) {
+            issue_layer(tmem_group, blob_addr + kOffL1 * 4, blob_addr + (kOffL1 + kL1Floats) * 4, kNPad, kK1 / 8, &bars[1 + g]);
+          } else if (layer < 5) {
+            const uint32_t b = blob_addr + (uint32_t)(kOffLh + (layer - 2) * 2 * kLhFloats) * 4u;
+            issue_layer(tmem_group, b, b + kLhFloats * 4u, kNPad, kKPad / 8, &bars[1 + g]);
+          } else {
+            const uint32_t b = blob_addr + (uint32_t)kOffL5 * 4u;
+            issue_layer(tmem_group, b, b + kL5Floats * 4u, kN5, kKPad / 8, &bars[1 + g]);
+          }
+        }
+      }
       __syncwarp();
-      tc_fence_after();
-      uint32_t acc[kD + 7];
-      SO3D_TMEM_LD16(tmem_lane + kColD, acc, 0);
-      SO3D_TMEM_LD16(tmem_lane + kColD + 16, acc, 16);
-      SO3D_TMEM_LD16(tmem_lane + kColD + 32, acc, 32);
-      SO3D_TMEM_LD16(tmem_lane + kColD + 48, acc, 48);
-      SO3D_TMEM_LD1(tmem_lane + kColD + 64, acc, 64);
-      tc_wait_ld();
+    }
+  } else {
+    // ---- epilogue warps ----
+    const int g = warp >> 3, h = (warp >> 2) & 1, r = (warp & 3) * 32 + lane;
+    const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
+    const uint32_t tmem_lane = tmem_group + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes of the group's columns
+    uint64_t* bar_d = &bars[1 + g];
+    uint64_t* bar_a = &bars[3 + g];
+    uint32_t ph = 0;
+    const float k_recip = __ldg(a.recip + ti), k_recipm1 = __ldg(a.recipm1 + ti);
+    const float k_c1 = __ldg(a.coef1 + ti), k_c2 = __ldg(a.coef2 + ti);
+
+    const int64_t tile0 = (int64_t)blockIdx.x * 2 + g, tstride = (int64_t)gridDim.x * 2;
+    Mat3 x = identity(), xn = identity();
+    if (h == 0 && tile0 < tiles && tile0 * kM + r < a.n) {
 #pragma unroll
-      for (int c = 0; c < kKPad / 8; ++c) {
-        uint32_t hi[8], lo[8];
+      for (int k = 0; k < 9; ++k) x.m[k] = __ldcs(a.x_t + (tile0 * kM + r) * 9 + k);
+    }
+    int par = 0;
+    for (int64_t tile = tile0; tile < tiles; tile += tstride, par ^= 1) {
+      const int64_t i = tile * kM + r;
+      const bool live = i < a.n;
+      if (h == 0) {
+        // layer 1 operand: [x(9), 1, 0 x 6]
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int col = c * 8 + k;
-          float v;
-          if (col < kD)
-            v = silu(__uint_as_float(acc[col]));
-          else
-            v = col == kD ? 1.0f : 0.0f;
+        for (int k = 0; k < 16; ++k) {
+          const float v = k < 9 ? x.m[k] : (k == 9 ? 1.0f : 0.0f);
           hi[k] = tf32_hi(v);
           lo[k] = tf32_lo(v, hi[k]);
         }
-        SO3D_TMEM_ST8(tmem_lane + kColAhi + c * 8, hi, 0);
-        SO3D_TMEM_ST8(tmem_lane + kColAlo + c * 8, lo, 0);
+        SO3D_TMEM_ST8(tmem_lane + kColAhi, hi, 0);
+        SO3D_TMEM_ST8(tmem_lane + kColAhi + 8, hi, 8);
+        SO3D_TMEM_ST8(tmem_lane + kColAlo, lo, 0);
+        SO3D_TMEM_ST8(tmem_lane + kColAlo + 8, lo, 8);
+        tc_wait_st();
       }
-      tc_wait_st();
       tc_fence_before();
-      group_sync(g);
-      if (r == 0) {
-        if (layer < 5) {
-          const uint32_t b = blob_addr + (uint32_t)(kOffLh + (layer - 2) * 2 * kLhFloats) * 4u;
-          issue_layer(tmem_group, b, b + kLhFloats * 4u, kNPad, kKPad / 8, bar);
-        } else {
-          const uint32_t b = blob_addr + (uint32_t)kOffL5 * 4u;
-          issue_layer(tmem_group, b, b + kL5Floats * 4u, kN5, kKPad / 8, bar);
-        }
-      }
-    }
-    // ---- output of layer 5 = predicted skew vector; fused reverse step (diffusion.py:291-326) ----
-    mbar_wait_bounded(bar, phase);
-    phase ^= 1;
-    __syncwarp();
-    tc_fence_after();
-    uint32_t pr[4];
-    SO3D_TMEM_LD4(tmem_lane + kColD, pr, 0);
-    tc_wait_ld();
-    tc_fence_before();  // the next tile's tcgen05.st / MMAs of this group are ordered after these loads by group_sync
-    const Vec3 pred{__uint_as_float(pr[0]), __uint_as_float(pr[1]), __uint_as_float(pr[2])};
-    if (live) {
-      if (a.pred_out) {
-        a.pred_out[i * 3 + 0] = pred.x;
-        a.pred_out[i * 3 + 1] = pred.y;
-        a.pred_out[i * 3 + 2] = pred.z;
-      }
-      if (a.out) {
-        Quat qh;
-        Quat qm = p_mean_quat(x, pred, k_recip, k_recipm1, k_c1, k_c2, &qh);
-        if (a.post_cdf && ti != 0) {
-          const NoiseDraw d = draw_axis_u(a.seed, a.row_offset + (uint64_t)i, a.rng_offset);
-          qm = qmul(qm, quat_axis_angle(d.axis, shared_row_angle(s_tab, d.u)));
-        }
-        const Mat3 o = quat_to_mat_unit(qm);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
+      if (h == 0) {
+        // prefetch the next tile's rotation while this tile runs through the network
+        const int64_t in = (tile + tstride) * kM + r;
+        xn = identity();
+        if (tile + tstride < tiles && in < a.n) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) __stcs(a.out + i * 9 + k, o.m[k]);
+          for (int k = 0; k < 9; ++k) xn.m[k] = __ldcs(a.x_t + in * 9 + k);
+        }
+      } else if (noisy && live) {
+        // the step's noise rotation does not depend on the network: drawn by the second thread of the particle
+        const NoiseDraw d = draw_axis_u(a.seed, a.row_offset + (uint64_t)i, a.rng_offset);
+        const Quat qn = quat_axis_angle(d.axis, shared_row_angle(s_tab, d.u));
+        s_noise[(g * 2 + par) * kM + r] = make_float4(qn.w, qn.x, qn.y, qn.z);
+      }
+#pragma unroll 1
+      for (int layer = 2; layer <= 5; ++layer) {
+        mbar_wait_bounded(bar_d, ph);
+        ph ^= 1;
+        tc_fence_after();
+        if (h == 0)
+          silu_epilogue<0>(tmem_lane);
+        else
+          silu_epilogue<1>(tmem_lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+      }
+      // ---- output of layer 5 = predicted skew vector; fused reverse step (diffusion.py:291-326) ----
+      mbar_wait_bounded(bar_d, ph);
+      ph ^= 1;
+      tc_fence_after();
+      uint32_t pr[4] = {0u, 0u, 0u, 0u};
+      if (h == 0) {
+        SO3D_TMEM_LD4(tmem_lane + kColD, pr, 0);
+        tc_wait_ld();
+      }
+      tc_fence_before();  // the next tile's tcgen05.st / MMAs of this group are ordered after these loads by bar_a
+      if (noisy) asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");  // the group's noise quaternions are in shared memory
+      if (h == 0) {
+        const Vec3 pred{__uint_as_float(pr[0]), __uint_as_float(pr[1]), __uint_as_float(pr[2])};
+        if (live) {
+          if (a.pred_out) {
+            a.pred_out[i * 3 + 0] = pred.x;
+            a.pred_out[i * 3 + 1] = pred.y;
+            a.pred_out[i * 3 + 2] = pred.z;
+          }
+          if (a.out) {
+            Quat qh;
+            Quat qm = p_mean_quat(x, pred, k_recip, k_recipm1, k_c1, k_c2, &qh);
+            if (noisy) {
+              const float4 qn = s_noise[(g * 2 + par) * kM + r];
+              qm = qmul(qm, Quat{qn.x, qn.y, qn.z, qn.w});
+            }
+            const Mat3 o = quat_to_mat_unit(qm);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) __stcs(a.out + i * 9 + k, o.m[k]);
+          }
+        }
+        x = xn;
       }
     }
   }
@@ -340,7 +402,7 @@ struct PackArgs {
 __device__ __forceinline__ void put_split(float* blob, int hi_off, int lo_off, int idx, float v) {
   const uint32_t hi = tf32_hi(v);
   blob[hi_off + idx] = __uint_as_float(hi);
-  blob[lo_off + idx] = __uint_as_float(tf32_lo(v, hi));
+  blob[lo_off + idx] = __uint_as_float(tf32_hi(v - __uint_as_float(hi)));  // lo rounded (not truncated) to tf32 as well
 }
 
 __global__ void __launch_bounds__(256) rotpredict_pack_kernel(const PackArgs p) {
@@ -418,7 +480,7 @@ int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const floa
   const int64_t pairs = ((n + kM - 1) / kM + 1) / 2;
   const int sms = so3d_host::sm_count();
   const int grid = (int)(pairs < sms ? pairs : sms);
-  rotpredict_p_sample_kernel<<<grid, 256, kSmemBytes, (cudaStream_t)stream>>>(a);
+  rotpredict_p_sample_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
   return so3d_host::check_launch("so3d_rotpredict_p_sample_f32");
 }
 
