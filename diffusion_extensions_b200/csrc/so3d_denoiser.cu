@@ -139,6 +139,11 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (!done && ++spins > (1u << 24)) __trap();  // a tensor-core op that never completes must not hang the device
   } while (!done);
 }
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -268,11 +273,12 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
     const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
     uint32_t ph = 0;
     for (int64_t tile = (int64_t)blockIdx.x * 2 + g; tile < tiles; tile += (int64_t)gridDim.x * 2) {
-      if (lane == 0) {
+      {
 #pragma unroll 1
         for (int layer = 1; layer <= 5; ++layer) {
           mbar_wait_bounded(&bars[3 + g], ph);
           ph ^= 1;
+          if (!elect_one()) continue;
           if (layer == 1) {
             issue_layer(tmem_group, blob_addr + kOffL1 * 4, blob_addr + (kOffL1 + kL1Floats) * 4, kNPad, kK1 / 8, &bars[1 + g]);
           } else if (layer < 5) {
