@@ -4,24 +4,31 @@
 // particle through HBM; here a particle costs 36 B in + 36 B out and the activations never leave the SM.
 //
 // Execution model (B200, tcgen05 + TMEM):
-//   * persistent grid, one CTA of 256 threads per SM; the five weight matrices (tf32 hi/lo split, canonical K-major
+//   * persistent grid, one CTA of 18 warps per SM; the five weight matrices (tf32 hi/lo split, canonical K-major
 //     no-swizzle UMMA layout, 158 KB) are staged ONCE per CTA in shared memory by bulk copies (TMA engine);
-//   * a CTA runs two independent groups of 128 threads; a group owns a tile of 128 particles = the 128 TMEM lanes,
-//     thread r <-> particle r <-> TMEM lane r.  While one group's MMAs run on the tensor core the other group does
+//   * warps 0..15 are two groups of 8 epilogue warps; a group owns a tile of 128 particles = the 128 TMEM lanes and
+//     works on it with TWO threads per particle (each takes half of the 65 columns), so four warps per scheduler
+//     hide the MUFU / tensor-memory latencies.  While one group's MMAs run on the tensor core the other group does
 //     its SiLU epilogue on the FP32/XU pipes;
+//   * warps 16, 17 are the MMA issuers of the two groups: they wait on an mbarrier for "A operand written" (one
+//     arrival per epilogue warp), issue the layer under elect.sync -- descriptors stay in uniform registers, the 27
+//     UTCHMMA of a layer go out back to back -- and tcgen05.commit to the group's "accumulator ready" mbarrier;
 //   * every layer is D[128 x N] = A[128 x K] * W^T on the 5th-gen tensor core: `tcgen05.mma.kind::tf32`, A operand
 //     read from TENSOR MEMORY (the previous layer's activations, written there by the epilogue with tcgen05.st --
 //     no shared-memory round trip, no layout shuffle), B = weights from shared memory, accumulator in TMEM;
 //   * fp32 accuracy from the tf32 tensor core by a 3-term split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
-//     (hi = top 19 bits, lo = exact remainder; dropped terms are O(2^-22)): three accumulating MMAs per K step;
+//     (hi = x rounded to nearest at 10 mantissa bits, lo = exact remainder; dropped terms are O(2^-22)): three
+//     accumulating MMAs per K step;
 //   * bias = one more K column (activation column 65 is the constant 1); the 56-wide sinusoidal time embedding
 //     (models.py:13-25) of the step's shared t is folded into the first layer's bias column (c1_table, built once
 //     per weight set by the caller), so layer 1 is a K = 16 product of the 9 matrix entries;
-//   * epilogue per layer: tcgen05.ld the 65 accumulators of the thread's particle, SiLU (MUFU.EX2 + MUFU.RCP),
-//     split, tcgen05.st as the next A operand; after layer 5 the 3 outputs feed the quaternion reverse step
-//     (so3d_math.cuh: p_mean_quat, Philox draw, shared-row inverse CDF) and the particle is written back.
-// Per particle-step: 3 x (3 x 9) + 3 x 2 MMAs of 128 x 80 x 8 and 3 x 9 of 128 x 16 x 8 per 128 particles
-// (~3.7 k tensor-core clocks), 520 MUFU ops: the kernel is co-bound by the tensor pipe and the XU pipe.
+//   * epilogue per layer: tcgen05.ld the thread's 32 / 33 accumulators, SiLU (MUFU.EX2 + MUFU.RCP), split,
+//     tcgen05.st as the next A operand; after layer 5 the 3 outputs feed the quaternion reverse step
+//     (so3d_math.cuh: p_mean_quat) in the particle's first thread, while its second thread has already drawn the
+//     step's noise rotation (Philox, shared-row inverse CDF) and parked it in shared memory.
+// Per 128 particles: 3 x (3 x 9) + 3 x 2 MMAs of 128 x 80 x 8 and 3 x 9 of 128 x 16 x 8 (~2.1 k tensor-pipe clocks
+// measured) and 4 x 65 x 2 MUFU per particle (4.2 k XU-pipe clocks): the kernel is bound by the XU pipe (62 % busy,
+// profiles/r01i_denoiser_full.md), then by instruction issue (51 %).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
