@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libso3d.so")
+# SO3D_LIB_PATH: tuning aid, loads an alternative build of the same library (tests/tools/build_variant.py)
+LIB_PATH = os.environ.get("SO3D_LIB_PATH") or os.path.join(_HERE, "libso3d.so")
 
 _c_f = ctypes.c_void_p  # device pointers are passed as raw addresses
 _i64 = ctypes.c_int64

@@ -35,15 +35,16 @@ def up_to_date():
     return os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: build a variant of the library elsewhere (A/B runs via SO3D_LIB_PATH)."""
+    if out is None and not force and up_to_date():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, *SRCS]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", out or LIB, *SRCS]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -138,7 +138,7 @@ struct OpLayout {
   static constexpr int kInFloats = kTile * kInWords;              // per stage
   static constexpr int kOutFloats = kTile * kOutWords;            // per stage
   static constexpr int kTabFloats = (Op::kTab + 3) & ~3;
-  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kInFloats + kOutStages * kOutFloats + kTabFloats) + 2 * sizeof(uint64_t);
+  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kInFloats + kOutStages * kOutFloats + kTabFloats) + 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
 };
 
 // register cap per op: minimum resident CTAs per SM promised to the compiler (0 = no cap)
@@ -151,8 +151,22 @@ struct OpMinCtas<Op, std::void_t<decltype(Op::kMinCtas)>> {
   static constexpr int value = Op::kMinCtas;
 };
 
+// schedule per op: ops whose rows chase per-row table entries through L2 (latency spread between warps) run the
+// warp-autonomous schedule below; streaming ops keep the CTA-synchronous one (fewer per-warp issue slots).
+// Measured on B200, 2^24 rows (profiles/r01k_probe_engine.jsonl): forward noising 0.577 -> 0.480 ms, per-row-t
+// reverse step 0.522 -> 0.475 ms with the warp schedule; closed-form score 0.191 -> 0.212 ms, log 0.213 -> 0.235 ms
+// (the per-warp store issue costs more than the barriers did), so those stay CTA-synchronous.
+template <class Op, class = void>
+struct OpWarpSchedule {
+  static constexpr bool value = false;
+};
 template <class Op>
-__global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(const Op op, const int64_t n, const int use_tma) {
+struct OpWarpSchedule<Op, std::void_t<decltype(Op::kWarpSchedule)>> {
+  static constexpr bool value = Op::kWarpSchedule;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_cta(const Op op, const int64_t n, const int use_tma) {
   extern __shared__ float4 smem4[];
   constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
   using Lay = OpLayout<Op>;
@@ -287,6 +301,179 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
   if (tid == 0) bulk_wait_read<0>();
 }
 
+// Warp-autonomous schedule (no CTA-wide barrier inside the tile loop):
+//   * input: one bulk load per array and 256-row tile into stage k & 1, completion on full[stage]; every warp
+//     waits on the mbarrier itself, copies its 32 rows to registers and releases the stage by an acq_rel
+//     atomic add on a per-stage counter -- the LAST warp to release (old & 7 == 7) issues the bulk loads of
+//     tile k+2 into the stage it has just freed, so nobody ever waits for a producer;
+//   * output: each warp owns the 32-row slice [32 w, 32 w + 32) of the output stage (32 x 36 B = 1152 B,
+//     32 x 12 B = 384 B: contiguous, 16-byte aligned), fences it to the async proxy and lane 0 issues the
+//     warp's own bulk stores; the warp's bulk groups are drained by lane 0 before the slice is reused;
+//   * ragged tail / unaligned arrays: the warp moves its own rows with coalesced ld/st.global.cs.
+// Warps of a CTA drift freely (by up to two tiles), which hides the per-row latency spread of the table
+// look-ups and removes the barrier stalls of the CTA-synchronous schedule (ncu r01e: 1.4-4.4 stalled warps
+// per issue on the reverse step / forward noising kernels).
+template <int W>
+__device__ __forceinline__ void warp_load(float* __restrict__ sm, const float* __restrict__ g, int rows, int lane) {
+  for (int i = lane; i < rows * W; i += 32) sm[i] = __ldcs(g + i);
+}
+template <int W>
+__device__ __forceinline__ void warp_store(float* __restrict__ g, const float* __restrict__ sm, int rows, int lane) {
+  for (int i = lane; i < rows * W; i += 32) __stcs(g + i, sm[i]);
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_cta(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(const Op op, const int64_t n, const int use_tma) {
+  extern __shared__ float4 smem4[];
+  constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
+  constexpr int kWarps = kTile / 32;
+  using Lay = OpLayout<Op>;
+  float* smem = reinterpret_cast<float*>(smem4);
+  // [in stage 0][in stage 1][out stage 0][out stage 1 if double-buffered]; every array starts 16-byte aligned
+  float* s_out = smem + 2 * Lay::kInFloats;
+  float* s_tab = s_out + Lay::kOutStages * Lay::kOutFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
+  uint32_t* released = reinterpret_cast<uint32_t*>(bars + 2);  // per input stage: warps that have copied their rows out
+  const int tid = threadIdx.x, lane = tid & 31, wrow = tid & ~31;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    released[0] = 0;
+    released[1] = 0;
+    fence_barrier_init();
+  }
+  op.setup(s_tab);
+  __syncthreads();
+
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  const int64_t my_tiles = (tiles > (int64_t)blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_row0 = [&](int64_t k) -> int64_t { return (blockIdx.x + k * gridDim.x) * (int64_t)kTile; };
+  auto tile_rows = [&](int64_t k) -> int {
+    const int64_t left = n - tile_row0(k);
+    return (int)(left < kTile ? left : kTile);
+  };
+  auto issue_load = [&](int64_t k) {  // one thread
+    if (kI9 + kI3 == 0) return;
+    const int64_t row0 = tile_row0(k);
+    const int st = (int)(k & 1);
+    float* base = smem + st * Lay::kInFloats;
+    mbar_expect_tx(&bars[st], (uint32_t)(kTile * Lay::kInWords * sizeof(float)));
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) bulk_load(base + a * kTile * 9, op.in9[a] + row0 * 9, kTile * 9 * sizeof(float), &bars[st]);
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
+  };
+  if (tid == 0 && use_tma) {
+    if (my_tiles > 0 && tile_rows(0) == kTile) issue_load(0);
+    if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
+  }
+
+  // software pipeline registers (empty structs for ops without prefetch hooks)
+  constexpr bool kPre = HasPre<Op>::value;
+  typename PreTypes<Op>::P1 p1_next{};   // Pre1 of tile k+1
+  typename PreTypes<Op>::P2 p2_cur{};    // Pre2 of tile k
+  auto pre_row = [&](int64_t k) -> int64_t {  // this thread's row of tile k, clamped into range (result unused if beyond)
+    const int64_t i = tile_row0(k) + tid;
+    return i < n ? i : n - 1;
+  };
+  if constexpr (kPre) {
+    if (my_tiles > 0) p2_cur = op.prefetch2(pre_row(0), op.prefetch1(pre_row(0)));
+    if (my_tiles > 1) p1_next = op.prefetch1(pre_row(1));
+  }
+
+  for (int64_t k = 0; k < my_tiles; ++k) {
+    const int st = (int)(k & 1);
+    const int64_t row0 = tile_row0(k);
+    const int rows = tile_rows(k);
+    const bool tma = use_tma && rows == kTile;
+    int wrows = rows - wrow;  // rows of this warp's slice that exist
+    wrows = wrows < 0 ? 0 : (wrows > 32 ? 32 : wrows);
+    float* s_i9 = smem + st * Lay::kInFloats;
+    float* s_i3 = s_i9 + kI9 * kTile * 9;
+    float* s_o9 = s_out + (Lay::kOutStages == 2 ? st : 0) * Lay::kOutFloats;
+    float* s_o3 = s_o9 + kO9 * kTile * 9;
+    if (kI9 + kI3 > 0) {
+      if (tma) {
+        mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+      } else {
+#pragma unroll
+        for (int a = 0; a < kI9; ++a) warp_load<9>(s_i9 + a * kTile * 9 + wrow * 9, op.in9[a] + (row0 + wrow) * 9, wrows, lane);
+#pragma unroll
+        for (int a = 0; a < kI3; ++a) warp_load<3>(s_i3 + a * kTile * 3 + wrow * 3, op.in3[a] + (row0 + wrow) * 3, wrows, lane);
+        __syncwarp();
+      }
+    }
+    Mat3 a9[kI9 > 0 ? kI9 : 1];
+    Vec3 a3[kI3 > 0 ? kI3 : 1];
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) a9[a] = sm_mat(s_i9 + a * kTile * 9, tid);
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, tid);
+    if (kI9 + kI3 > 0) {
+      __syncwarp();  // every lane's copy of its row is complete
+      if (tma && lane == 0 && k + 2 < my_tiles) {
+        const uint32_t old = atom_add_acq_rel_cta(&released[st], 1u);
+        if ((old & (kWarps - 1)) == kWarps - 1 && tile_rows(k + 2) == kTile) issue_load(k + 2);  // last warp out refills the stage
+      }
+    }
+
+    Mat3 o9[kO9 > 0 ? kO9 : 1];
+    Vec3 o3[kO3 > 0 ? kO3 : 1];
+    if constexpr (kPre) {
+      typename PreTypes<Op>::P2 p2_next{};
+      typename PreTypes<Op>::P1 p1_next2{};
+      if (k + 1 < my_tiles) p2_next = op.prefetch2(pre_row(k + 1), p1_next);  // loads land during this tile's arithmetic
+      if (k + 2 < my_tiles) p1_next2 = op.prefetch1(pre_row(k + 2));
+      if (tid < rows) op.row(row0 + tid, p2_cur, a9, a3, o9, o3, s_tab);
+      p2_cur = p2_next;
+      p1_next = p1_next2;
+    } else {
+      if (tid < rows) op.row(row0 + tid, a9, a3, o9, o3, s_tab);
+    }
+    if (kO9 + kO3 > 0) {
+      // this warp's earlier bulk stores must have finished reading the slice that is about to be overwritten
+      if (lane == 0) {
+        if (Lay::kOutStages == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      }
+      __syncwarp();
+      if (tid < rows) {
+#pragma unroll
+        for (int a = 0; a < kO9; ++a) sm_put_mat(s_o9 + a * kTile * 9, tid, o9[a]);
+#pragma unroll
+        for (int a = 0; a < kO3; ++a) sm_put_vec(s_o3 + a * kTile * 3, tid, o3[a]);
+      }
+      if (tma) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < kO9; ++a)
+            if (op.out9[a]) bulk_store(op.out9[a] + (row0 + wrow) * 9, s_o9 + a * kTile * 9 + wrow * 9, 32 * 9 * sizeof(float));
+#pragma unroll
+          for (int a = 0; a < kO3; ++a)
+            if (op.out3[a]) bulk_store(op.out3[a] + (row0 + wrow) * 3, s_o3 + a * kTile * 3 + wrow * 3, 32 * 3 * sizeof(float));
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < kO9; ++a)
+          if (op.out9[a]) warp_store<9>(op.out9[a] + (row0 + wrow) * 9, s_o9 + a * kTile * 9 + wrow * 9, wrows, lane);
+#pragma unroll
+        for (int a = 0; a < kO3; ++a)
+          if (op.out3[a]) warp_store<3>(op.out3[a] + (row0 + wrow) * 3, s_o3 + a * kTile * 3 + wrow * 3, wrows, lane);
+        __syncwarp();  // the slice may be rewritten next iteration (single output stage)
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();
+}
+
 template <class Op>
 int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int ctas_per_sm = 0) {
   if (n < 0) return fail(SO3D_EINVAL, "negative n");
@@ -306,19 +493,26 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
   static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
   // Persistent grid = exactly the CTAs that are resident at once (registers and shared memory both count): with
   // a static partition of the tiles, a grid larger than one wave leaves the last, partial wave's SMs idle.
-  static int resident = 0;  // per Op instantiation
-  if (resident == 0) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(rowwise_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int resident[2] = {0, 0};  // per Op instantiation and schedule
+  static const int cta_sync = [] {  // A/B aid: SO3D_ENGINE=cta|warp overrides the op's own choice
+    const char* e = getenv("SO3D_ENGINE");
+    if (e && strcmp(e, "cta") == 0) return 1;
+    if (e && strcmp(e, "warp") == 0) return 0;
+    return OpWarpSchedule<Op>::value ? 0 : 1;
+  }();
+  auto kern = cta_sync ? rowwise_kernel_cta<Op> : rowwise_kernel<Op>;
+  if (resident[cta_sync] == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowwise_kernel<Op>, kTile, smem) != cudaSuccess || occ < 1) occ = 1;
-    resident = occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTile, smem) != cudaSuccess || occ < 1) occ = 1;
+    resident[cta_sync] = occ;
   }
-  if (ctas_per_sm <= 0 || ctas_per_sm > resident) ctas_per_sm = resident;
+  if (ctas_per_sm <= 0 || ctas_per_sm > resident[cta_sync]) ctas_per_sm = resident[cta_sync];
   if (const char* e = getenv("SO3D_CTAS_PER_SM")) {  // tuning aid: cap the persistent grid (CTAs per SM)
     const int v = atoi(e);
     if (v > 0 && v < ctas_per_sm) ctas_per_sm = v;
   }
-  rowwise_kernel<Op><<<grid_for(n, ctas_per_sm), kTile, smem, (cudaStream_t)stream>>>(op, n, use_tma);
+  kern<<<grid_for(n, ctas_per_sm), kTile, smem, (cudaStream_t)stream>>>(op, n, use_tma);
   return check_launch(name);
 }
 
@@ -502,6 +696,7 @@ template <int kMode>
 struct LogpScoreOp {  // distributions.py:74-77 + score, fused with the axis-angle extraction
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
+  static constexpr int kMinCtas = (kMode == kClosed || kMode == kAuto) ? 5 : 1;  // HBM-bound evaluators: >= 5 CTAs (<= 51 registers)
   const float* eps;
   int eps_stride;
   float* logp;
@@ -625,6 +820,7 @@ template <bool kShared>
 struct SampleOp {
   SO3D_OP_ARRAYS(0, 0, 1, 1)
   static constexpr int kTab = kTabCdfFloats;
+  static constexpr bool kWarpSchedule = !kShared;
   const float* cdf;
   const uint32_t* guide;
   const float* loc;
@@ -711,9 +907,16 @@ struct BinghamOp {
 template <bool kExtra>  // kExtra: the optional noise / score outputs are compiled in (more shared memory per stage)
 struct QSampleOp {
   // per-row table rows are dependent L2 accesses: latency-bound, so favour resident CTAs over output double-buffering
-  SO3D_OP_ARRAYS_S(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1), 1)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
+#ifndef SO3D_QS_OUTSTAGES
+#define SO3D_QS_OUTSTAGES 1
+#endif
+#ifndef SO3D_QS_MINCTAS
+#define SO3D_QS_MINCTAS 4
+#endif
+  SO3D_OP_ARRAYS_S(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1), SO3D_QS_OUTSTAGES)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
   static constexpr int kTab = kGrid;  // loc only
-  static constexpr int kMinCtas = 5;  // cap registers at 51: the software pipeline must not cost occupancy
+  static constexpr int kMinCtas = SO3D_QS_MINCTAS;  // 4 CTAs (<= 64 registers, no spills) beat 5 CTAs with 56 B of spills: 0.442 vs 0.476 ms (r01m)
+  static constexpr bool kWarpSchedule = true;
   const int64_t* t;
   const float* sqrt_ac;
   const float* sqrt_1m_ac;
@@ -789,6 +992,16 @@ template <bool kSharedT, bool kX0>
 struct PStepOp {
   SO3D_OP_ARRAYS_S(1, 1, (kX0 ? 2 : 1), 0, (kSharedT ? 2 : 1))  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
+  // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
+  // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
+#ifndef SO3D_PS_MINCTAS
+#define SO3D_PS_MINCTAS 3
+#endif
+#ifndef SO3D_PSS_MINCTAS
+#define SO3D_PSS_MINCTAS 1
+#endif
+  static constexpr int kMinCtas = kSharedT ? SO3D_PSS_MINCTAS : SO3D_PS_MINCTAS;
+  static constexpr bool kWarpSchedule = !kSharedT;
   const int64_t* t;
   const float* recip;
   const float* recipm1;
@@ -834,6 +1047,7 @@ constexpr uint64_t kShiftStream = 0x8000000000000000ull;
 struct SE3QSampleOp {
   SO3D_OP_ARRAYS_S(1, 1, 1, 3, 1)  // in: rot0 | shift0;  out: rot_t | target_rot, shift_t, target_shift
   static constexpr int kTab = kGrid;
+  static constexpr bool kWarpSchedule = true;
   const int64_t* t;
   const float* sqrt_ac;
   const float* sqrt_1m_ac;
@@ -869,6 +1083,16 @@ template <bool kSharedT>
 struct SE3PStepOp {
   SO3D_OP_ARRAYS_S(1, 3, 1, 1, 1)  // in: rot_t | pred_rot, shift_t, pred_shift;  out: rot | shift
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
+  // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
+  // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
+#ifndef SO3D_PS_MINCTAS
+#define SO3D_PS_MINCTAS 3
+#endif
+#ifndef SO3D_PSS_MINCTAS
+#define SO3D_PSS_MINCTAS 1
+#endif
+  static constexpr int kMinCtas = kSharedT ? SO3D_PSS_MINCTAS : SO3D_PS_MINCTAS;
+  static constexpr bool kWarpSchedule = !kSharedT;
   const int64_t* t;
   const float* recip;
   const float* recipm1;

@@ -730,6 +730,9 @@ SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out)
 // FP32 instruction throughput is set by vector-register operand reads: 3-register FFMA 85, 2-register
 // forms 117, 1-register forms 129 lanes/clk/SM -- so each factor kept out of the vector register file
 // is a direct saving, and FFMA2 (f32x2) does not help (same operand words per flop).
+// Also measured (profiles/r01l_series_ab.jsonl): deriving every second weight by a multiply, e_{l-1} = e_l rho_l,
+// rho_{l-2} = rho_l 2^(4c) (half the MUFU, +0.5 FMUL per term) is SLOWER, 12.9 vs 12.2 clk per warp-term: the
+// FP32 operand bandwidth is the wall, not the XU pipe.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSeriesBlock = 32;       // unrolled terms per block
 constexpr int kSeriesMaxTerms = 2896;  // m(m+1) is exact in fp32 below this
@@ -934,6 +937,9 @@ SO3D_HD float igso3_angle_from_record(const float* trap, const float* loc, const
     return (wgt < 0.5f) ? fmaf(wgt, d, a0) : fmaf(-d, 1.0f - wgt, a1);
   }
   const bool in01 = (u >= 0.f) && (u < 1.0f);
+  // (Measured, profiles/r01n_probe_engine.jsonl: resolving 2..8-point buckets with one batch of nine independent
+  // loads instead of this dependent search is SLOWER, 0.459 vs 0.442 ms for the forward-noising kernel -- the kernel
+  // is issue-bound, the search's latency is hidden by the other warps, and the batch costs more issue slots.)
   return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, in01 ? lo : 0, in01 ? hi : kCdf));
 }
 
