@@ -537,19 +537,19 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
 struct LogOp {  // util.py:164-192
   SO3D_OP_ARRAYS(1, 0, 1, 0)
   SO3D_OP_NO_TAB
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = hat(log_vec(a9[0])); }
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = hat(log_vec_fast(a9[0])); }
 };
 struct LogVecOp {
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
-  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const { o3[0] = log_vec(a9[0]); }
+  __device__ void row(int64_t, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const { o3[0] = log_vec_fast(a9[0]); }
 };
 struct RmatToAaOp {  // util.py:208-219
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
   float* angle;
   __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const {
-    const AxisAngle a = axis_angle(a9[0]);
+    const AxisAngleF a = axis_angle_fast(a9[0]);
     o3[0] = a.axis;
     angle[i] = a.theta;
   }
@@ -563,14 +563,14 @@ struct AaToRmatOp {  // util.py:195-205
 struct ExpVecOp {  // diffusion.py:294
   SO3D_OP_ARRAYS(0, 1, 1, 0)
   SO3D_OP_NO_TAB
-  __device__ void row(int64_t, const Mat3*, const Vec3* a3, Mat3* o9, Vec3*, const float*) const { o9[0] = exp_vec(a3[0]); }
+  __device__ void row(int64_t, const Mat3*, const Vec3* a3, Mat3* o9, Vec3*, const float*) const { o9[0] = quat_to_mat_unit(quat_exp_vec(a3[0])); }
 };
 struct ScaleOp {  // util.py:349-361
   SO3D_OP_ARRAYS(1, 0, 1, 0)
   SO3D_OP_NO_TAB
   const float* s;
   int s_stride;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = scale_rot(a9[0], s[i * s_stride]); }
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const { o9[0] = scale_rot_fast(a9[0], s[i * s_stride]); }
 };
 struct RmatToQuatOp {
   SO3D_OP_ARRAYS(1, 0, 0, 0)
@@ -642,8 +642,8 @@ struct LerpOp {  // util.py:325-338
   const float* w;
   int w_stride;
   __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3* o9, Vec3*, const float*) const {
-    const AxisAngle a = axis_angle(mul_tn(a9[0], a9[1]));
-    o9[0] = mul_nn(a9[0], rodrigues(a.axis, w[i * w_stride] * a.theta));
+    const AxisAngleF a = axis_angle_fast(mul_tn(a9[0], a9[1]));
+    o9[0] = mul_nn(a9[0], quat_to_mat_unit(quat_axis_angle(a.axis, w[i * w_stride] * a.theta)));
   }
 };
 

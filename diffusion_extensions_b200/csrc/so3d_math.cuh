@@ -454,6 +454,17 @@ SO3D_HD AxisAngleF axis_angle_fast(const Mat3& r) {
   return o;
 }
 
+// The L0 maps of util.py on the lean primitives (what the row-engine kernels run; the general-purpose versions
+// above stay as the backward passes' and the host harness's definition).
+SO3D_HD Vec3 log_vec_fast(const Mat3& r) {  // util.py:164-192: vee(log R) = theta axis
+  const AxisAngleF a = axis_angle_fast(r);
+  return Vec3{a.theta * a.axis.x, a.theta * a.axis.y, a.theta * a.axis.z};
+}
+SO3D_HD Mat3 scale_rot_fast(const Mat3& r, float s) {  // util.py:349-361: rotation by s theta about the axis of R
+  const AxisAngleF a = axis_angle_fast(r);
+  return quat_to_mat_unit(quat_axis_angle(a.axis, s * a.theta));
+}
+
 // half-angle in [0, pi/2] and unit axis of a (near-)unit quaternion, with q and -q identified
 SO3D_HD void quat_axis_halfangle(const Quat& q, Vec3* n, float* half) {
   const float v2 = fmaf(q.x, q.x, fmaf(q.y, q.y, q.z * q.z));

@@ -25,6 +25,16 @@ void hm_exp_vec(const float* v, float* R, long n) {
 void hm_scale(const float* R, const float* s, float* out, long n) {
   for (long i = 0; i < n; ++i) st(out + 9 * i, scale_rot(ld(R + 9 * i), s[i]));
 }
+// what the row-engine kernels run for the L0 maps (lean primitives)
+void hm_log_vec_fast(const float* R, float* v, long n) {
+  for (long i = 0; i < n; ++i) { Vec3 a = log_vec_fast(ld(R + 9 * i)); v[3*i]=a.x; v[3*i+1]=a.y; v[3*i+2]=a.z; }
+}
+void hm_exp_vec_fast(const float* v, float* R, long n) {
+  for (long i = 0; i < n; ++i) st(R + 9 * i, quat_to_mat_unit(quat_exp_vec(Vec3{v[3*i], v[3*i+1], v[3*i+2]})));
+}
+void hm_scale_fast(const float* R, const float* s, float* out, long n) {
+  for (long i = 0; i < n; ++i) st(out + 9 * i, scale_rot_fast(ld(R + 9 * i), s[i]));
+}
 void hm_quat_to_rmat(const float* q, float* R, long n) {
   for (long i = 0; i < n; ++i) st(R + 9 * i, quat_to_rmat(q[4*i], q[4*i+1], q[4*i+2], q[4*i+3]));
 }

@@ -100,6 +100,34 @@ def test_exp_scale_quat(hm):
     assert np.max(np.abs(O.quat_to_rmat(q2) - R)) < 2e-6
 
 
+def test_l0_maps_on_lean_primitives(hm):
+    """The forward L0 kernels (log / exp / so3_scale) run the branch-free quaternion primitives: same tolerances
+    against the fp64 oracle as the general-purpose versions above, including identity, pi and tiny angles."""
+    n = 4096
+    rng = np.random.default_rng(11)
+    R, _, ang_t = rand_rots(n, 12)
+    v = np.empty((n, 3), np.float32)
+    hm.hm_log_vec_fast(fp(R), fp(v), ctypes.c_long(n))
+    assert np.max(np.abs(v - O.log_vec(R))[ang_t < 3.1]) < 3e-6
+    assert np.max(np.abs(np.linalg.norm(v, axis=-1) - ang_t)) < 2e-6
+    ax = rng.standard_normal((64, 3)); ax /= np.linalg.norm(ax, axis=-1, keepdims=True)
+    Re = np.concatenate([f32(np.eye(3))[None], f32(O.rodrigues(ax, np.full(64, math.pi))), f32(O.rodrigues(ax, np.full(64, 1e-5)))])
+    ve = np.empty((129, 3), np.float32)
+    hm.hm_log_vec_fast(fp(Re), fp(ve), ctypes.c_long(129))
+    assert np.array_equal(ve[0], [0, 0, 0])
+    assert np.max(np.abs(np.linalg.norm(ve[1:65], axis=-1) - math.pi)) < 2e-6
+    assert np.min(np.abs((ve[1:65] / math.pi * ax).sum(-1))) > 1 - 1e-6          # axis at pi: defined up to sign
+    assert np.max(np.abs(ve[65:] - 1e-5 * ax)) < 1e-9
+    w = f32(rng.standard_normal((n, 3)) * np.exp(rng.uniform(-12, 1, (n, 1))))
+    out = np.empty((n, 3, 3), np.float32)
+    hm.hm_exp_vec_fast(fp(w), fp(out), ctypes.c_long(n))
+    assert np.max(np.abs(out - O.exp_vec(w))) < 1e-6
+    R3, _, _ = rand_rots(n, 13, 3.0)
+    s = f32(np.exp(rng.uniform(math.log(1e-4), math.log(3.0), n)))
+    hm.hm_scale_fast(fp(R3), fp(s), fp(out), ctypes.c_long(n))
+    assert np.max(np.abs(out - O.so3_scale(R3, s))) < 3e-6
+
+
 def eset(n, seed, kmax=4.0):
     rng = np.random.default_rng(seed)
     eps = np.exp(rng.uniform(math.log(6.4e-3), 0.0, n)).astype(np.float32)
