@@ -11,9 +11,10 @@ Deliberate deviations from the reference:
   * log_rmat / rmat_to_aa are accurate up to and at a rotation by pi (Q4) and return the axis
     (0,0,1) with angle 0 at the identity instead of NaN (Q10).
 """
+import inspect
 from itertools import product
 from math import log
-from typing import Tuple
+from typing import Iterable, Tuple
 
 import torch
 
@@ -91,6 +92,21 @@ def rmat_to_euler(rmat: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch
 # hat / vee  (util.py:79-92) -- pure data movement, kept as torch indexing (fused away inside the
 # kernels wherever they sit on the hot path)
 # ---------------------------------------------------------------------------------------------
+def rmat2six(x: torch.Tensor) -> torch.Tensor:
+    """util.py:62-64: the 6-D rotation representation = the first two ROWS, flattened."""
+    return torch.flatten(x[..., :2, :], -2, -1)
+
+
+def six2rmat(x: torch.Tensor) -> torch.Tensor:
+    """util.py:67-76: Gram-Schmidt of the two 3-vectors, third row by the cross product (plain torch: a
+    network-output adapter, differentiable, not on the sampling path)."""
+    a1, a2 = x[..., :3], x[..., 3:6]
+    b1 = a1 / a1.norm(p=2, dim=-1, keepdim=True)
+    b2 = a2 - (b1 * a2).sum(dim=-1, keepdim=True) * b1
+    b2 = b2 / b2.norm(p=2, dim=-1, keepdim=True)
+    return torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), dim=-2)
+
+
 def skew2vec(skew: torch.Tensor) -> torch.Tensor:
     return torch.stack((skew[..., 2, 1], -skew[..., 2, 0], skew[..., 1, 0]), dim=-1)
 
@@ -257,6 +273,18 @@ def so3_lerp(rot_a: torch.Tensor, rot_b: torch.Tensor, weight: torch.Tensor) -> 
     return ops.so3_lerp(rot_a, rot_b, w)
 
 
+def so3_bezier(*rots, weight):
+    """util.py:340-346: de Casteljau on SO(3) with so3_lerp.  (The reference recurses with the tuple slices as ONE
+    argument, so it only works for two control rotations; this is the evident intent for any number >= 2.)"""
+    if len(rots) < 2:
+        raise ValueError("so3_bezier needs at least two control rotations")
+    if len(rots) == 2:
+        return so3_lerp(*rots, weight=weight)
+    a = so3_bezier(*rots[:-1], weight=weight)
+    b = so3_bezier(*rots[1:], weight=weight)
+    return so3_lerp(a, b, weight=weight)
+
+
 def so3_scale(rmat, scalars):
     """util.py:349-361: scale the rotation angle, exp(scalars * log(rmat))."""
     if not isinstance(scalars, torch.Tensor):
@@ -352,3 +380,50 @@ __all__ = [
     "AffineT", "AffineGrad", "euler_to_rmat", "rmat_to_euler", "se3_lerp", "se3_scale",
     "rmat_cosine_dist", "rmat_gaussian_kernel", "rmat_cosine_kernel", "MMD", "Ker_2samp_test", "Ker_2samp_log_prob",
 ]
+
+
+# ---------------------------------------------------------------------------------------------
+# small helpers the reference's scripts import from util (util.py:426-481)
+# ---------------------------------------------------------------------------------------------
+def to_device(device, *objects, non_blocking=False):
+    """util.py:426-437: move tensors / AffineT / nested iterables of them to `device`, keeping the structure."""
+    out = []
+    for obj in objects:
+        if isinstance(obj, (torch.Tensor, AffineT)):
+            out.append(obj.to(device, non_blocking=non_blocking) if isinstance(obj, torch.Tensor) else obj.to(device))
+        elif isinstance(obj, Iterable) and not isinstance(obj, (str, bytes)):
+            out.append(to_device(device, *obj, non_blocking=non_blocking))
+        else:
+            raise NotImplementedError(f"Object type {type(obj)} unsupported")
+    return out
+
+
+def init_from_dict(argdict, *classes):
+    """util.py:440-460: build each class from the entries of `argdict` its constructor names (others ignored)."""
+    objs = []
+    for cls in classes:
+        names = [k for k, v in inspect.signature(cls).parameters.items() if v.kind == inspect.Parameter.POSITIONAL_OR_KEYWORD]
+        objs.append(cls(**{k: v for k, v in argdict.items() if k in names}))
+    return objs
+
+
+def identity(x):
+    return x
+
+
+def masked_mean(tensor, mask, dim=-1):
+    """util.py:467-475: mean over `dim` of the entries where mask is set (0 where none are); zeroes the masked
+    entries of `tensor` IN PLACE like the reference."""
+    mask = mask[(..., *((None,) * (tensor.dim() - mask.dim())))]
+    tensor.masked_fill_(~mask, 0.)
+    total = mask.sum(dim=dim)
+    mean = tensor.sum(dim=dim) / total.clamp(min=1.)
+    mean.masked_fill_(total == 0, 0.)
+    return mean
+
+
+def cycle(iterable):
+    """util.py:478-481: endless iterator over `iterable` (restarts it when exhausted)."""
+    while True:
+        for x in iterable:
+            yield x

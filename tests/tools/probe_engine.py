@@ -58,6 +58,7 @@ cases = [
     ("p_sample shared t", 84, lambda: ops.p_sample_fused(R, pred, t1, *sched, post_cdf=post, seed=1, rng_offset=1)),
     ("p_sample per-row t", 92, lambda: ops.p_sample_fused(R, pred, tt, *sched, post_cdf=post, seed=1, rng_offset=1, post_guide=post_guide)),
     ("q_sample per-row t", 92, lambda: ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fwd_guide)),
+    ("q_sample + score", 104, lambda: ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fwd_guide, want_score=True)),
     ("score auto", 56, lambda: ops.igso3_logp_score(R, eps, mode="auto")),
     ("score closed", 56, lambda: ops.igso3_logp_score(R, eps, mode="closed")),
     ("sample shared row", 48, lambda: ops.igso3_sample(fwd, (n,), row=500, seed=1, rng_offset=1)),
