@@ -184,17 +184,17 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
   op.setup(s_tab);
   __syncthreads();
 
+  // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
+  // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is
+  // carried incrementally: no 64-bit multiplies in the tile loop (the kernels are issue-bound).
   const int64_t tiles = (n + kTile - 1) / kTile;
-  const int64_t my_tiles = (tiles > (int64_t)blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  auto tile_row0 = [&](int64_t k) -> int64_t { return (blockIdx.x + k * gridDim.x) * (int64_t)kTile; };
-  auto tile_rows = [&](int64_t k) -> int {
-    const int64_t left = n - tile_row0(k);
-    return (int)(left < kTile ? left : kTile);
-  };
-  auto issue_load = [&](int64_t k) {  // thread 0 only
+  const int my_tiles = (tiles > (int64_t)blockIdx.x) ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int my_full = my_tiles - (((n % kTile) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
+  const int64_t first_row = (int64_t)blockIdx.x * kTile, stride_rows = (int64_t)gridDim.x * kTile;
+  auto tile_row0 = [&](int k) -> int64_t { return first_row + k * stride_rows; };  // off the per-tile path
+  auto issue_load = [&](int k, int64_t row0) {  // thread 0 only
     if (kI9 + kI3 == 0) return;
-    const int64_t row0 = tile_row0(k);
-    const int st = (int)(k & 1);
+    const int st = k & 1;
     float* base = smem + st * Lay::kInFloats;
     mbar_expect_tx(&bars[st], (uint32_t)(kTile * Lay::kInWords * sizeof(float)));
 #pragma unroll
@@ -203,27 +203,27 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
   };
   if (tid == 0 && use_tma) {
-    if (my_tiles > 0 && tile_rows(0) == kTile) issue_load(0);
-    if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
+    if (my_full > 0) issue_load(0, tile_row0(0));
+    if (my_full > 1) issue_load(1, tile_row0(1));
   }
 
   // software pipeline registers (empty structs for ops without prefetch hooks)
   constexpr bool kPre = HasPre<Op>::value;
   typename PreTypes<Op>::P1 p1_next{};   // Pre1 of tile k+1
   typename PreTypes<Op>::P2 p2_cur{};    // Pre2 of tile k
-  auto pre_row = [&](int64_t k) -> int64_t {  // this thread's row of tile k, clamped into range (result unused if beyond)
-    const int64_t i = tile_row0(k) + tid;
+  auto pre_row = [&](int64_t row0) -> int64_t {  // this thread's row of the tile at row0, clamped into range (result unused if beyond)
+    const int64_t i = row0 + tid;
     return i < n ? i : n - 1;
   };
   if constexpr (kPre) {
-    if (my_tiles > 0) p2_cur = op.prefetch2(pre_row(0), op.prefetch1(pre_row(0)));
-    if (my_tiles > 1) p1_next = op.prefetch1(pre_row(1));
+    if (my_tiles > 0) p2_cur = op.prefetch2(pre_row(first_row), op.prefetch1(pre_row(first_row)));
+    if (my_tiles > 1) p1_next = op.prefetch1(pre_row(first_row + stride_rows));
   }
 
-  for (int64_t k = 0; k < my_tiles; ++k) {
-    const int st = (int)(k & 1);
-    const int64_t row0 = tile_row0(k);
-    const int rows = tile_rows(k);
+  int64_t row0 = first_row;
+  for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
+    const int st = k & 1;
+    const int rows = k < my_full ? kTile : (int)(n - row0);
     const bool tma = use_tma && rows == kTile;
     float* s_i9 = smem + st * Lay::kInFloats;
     float* s_i3 = s_i9 + kI9 * kTile * 9;
@@ -248,15 +248,15 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, tid);
     if (Lay::kOutStages == 2 && tid == 0) bulk_wait_read<1>();  // the stores that read out[st] two iterations ago have drained
     __syncthreads();                                            // A
-    if (tid == 0 && use_tma && k + 2 < my_tiles && tile_rows(k + 2) == kTile) issue_load(k + 2);
+    if (tid == 0 && use_tma && k + 2 < my_full) issue_load(k + 2, row0 + 2 * stride_rows);
 
     Mat3 o9[kO9 > 0 ? kO9 : 1];
     Vec3 o3[kO3 > 0 ? kO3 : 1];
     if constexpr (kPre) {
       typename PreTypes<Op>::P2 p2_next{};
       typename PreTypes<Op>::P1 p1_next2{};
-      if (k + 1 < my_tiles) p2_next = op.prefetch2(pre_row(k + 1), p1_next);  // loads land during this tile's arithmetic
-      if (k + 2 < my_tiles) p1_next2 = op.prefetch1(pre_row(k + 2));
+      if (k + 1 < my_tiles) p2_next = op.prefetch2(pre_row(row0 + stride_rows), p1_next);  // loads land during this tile's arithmetic
+      if (k + 2 < my_tiles) p1_next2 = op.prefetch1(pre_row(row0 + 2 * stride_rows));
       if (tid < rows) op.row(row0 + tid, p2_cur, a9, a3, o9, o3, s_tab);
       p2_cur = p2_next;
       p1_next = p1_next2;
@@ -350,17 +350,17 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
   op.setup(s_tab);
   __syncthreads();
 
+  // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
+  // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is
+  // carried incrementally: no 64-bit multiplies in the tile loop (the kernels are issue-bound).
   const int64_t tiles = (n + kTile - 1) / kTile;
-  const int64_t my_tiles = (tiles > (int64_t)blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  auto tile_row0 = [&](int64_t k) -> int64_t { return (blockIdx.x + k * gridDim.x) * (int64_t)kTile; };
-  auto tile_rows = [&](int64_t k) -> int {
-    const int64_t left = n - tile_row0(k);
-    return (int)(left < kTile ? left : kTile);
-  };
-  auto issue_load = [&](int64_t k) {  // one thread
+  const int my_tiles = (tiles > (int64_t)blockIdx.x) ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int my_full = my_tiles - (((n % kTile) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
+  const int64_t first_row = (int64_t)blockIdx.x * kTile, stride_rows = (int64_t)gridDim.x * kTile;
+  auto tile_row0 = [&](int k) -> int64_t { return first_row + k * stride_rows; };  // off the per-tile path
+  auto issue_load = [&](int k, int64_t row0) {  // one thread
     if (kI9 + kI3 == 0) return;
-    const int64_t row0 = tile_row0(k);
-    const int st = (int)(k & 1);
+    const int st = k & 1;
     float* base = smem + st * Lay::kInFloats;
     mbar_expect_tx(&bars[st], (uint32_t)(kTile * Lay::kInWords * sizeof(float)));
 #pragma unroll
@@ -369,27 +369,27 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
     for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
   };
   if (tid == 0 && use_tma) {
-    if (my_tiles > 0 && tile_rows(0) == kTile) issue_load(0);
-    if (my_tiles > 1 && tile_rows(1) == kTile) issue_load(1);
+    if (my_full > 0) issue_load(0, tile_row0(0));
+    if (my_full > 1) issue_load(1, tile_row0(1));
   }
 
   // software pipeline registers (empty structs for ops without prefetch hooks)
   constexpr bool kPre = HasPre<Op>::value;
   typename PreTypes<Op>::P1 p1_next{};   // Pre1 of tile k+1
   typename PreTypes<Op>::P2 p2_cur{};    // Pre2 of tile k
-  auto pre_row = [&](int64_t k) -> int64_t {  // this thread's row of tile k, clamped into range (result unused if beyond)
-    const int64_t i = tile_row0(k) + tid;
+  auto pre_row = [&](int64_t row0) -> int64_t {  // this thread's row of the tile at row0, clamped into range (result unused if beyond)
+    const int64_t i = row0 + tid;
     return i < n ? i : n - 1;
   };
   if constexpr (kPre) {
-    if (my_tiles > 0) p2_cur = op.prefetch2(pre_row(0), op.prefetch1(pre_row(0)));
-    if (my_tiles > 1) p1_next = op.prefetch1(pre_row(1));
+    if (my_tiles > 0) p2_cur = op.prefetch2(pre_row(first_row), op.prefetch1(pre_row(first_row)));
+    if (my_tiles > 1) p1_next = op.prefetch1(pre_row(first_row + stride_rows));
   }
 
-  for (int64_t k = 0; k < my_tiles; ++k) {
-    const int st = (int)(k & 1);
-    const int64_t row0 = tile_row0(k);
-    const int rows = tile_rows(k);
+  int64_t row0 = first_row;
+  for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
+    const int st = k & 1;
+    const int rows = k < my_full ? kTile : (int)(n - row0);
     const bool tma = use_tma && rows == kTile;
     int wrows = rows - wrow;  // rows of this warp's slice that exist
     wrows = wrows < 0 ? 0 : (wrows > 32 ? 32 : wrows);
@@ -416,9 +416,9 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
     for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, tid);
     if (kI9 + kI3 > 0) {
       __syncwarp();  // every lane's copy of its row is complete
-      if (tma && lane == 0 && k + 2 < my_tiles) {
+      if (tma && lane == 0 && k + 2 < my_full) {
         const uint32_t old = atom_add_acq_rel_cta(&released[st], 1u);
-        if ((old & (kWarps - 1)) == kWarps - 1 && tile_rows(k + 2) == kTile) issue_load(k + 2);  // last warp out refills the stage
+        if ((old & (kWarps - 1)) == kWarps - 1) issue_load(k + 2, row0 + 2 * stride_rows);  // last warp out refills the stage
       }
     }
 
@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
     if constexpr (kPre) {
       typename PreTypes<Op>::P2 p2_next{};
       typename PreTypes<Op>::P1 p1_next2{};
-      if (k + 1 < my_tiles) p2_next = op.prefetch2(pre_row(k + 1), p1_next);  // loads land during this tile's arithmetic
-      if (k + 2 < my_tiles) p1_next2 = op.prefetch1(pre_row(k + 2));
+      if (k + 1 < my_tiles) p2_next = op.prefetch2(pre_row(row0 + stride_rows), p1_next);  // loads land during this tile's arithmetic
+      if (k + 2 < my_tiles) p1_next2 = op.prefetch1(pre_row(row0 + 2 * stride_rows));
       if (tid < rows) op.row(row0 + tid, p2_cur, a9, a3, o9, o3, s_tab);
       p2_cur = p2_next;
       p1_next = p1_next2;
