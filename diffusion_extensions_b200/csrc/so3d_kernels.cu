@@ -1013,13 +1013,29 @@ struct PStepOp {
   const float* loc;
   uint64_t seed, rng_offset, row_offset;
   __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
+  // shared t: the step's five scalars are staged once per CTA next to the CDF row (broadcast LDS per tile instead of a
+  // dependent t -> schedule chain of global loads and 64-bit address math in every tile: -25 issue slots per warp-tile)
   __device__ void setup(float* tab) const {
     if (post_cdf) stage_cdf(tab, kSharedT ? post_cdf + clamp_t(t[0]) * kCdf : nullptr, loc);
+    if (kSharedT && threadIdx.x == 0) {
+      const int64_t ti = clamp_t(t[0]);
+      tab[kTabScal] = __int_as_float((int)ti);
+      tab[kTabScal + 1] = recip[ti];
+      tab[kTabScal + 2] = recipm1[ti];
+      tab[kTabScal + 3] = coef1[ti];
+      tab[kTabScal + 4] = coef2[ti];
+    }
   }
   __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3*, const float* tab) const {
-    const int64_t ti = clamp_t(kSharedT ? t[0] : t[i]);
-    const float k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti);
-    const float k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti);
+    int64_t ti;
+    float k_recip, k_recipm1, k_c1, k_c2;
+    if (kSharedT) {
+      ti = __float_as_int(tab[kTabScal]);
+      k_recip = tab[kTabScal + 1], k_recipm1 = tab[kTabScal + 2], k_c1 = tab[kTabScal + 3], k_c2 = tab[kTabScal + 4];
+    } else {
+      ti = clamp_t(t[i]);
+      k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti), k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti);
+    }
     Quat qh;
     Quat qm = p_mean_quat(a9[0], a3[0], k_recip, k_recipm1, k_c1, k_c2, &qh);
     if (post_cdf && ti != 0) {                                                     // diffusion.py:320-326
@@ -1108,11 +1124,26 @@ struct SE3PStepOp {
   __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
   __device__ void setup(float* tab) const {
     if (post_cdf) stage_cdf(tab, kSharedT ? post_cdf + clamp_t(t[0]) * kCdf : nullptr, loc);
+    if (kSharedT && threadIdx.x == 0) {  // the step's scalars, staged once per CTA (see PStepOp)
+      const int64_t ti = clamp_t(t[0]);
+      tab[kTabScal] = __int_as_float((int)ti);
+      tab[kTabScal + 1] = recip[ti];
+      tab[kTabScal + 2] = recipm1[ti];
+      tab[kTabScal + 3] = coef1[ti];
+      tab[kTabScal + 4] = coef2[ti];
+      tab[kTabScal + 5] = sigma[ti];
+    }
   }
   __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
-    const int64_t ti = clamp_t(kSharedT ? t[0] : t[i]);
-    const float k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti);
-    const float k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti);
+    int64_t ti;
+    float k_recip, k_recipm1, k_c1, k_c2, k_sigma;
+    if (kSharedT) {
+      ti = __float_as_int(tab[kTabScal]);
+      k_recip = tab[kTabScal + 1], k_recipm1 = tab[kTabScal + 2], k_c1 = tab[kTabScal + 3], k_c2 = tab[kTabScal + 4], k_sigma = tab[kTabScal + 5];
+    } else {
+      ti = clamp_t(t[i]);
+      k_recip = __ldg(recip + ti), k_recipm1 = __ldg(recipm1 + ti), k_c1 = __ldg(coef1 + ti), k_c2 = __ldg(coef2 + ti), k_sigma = __ldg(sigma + ti);
+    }
     Quat qh;
     Quat qm = p_mean_quat(a9[0], a3[0], k_recip, k_recipm1, k_c1, k_c2, &qh);
     const Vec3 st = a3[1], ps = a3[2];
@@ -1125,7 +1156,7 @@ struct SE3PStepOp {
       const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
       qm = qmul(qm, quat_axis_angle(d.axis, ang));
       const Normal4 z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset | kShiftStream));
-      const float ns = __ldg(sigma + ti) * shift_scale;
+      const float ns = k_sigma * shift_scale;
       m = Vec3{fmaf(ns, z.a, m.x), fmaf(ns, z.b, m.y), fmaf(ns, z.c, m.z)};
     }
     o9[0] = quat_to_mat_unit(qm);
