@@ -165,6 +165,20 @@ struct OpWarpSchedule<Op, std::void_t<decltype(Op::kWarpSchedule)>> {
   static constexpr bool value = Op::kWarpSchedule;
 };
 
+// Compute-bound ops (the 2000-term series) set Op::kWideIndex: they keep the 64-bit per-tile index arithmetic of
+// the first engine.  The tile loop is noise for them, but ptxas's list schedule of the unrolled 32-term block is
+// sensitive to the surrounding code: with the strength-reduced indices below the SAME instructions come out in an
+// order that runs 2.6 % slower (11.29 vs 11.00 ms per 2^24 evaluations, profiles/r01x_bench.json vs r01q), so the
+// headline kernel's instantiation is kept on the source form that yields the faster schedule.
+template <class Op, class = void>
+struct OpWideIndex {
+  static constexpr bool value = false;
+};
+template <class Op>
+struct OpWideIndex<Op, std::void_t<decltype(Op::kWideIndex)>> {
+  static constexpr bool value = Op::kWideIndex;
+};
+
 template <class Op>
 __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_cta(const Op op, const int64_t n, const int use_tma) {
   extern __shared__ float4 smem4[];
@@ -187,14 +201,31 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
   // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
   // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is
   // carried incrementally: no 64-bit multiplies in the tile loop (the kernels are issue-bound).
+  constexpr bool kWide = OpWideIndex<Op>::value;
+  using KIdx = std::conditional_t<kWide, int64_t, int>;
   const int64_t tiles = (n + kTile - 1) / kTile;
-  const int my_tiles = (tiles > (int64_t)blockIdx.x) ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  const int my_full = my_tiles - (((n % kTile) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
+  const KIdx my_tiles = (tiles > (int64_t)blockIdx.x) ? (KIdx)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int my_full = (int)my_tiles - (((n % kTile) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
   const int64_t first_row = (int64_t)blockIdx.x * kTile, stride_rows = (int64_t)gridDim.x * kTile;
-  auto tile_row0 = [&](int k) -> int64_t { return first_row + k * stride_rows; };  // off the per-tile path
-  auto issue_load = [&](int k, int64_t row0) {  // thread 0 only
+  auto tile_row0 = [&](KIdx k) -> int64_t {  // off the per-tile path unless kWide
+    if constexpr (kWide) return (blockIdx.x + k * gridDim.x) * (int64_t)kTile;
+    else return first_row + k * stride_rows;
+  };
+  auto tile_rows = [&](KIdx k, int64_t row0) -> int {
+    if constexpr (kWide) {
+      const int64_t left = n - row0;
+      return (int)(left < kTile ? left : kTile);
+    } else {
+      return k < my_full ? kTile : (int)(n - row0);
+    }
+  };
+  auto tile_full = [&](KIdx k) -> bool {  // tile k exists and is a full tile
+    if constexpr (kWide) return k < my_tiles && tile_rows(k, tile_row0(k)) == kTile;
+    else return k < my_full;
+  };
+  auto issue_load = [&](KIdx k, int64_t row0) {  // thread 0 only
     if (kI9 + kI3 == 0) return;
-    const int st = k & 1;
+    const int st = (int)(k & 1);
     float* base = smem + st * Lay::kInFloats;
     mbar_expect_tx(&bars[st], (uint32_t)(kTile * Lay::kInWords * sizeof(float)));
 #pragma unroll
@@ -203,8 +234,8 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
   };
   if (tid == 0 && use_tma) {
-    if (my_full > 0) issue_load(0, tile_row0(0));
-    if (my_full > 1) issue_load(1, tile_row0(1));
+    if (tile_full(0)) issue_load(0, tile_row0(0));
+    if (tile_full(1)) issue_load(1, tile_row0(1));
   }
 
   // software pipeline registers (empty structs for ops without prefetch hooks)
@@ -220,10 +251,11 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     if (my_tiles > 1) p1_next = op.prefetch1(pre_row(first_row + stride_rows));
   }
 
-  int64_t row0 = first_row;
-  for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
-    const int st = k & 1;
-    const int rows = k < my_full ? kTile : (int)(n - row0);
+  int64_t row_run = first_row;
+  for (KIdx k = 0; k < my_tiles; ++k, row_run += stride_rows) {
+    const int st = (int)(k & 1);
+    const int64_t row0 = kWide ? tile_row0(k) : row_run;
+    const int rows = tile_rows(k, row0);
     const bool tma = use_tma && rows == kTile;
     float* s_i9 = smem + st * Lay::kInFloats;
     float* s_i3 = s_i9 + kI9 * kTile * 9;
@@ -248,7 +280,7 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     for (int a = 0; a < kI3; ++a) a3[a] = sm_vec(s_i3 + a * kTile * 3, tid);
     if (Lay::kOutStages == 2 && tid == 0) bulk_wait_read<1>();  // the stores that read out[st] two iterations ago have drained
     __syncthreads();                                            // A
-    if (tid == 0 && use_tma && k + 2 < my_full) issue_load(k + 2, row0 + 2 * stride_rows);
+    if (tid == 0 && use_tma && tile_full(k + 2)) issue_load(k + 2, kWide ? tile_row0(k + 2) : row0 + 2 * stride_rows);
 
     Mat3 o9[kO9 > 0 ? kO9 : 1];
     Vec3 o3[kO3 > 0 ? kO3 : 1];
@@ -697,6 +729,7 @@ struct LogpScoreOp {  // distributions.py:74-77 + score, fused with 
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
   static constexpr int kMinCtas = (kMode == kClosed || kMode == kAuto) ? 5 : 1;  // HBM-bound evaluators: >= 5 CTAs (<= 51 registers)
+  static constexpr bool kWideIndex = (kMode == kSeries || kMode == kSeriesAdaptive);  // see rowwise_kernel_cta
   const float* eps;
   int eps_stride;
   float* logp;
@@ -828,7 +861,8 @@ struct SampleOp {
   int64_t shared_row, rows;
   const float* u_in;
   const float* axes_in;
-  uint64_t seed, rng_offset, row_offset;
+  PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
+  uint64_t row_offset;
   const float* mean;
   int mean_stride;
   float* angle_out;
@@ -842,7 +876,7 @@ struct SampleOp {
       axis = Vec3{ax * inv, ay * inv, az * inv};
     }
     if (!axes_in || !u_in) {
-      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+      const NoiseDraw d = draw_axis_u(key, row_offset + (uint64_t)i);
       if (!axes_in) axis = d.axis;
       u = d.u;
     }
@@ -878,7 +912,8 @@ struct BinghamOp {
   const float* z_in;  // optional explicit normals (n x 4)
   bool z_vec;
   float* q_out;       // optional (n x 4, 16-byte aligned)
-  uint64_t seed, rng_offset, row_offset;
+  PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
+  uint64_t row_offset;
   __device__ void row(int64_t i, const Mat3*, const Vec3*, Mat3* o9, Vec3*, const float*) const {
     Normal4 z;
     if (z_in) {
@@ -886,7 +921,7 @@ struct BinghamOp {
                              : make_float4(z_in[4 * i], z_in[4 * i + 1], z_in[4 * i + 2], z_in[4 * i + 3]);
       z = Normal4{v.x, v.y, v.z, v.w};
     } else {
-      z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset));
+      z = normal4_from_u4(philox4x32_10(key, row_offset + (uint64_t)i));
     }
     const float v0 = __ldg(tril + 0) * z.a;
     const float v1 = fmaf(__ldg(tril + 4), z.a, __ldg(tril + 5) * z.b);
@@ -924,7 +959,8 @@ struct QSampleOp {
   const float* cdf;
   const uint32_t* guide;
   const float* loc;
-  uint64_t seed, rng_offset, row_offset;
+  PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
+  uint64_t row_offset;
   __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
   // software pipeline: t two tiles ahead; the draw (a pure function of the global row index), the schedule
   // scalars and the guide record one tile ahead -- the row itself then touches no dependent global memory
@@ -945,7 +981,7 @@ struct QSampleOp {
     p.ti = (int)ti;
     p.eps = __ldg(sqrt_1m_ac + ti);
     p.sc = __ldg(sqrt_ac + ti);
-    p.d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+    p.d = draw_axis_u(key, row_offset + (uint64_t)i);
     p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuide + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
     return p;
   }
@@ -990,7 +1026,10 @@ struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
 // its guide live in shared memory; otherwise per-row t with table rows (and the optional guide) read through L2.
 template <bool kSharedT, bool kX0>
 struct PStepOp {
-  SO3D_OP_ARRAYS_S(1, 1, (kX0 ? 2 : 1), 0, (kSharedT ? 2 : 1))  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
+#ifndef SO3D_PSS_OUTSTAGES
+#define SO3D_PSS_OUTSTAGES 2
+#endif
+  SO3D_OP_ARRAYS_S(1, 1, (kX0 ? 2 : 1), 0, (kSharedT ? SO3D_PSS_OUTSTAGES : 1))  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
   // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
   // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
@@ -1039,6 +1078,8 @@ struct PStepOp {
     Quat qh;
     Quat qm = p_mean_quat(a9[0], a3[0], k_recip, k_recipm1, k_c1, k_c2, &qh);
     if (post_cdf && ti != 0) {                                                     // diffusion.py:320-326
+      // (the launcher-side key schedule the other ops use measured 2 % slower here: ptxas then allocates 46 instead of
+      // 63 registers and schedules with less overlap, profiles/r01w_probe_engine.jsonl)
       const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
       const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
       qm = qmul(qm, quat_axis_angle(d.axis, ang));
@@ -1072,20 +1113,21 @@ struct SE3QSampleOp {
   const uint32_t* guide;
   const float* loc;
   float shift_scale;
-  uint64_t seed, rng_offset, row_offset;
+  PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
+  uint64_t row_offset;
   __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
   __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
     int64_t ti = t[i];
     ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
     const float eps = __ldg(sqrt_1m_ac + ti), sc = __ldg(sqrt_ac + ti);
-    const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+    const NoiseDraw d = draw_axis_u(key, row_offset + (uint64_t)i);
     const float ang = table_row_angle(cdf, guide, ti, tab, d.u);
     const Quat qn = quat_axis_angle(d.axis, ang);
     const AxisAngleF ax = axis_angle_fast(a9[0]);
     o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, sc * ax.theta), qn));
     const float k = ang * rcp_approx(eps);
     o3[0] = Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z};
-    const Normal4 z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset | kShiftStream));
+    const Normal4 z = normal4_from_u4(philox4x32_10(key_shift, row_offset + (uint64_t)i));
     const float ns = eps * shift_scale;
     o3[1] = Vec3{fmaf(sc, a3[0].x, ns * z.a), fmaf(sc, a3[0].y, ns * z.b), fmaf(sc, a3[0].z, ns * z.c)};
     o3[2] = Vec3{z.a, z.b, z.c};
@@ -1120,7 +1162,8 @@ struct SE3PStepOp {
   const uint32_t* post_guide;
   const float* loc;
   float shift_scale;
-  uint64_t seed, rng_offset, row_offset;
+  PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
+  uint64_t row_offset;
   __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
   __device__ void setup(float* tab) const {
     if (post_cdf) stage_cdf(tab, kSharedT ? post_cdf + clamp_t(t[0]) * kCdf : nullptr, loc);
@@ -1152,10 +1195,10 @@ struct SE3PStepOp {
     m.y = fmaf(k_c1, fmaf(k_recip, st.y, -k_recipm1 * ps.y), k_c2 * st.y);
     m.z = fmaf(k_c1, fmaf(k_recip, st.z, -k_recipm1 * ps.z), k_c2 * st.z);
     if (post_cdf && ti != 0) {
-      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+      const NoiseDraw d = draw_axis_u(key, row_offset + (uint64_t)i);
       const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
       qm = qmul(qm, quat_axis_angle(d.axis, ang));
-      const Normal4 z = normal4_from_u4(philox4x32_10(seed, row_offset + (uint64_t)i, rng_offset | kShiftStream));
+      const Normal4 z = normal4_from_u4(philox4x32_10(key_shift, row_offset + (uint64_t)i));
       const float ns = k_sigma * shift_scale;
       m = Vec3{fmaf(ns, z.a, m.x), fmaf(ns, z.b, m.y), fmaf(ns, z.c, m.z)};
     }
@@ -1393,7 +1436,7 @@ static int launch_sample(const float* cdf, const uint32_t* guide, const float* l
   SampleOp<kShared> op;
   op.out9[0] = R; op.out3[0] = axis3;
   op.cdf = cdf; op.guide = guide; op.loc = loc; op.row_idx = row_idx; op.shared_row = row; op.rows = rows; op.u_in = u; op.axes_in = axes3;
-  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset; op.mean = mean; op.mean_stride = mean_stride; op.angle_out = angle;
+  op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset; op.mean = mean; op.mean_stride = mean_stride; op.angle_out = angle;
   return launch_rowwise(op, n, stream, "so3d_igso3_sample_f32");
 }
 
@@ -1405,7 +1448,7 @@ static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_
   op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
   if (kExtra) { op.out9[kExtra ? 1 : 0] = noise; op.out3[kExtra ? 1 : 0] = score3; }
   op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
-  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
   return launch_rowwise(op, n, stream, "so3d_q_sample_f32");
 }
 
@@ -1467,7 +1510,7 @@ int so3d_bingham_sample_f32(const float* scale_tril16, const float* z4, uint64_t
   SO3D_REQUIRE(!q4 || aligned16(q4), "so3d_bingham_sample_f32: q4 must be 16-byte aligned");
   BinghamOp op;
   op.out9[0] = R; op.tril = scale_tril16; op.z_in = z4; op.z_vec = aligned16(z4); op.q_out = q4;
-  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
   return launch_rowwise(op, n, stream, "so3d_bingham_sample_f32");
 }
 
@@ -1509,7 +1552,7 @@ static int launch_se3_p_step(const float* rot_t, const float* shift_t, const flo
   op.in9[0] = rot_t; op.in3[0] = pred_rot3; op.in3[1] = shift_t; op.in3[2] = pred_shift3; op.out9[0] = rot_out; op.out3[0] = shift_out;
   op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.sigma = sigma; op.T = T;
   op.post_cdf = post_cdf; op.post_guide = post_guide; op.loc = loc; op.shift_scale = shift_scale;
-  op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
   return launch_rowwise(op, n, stream, "so3d_se3_p_sample_f32");
 }
 
@@ -1527,7 +1570,7 @@ int so3d_se3_q_sample_f32(const float* rot0, const float* shift0, const int64_t*
   SE3QSampleOp op;
   op.in9[0] = rot0; op.in3[0] = shift0; op.out9[0] = rot_t; op.out3[0] = target_rot3; op.out3[1] = shift_t; op.out3[2] = target_shift3;
   op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
-  op.shift_scale = shift_scale; op.seed = seed; op.rng_offset = rng_offset; op.row_offset = row_offset;
+  op.shift_scale = shift_scale; op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
   return launch_rowwise(op, n, stream, "so3d_se3_q_sample_f32");
 }
 

@@ -989,6 +989,41 @@ SO3D_HD U4 philox4x32_10(uint64_t seed, uint64_t row, uint64_t offset) {
   return c;
 }
 
+// The same generator with everything that depends only on (seed, offset) -- the ten round keys and the half of
+// round 0 that multiplies the offset -- computed once on the host and passed by value in the kernel parameters
+// (constant-bank operands): bit-identical to philox4x32_10(seed, row, offset), ~22 issue slots fewer per warp and
+// tile than leaving the key schedule to the uniform datapath inside the tile loop.
+struct PhiloxKey {
+  uint32_t k0[10], k1[10];  // k0[0] already xor-ed with mulhi(0xCD9E8D57, offset_lo); k1[0] with offset_hi
+  uint32_t lo1;             // 0xCD9E8D57 * offset_lo
+};
+SO3D_HD PhiloxKey make_philox_key(uint64_t seed, uint64_t offset) {
+  PhiloxKey k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    k.k0[i] = a;
+    k.k1[i] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  const uint32_t ol = (uint32_t)offset, oh = (uint32_t)(offset >> 32);
+  k.k0[0] ^= (uint32_t)(((uint64_t)0xCD9E8D57u * (uint64_t)ol) >> 32);
+  k.k1[0] ^= oh;
+  k.lo1 = 0xCD9E8D57u * ol;
+  return k;
+}
+SO3D_HD U4 philox4x32_10(const PhiloxKey& k, uint64_t row) {
+  const uint32_t rl = (uint32_t)row, rh = (uint32_t)(row >> 32);
+  U4 c{k.k0[0] ^ rh, k.lo1, mulhi32(0xD2511F53u, rl) ^ k.k1[0], 0xD2511F53u * rl};
+#pragma unroll
+  for (int i = 1; i < 10; ++i) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k.k0[i], lo1, hi0 ^ c.w ^ k.k1[i], lo0};
+  }
+  return c;
+}
+
 // 24-bit uniform in [0, 1), the same lattice torch.rand(float32) uses.
 SO3D_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
@@ -1023,12 +1058,13 @@ struct NoiseDraw {
   Vec3 axis;
   float u;
 };
-SO3D_HD NoiseDraw draw_axis_u(uint64_t seed, uint64_t row, uint64_t offset) {
-  const U4 r = philox4x32_10(seed, row, offset);
+SO3D_HD NoiseDraw draw_from_block(const U4& r) {
   NoiseDraw d;
   d.axis = sphere_from_uniforms(u01(r.x), u01(r.y));
   d.u = u01(r.z);
   return d;
 }
+SO3D_HD NoiseDraw draw_axis_u(uint64_t seed, uint64_t row, uint64_t offset) { return draw_from_block(philox4x32_10(seed, row, offset)); }
+SO3D_HD NoiseDraw draw_axis_u(const PhiloxKey& k, uint64_t row) { return draw_from_block(philox4x32_10(k, row)); }
 
 }  // namespace so3d

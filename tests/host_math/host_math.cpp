@@ -82,6 +82,11 @@ void hm_angle_from_record(const float* trap, const float* loc, const float* u, f
 void hm_philox(unsigned long long seed, unsigned long long row0, unsigned long long offset, unsigned* out, long n) {
   for (long i = 0; i < n; ++i) { U4 r = philox4x32_10(seed, row0 + i, offset); out[4*i]=r.x; out[4*i+1]=r.y; out[4*i+2]=r.z; out[4*i+3]=r.w; }
 }
+// the launcher-side key schedule (what the kernels use) must reproduce the plain generator bit for bit
+void hm_philox_keyed(unsigned long long seed, unsigned long long row0, unsigned long long offset, unsigned* out, long n) {
+  const PhiloxKey k = make_philox_key(seed, offset);
+  for (long i = 0; i < n; ++i) { U4 r = philox4x32_10(k, row0 + i); out[4*i]=r.x; out[4*i+1]=r.y; out[4*i+2]=r.z; out[4*i+3]=r.w; }
+}
 void hm_draw(unsigned long long seed, unsigned long long row0, unsigned long long offset, float* axis, float* u, long n) {
   for (long i = 0; i < n; ++i) { NoiseDraw d = draw_axis_u(seed, row0 + i, offset); axis[3*i]=d.axis.x; axis[3*i+1]=d.axis.y; axis[3*i+2]=d.axis.z; u[i]=d.u; }
 }

@@ -280,6 +280,13 @@ def test_philox_known_answer_and_draws(hm):
     off = (0x13198a2e | (0x03707344 << 32))
     hm.hm_philox(ctypes.c_ulonglong(seed), ctypes.c_ulonglong(row), ctypes.c_ulonglong(off), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.c_long(1))
     assert [hex(x) for x in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    # precomputed key schedule == plain generator, including 64-bit rows / offsets and the SE(3) stream bit
+    rng = np.random.default_rng(9)
+    for seed, row0, off in [(0, 0, 0), (1234, 2**32 - 3, 7), (2**64 - 1, 2**40 + 5, 2**63 | 12345), (int(rng.integers(0, 2**62)), int(rng.integers(0, 2**62)), int(rng.integers(0, 2**62)))]:
+        a = np.empty(4 * 64, np.uint32); b = np.empty(4 * 64, np.uint32)
+        hm.hm_philox(ctypes.c_ulonglong(seed), ctypes.c_ulonglong(row0), ctypes.c_ulonglong(off), a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.c_long(64))
+        hm.hm_philox_keyed(ctypes.c_ulonglong(seed), ctypes.c_ulonglong(row0), ctypes.c_ulonglong(off), b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.c_long(64))
+        assert np.array_equal(a, b)
     n = 200000
     axis = np.empty((n, 3), np.float32); u = np.empty(n, np.float32)
     hm.hm_draw(ctypes.c_ulonglong(1234), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), fp(axis), fp(u), ctypes.c_long(n))
