@@ -127,7 +127,9 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
-// x * sigmoid(x) (torch.nn.SiLU): one MUFU.EX2 and one MUFU.RCP
+// x * sigmoid(x) (torch.nn.SiLU): one MUFU.EX2 and one MUFU.RCP.  (Measured: sharing one MUFU.RCP between two
+// activations -- r = 1/(a0 a1), 1/a0 = r a1 -- is slower, 3.97 vs 3.37 ms per 2^24-particle step: the extra live values
+// spill at the 96-register cap of this 18-warp CTA, profiles/r02a_probe_denoiser.log.)
 __device__ __forceinline__ float silu(float x) {
   const float e = fast_ex2(-1.4426950408889634f * x);
   return x * rcp_approx(1.0f + e);
