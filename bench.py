@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU runs: leave the ranks' CPU affinity alone (A/B of the e2e leg)")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 20, help="rows per chunk of the host-buffer pipeline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -251,6 +252,10 @@ def main():
     dist_on = world > 1
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = None
+    if dist_on and not args.no_numa_bind:
+        # one process per GPU: keep it (and the pinned staging buffers it is about to allocate) on the GPU's NUMA node
+        numa = dx.parallel.bind_to_gpu_numa_node(local)
     if dist_on:
         torch.distributed.init_process_group("nccl", device_id=device)
     dx._lib.load()
@@ -301,7 +306,7 @@ def main():
         torch.cuda.synchronize()
         assert torch.equal(hlogp[:4096], logp[:4096].cpu()) and torch.equal(hscore[-4096:], score[-4096:].cpu())
         e2e = {"value": world * n_e2e * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_e2e * 40, "d2h_bytes_per_step": n_e2e * 16,
-               "ms_per_step": ms_e2e / e2e_steps, "api": "ops.HostScorePipeline.run (3-stream chunked overlap)", "chunk_rows": args.e2e_chunk,
+               "ms_per_step": ms_e2e / e2e_steps, "api": "ops.HostScorePipeline.run (3-stream chunked overlap)", "chunk_rows": args.e2e_chunk, "numa_bind_rank0": numa,
                "pcie_gbs": {"h2d": n_e2e * 40 / (ms_e2e / e2e_steps * 1e-3) / 1e9, "d2h": n_e2e * 16 / (ms_e2e / e2e_steps * 1e-3) / 1e9}}
 
     # ---- secondary kernels ----------------------------------------------------------------------

@@ -12,5 +12,6 @@ from .distributions import IsotropicGaussianSO3, IGSO3xR3, Bingham  # noqa: F401
 from .diffusion import SO3Diffusion, ProjectedSO3Diffusion, SE3Diffusion, ProjectedSE3Diffusion  # noqa: F401
 from .util import AffineT, AffineGrad  # noqa: F401
 from .denoiser import RotPredict, SinusoidalPosEmb  # noqa: F401
+from . import parallel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -144,3 +144,31 @@ def test_shard_bounds_properties():
             assert prev == n
     with pytest.raises(ValueError):
         P.shard_bounds(10, 2, 2)
+
+
+def test_bind_to_gpu_numa_node_with_fake_sysfs(tmp_path):
+    """Host logic of the NUMA binding on a fabricated sysfs tree: parses cpulist, intersects with the allowed CPUs,
+    sets the affinity, and degrades to {"bound": False} (never raises) when the tree is missing or the node is -1."""
+    import os
+
+    from diffusion_extensions_b200 import parallel as P
+
+    assert P._parse_cpulist("0-2,5,7-8\n") == {0, 1, 2, 5, 7, 8}
+    before = os.sched_getaffinity(0)
+    try:
+        one = min(before)
+        bdf = "0000:1b:00.0"
+        (tmp_path / "bus" / "pci" / "devices" / bdf).mkdir(parents=True)
+        (tmp_path / "bus" / "pci" / "devices" / bdf / "numa_node").write_text("1\n")
+        (tmp_path / "devices" / "system" / "node" / "node1").mkdir(parents=True)
+        (tmp_path / "devices" / "system" / "node" / "node1" / "cpulist").write_text(f"{one}\n")
+        info = P.bind_to_gpu_numa_node(0, sysfs=str(tmp_path), bdf=bdf)
+        assert info == {"bound": True, "node": 1, "cpus": 1, "pci": bdf}
+        assert os.sched_getaffinity(0) == {one}
+        os.sched_setaffinity(0, before)
+        (tmp_path / "bus" / "pci" / "devices" / bdf / "numa_node").write_text("-1\n")
+        assert P.bind_to_gpu_numa_node(0, sysfs=str(tmp_path), bdf=bdf)["bound"] is False
+        assert P.bind_to_gpu_numa_node(0, sysfs=str(tmp_path / "nowhere"), bdf=bdf)["bound"] is False
+        assert os.sched_getaffinity(0) == before
+    finally:
+        os.sched_setaffinity(0, before)
