@@ -195,8 +195,6 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     mbar_init(&bars[1], 1);
     fence_barrier_init();
   }
-  op.setup(s_tab);
-  __syncthreads();
 
   // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
   // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is
@@ -233,10 +231,14 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
 #pragma unroll
     for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
   };
+  // the first two tiles are requested BEFORE the op stages its tables, so their DRAM latency overlaps the setup
+  // (thread 0 initialised the barriers itself; the other threads first touch them after the __syncthreads below)
   if (tid == 0 && use_tma) {
     if (tile_full(0)) issue_load(0, tile_row0(0));
     if (tile_full(1)) issue_load(1, tile_row0(1));
   }
+  op.setup(s_tab);
+  __syncthreads();
 
   // software pipeline registers (empty structs for ops without prefetch hooks)
   constexpr bool kPre = HasPre<Op>::value;
@@ -379,8 +381,6 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
     released[1] = 0;
     fence_barrier_init();
   }
-  op.setup(s_tab);
-  __syncthreads();
 
   // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
   // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is
@@ -400,10 +400,12 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
 #pragma unroll
     for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kTile * 9 + a * kTile * 3, op.in3[a] + row0 * 3, kTile * 3 * sizeof(float), &bars[st]);
   };
-  if (tid == 0 && use_tma) {
+  if (tid == 0 && use_tma) {  // before the op's setup: the first tiles' DRAM latency overlaps the table staging
     if (my_full > 0) issue_load(0, tile_row0(0));
     if (my_full > 1) issue_load(1, tile_row0(1));
   }
+  op.setup(s_tab);
+  __syncthreads();
 
   // software pipeline registers (empty structs for ops without prefetch hooks)
   constexpr bool kPre = HasPre<Op>::value;
