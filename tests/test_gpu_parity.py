@@ -626,6 +626,42 @@ def test_shard_invariance_of_random_draws(dx, cuda_device):
         assert torch.equal(part, fullp[lo:hi])
 
 
+def test_warp_schedule_ragged_and_unaligned_pieces(dx, cuda_device):
+    """The ops on the warp-autonomous engine schedule (per-row table look-ups: forward noising, per-row-t reverse step,
+    per-row sampler, SE(3) noising) on pieces of every awkward size and alignment -- 1 row, a partial warp, one row past
+    a warp / a tile, pieces starting 4-byte-aligned only (bulk copies impossible: per-warp ld/st fallback) -- must equal
+    the corresponding rows of one big aligned launch bit for bit (global-row Philox counters)."""
+    n = 3000
+    p = dx.SE3Diffusion(None).to(cuda_device)
+    x0 = dev(rand_rots(n, 61)[0], cuda_device)
+    sh = torch.randn(n, 3, device=cuda_device)
+    pred = torch.randn(n, 3, device=cuda_device) * 0.3
+    t = torch.randint(0, 1000, (n,), device=cuda_device)
+    fwd, post, _ = p.tables()
+    fg, pg = p.guides()
+    sched = (p.sqrt_recip_alphas_cumprod, p.sqrt_recipm1_alphas_cumprod, p.posterior_mean_coef1, p.posterior_mean_coef2)
+    qargs = (p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd)
+    full_q = dx.ops.q_sample_fused(x0, t, *qargs, seed=5, rng_offset=3, guide=fg, want_noise=True, want_score=True)
+    full_p = dx.ops.p_sample_fused(x0, pred, t, *sched, post_cdf=post, seed=6, rng_offset=4, post_guide=pg)
+    full_s = dx.ops.igso3_sample(post, (n,), row_idx=t, seed=7, rng_offset=5, guide=pg)
+    full_e = dx.ops.se3_q_sample_fused(x0, sh, t, *qargs, 75.0, seed=8, rng_offset=6, guide=fg)
+    pieces = [(0, 1), (1, 32), (3, 36), (64, 64 + 255), (401, 401 + 257), (1001, 1001 + 513), (2000, 3000), (2999, 3000)]
+    for lo, hi in pieces:
+        q = dx.ops.q_sample_fused(x0[lo:hi], t[lo:hi], *qargs, seed=5, rng_offset=3, row_offset=lo, guide=fg, want_noise=True, want_score=True)
+        for k in ("x_t", "target", "noise", "score"):
+            assert torch.equal(q[k], full_q[k][lo:hi]), (k, lo, hi)
+        pp = dx.ops.p_sample_fused(x0[lo:hi], pred[lo:hi], t[lo:hi], *sched, post_cdf=post, seed=6, rng_offset=4, row_offset=lo, post_guide=pg)
+        assert torch.equal(pp, full_p[lo:hi]), ("p_sample", lo, hi)
+        ss = dx.ops.igso3_sample(post, (hi - lo,), row_idx=t[lo:hi], seed=7, rng_offset=5, row_offset=lo, guide=pg)
+        assert torch.equal(ss, full_s[lo:hi]), ("sample", lo, hi)
+        e = dx.ops.se3_q_sample_fused(x0[lo:hi], sh[lo:hi], t[lo:hi], *qargs, 75.0, seed=8, rng_offset=6, row_offset=lo, guide=fg)
+        for k in ("rot", "shift", "target_rot", "target_shift"):
+            assert torch.equal(e[k], full_e[k][lo:hi]), (k, lo, hi)
+    # and the rows are what they should be: x_t = so3_scale(x0, sqrt_ac[t]) @ noise (diffusion.py:344-346)
+    ref = O.so3_scale(host(x0), host(p.sqrt_alphas_cumprod)[t.cpu().numpy()]) @ host(full_q["noise"]).astype(np.float64)
+    assert np.max(np.abs(host(full_q["x_t"]) - ref)) < 5e-6
+
+
 def test_guide_table_lookup_is_exact(dx, cuda_device):
     """The guided inverse-CDF search returns exactly the index of the full search: sampling with and
     without the guide table gives bit-identical rotations, for per-row table rows and for the shared row."""
