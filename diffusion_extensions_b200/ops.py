@@ -275,7 +275,12 @@ class HostScorePipeline:
     With 40 B in and 16 B out per evaluation the PCIe link (not the kernel) bounds the end-to-end rate, so the
     pipeline runs at the speed of the slowest leg instead of their sum.  Device staging buffers are a ring of
     `depth` chunks allocated once; nothing synchronises with the host until `run` returns (it waits for the
-    last D2H copy, because the caller is about to read host memory)."""
+    last D2H copy, because the caller is about to read host memory).
+
+    Streaming several batches: `run(..., wait=False, join=False)` neither joins the pipeline's streams to the current
+    stream at entry nor at exit, so the H2D copies of the next batch start while the previous batch's last kernels and
+    D2H copies drain (the staging slots are guarded by events that persist across calls); call `finish()` once at the
+    end to make the current stream wait for everything issued so far."""
 
     def __init__(self, device, chunk_rows=1 << 20, depth=3, per_row_eps=True):
         self.device = torch.device(device)
@@ -290,8 +295,17 @@ class HostScorePipeline:
         self.ev_k = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         self.launches = 0
+        self.issued = 0  # chunks issued so far over all calls: slot b has been used before iff issued > b
 
-    def run(self, hR, heps, h_logp, h_score, mode="series", L=2000, wait=True):
+    def finish(self, wait=False):
+        """Make the current stream wait for every chunk issued so far (and optionally the host too)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_k)
+        if wait:
+            self.s_out.synchronize()
+
+    def run(self, hR, heps, h_logp, h_score, mode="series", L=2000, wait=True, join=True):
         """hR (n,3,3), heps (n,) or a scalar tensor/float, h_logp (n,), h_score (n,3): pinned host float32 tensors."""
         for name, t in (("rotations", hR), ("logp", h_logp), ("score", h_score)):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
@@ -303,13 +317,18 @@ class HostScorePipeline:
         eps_shared = None if per_row else torch.as_tensor(heps, dtype=torch.float32).reshape(1).to(self.device)
         m = _mode(mode)
         cur = torch.cuda.current_stream(self.device)
-        for st in (self.s_in, self.s_k, self.s_out):
-            st.wait_stream(cur)
-        for c, lo in enumerate(range(0, n, self.chunk)):
+        if join:
+            for st in (self.s_in, self.s_k, self.s_out):
+                st.wait_stream(cur)
+        if eps_shared is not None:
+            self.s_k.wait_stream(cur)                       # the shared eps was uploaded on the current stream
+        for lo in range(0, n, self.chunk):
             hi = min(n, lo + self.chunk)
-            rows, b = hi - lo, c % self.depth
+            rows, b = hi - lo, self.issued % self.depth
+            used = self.issued >= self.depth                # the slot carries a chunk of this or an earlier call
+            self.issued += 1
             with torch.cuda.stream(self.s_in):
-                if c >= self.depth:
+                if used:
                     self.s_in.wait_event(self.ev_k[b])      # the kernel that read this staging slot is done
                 self.dR[b][:rows].copy_(hR[lo:hi], non_blocking=True)
                 if per_row:
@@ -317,7 +336,7 @@ class HostScorePipeline:
                 self.ev_in[b].record(self.s_in)
             with torch.cuda.stream(self.s_k):
                 self.s_k.wait_event(self.ev_in[b])
-                if c >= self.depth:
+                if used:
                     self.s_k.wait_event(self.ev_out[b])     # the D2H copy that read this result slot is done
                 e = self.deps[b] if per_row else eps_shared
                 call("so3d_igso3_logp_score_f32", ptr(self.dR[b]), ptr(e), 1 if per_row else 0, ptr(self.dlogp[b]), ptr(self.dscore[b]), None,
@@ -329,10 +348,8 @@ class HostScorePipeline:
                 h_logp[lo:hi].copy_(self.dlogp[b][:rows], non_blocking=True)
                 h_score[lo:hi].copy_(self.dscore[b][:rows], non_blocking=True)
                 self.ev_out[b].record(self.s_out)
-        cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_k)
-        if wait:
-            self.s_out.synchronize()
+        if join or wait:
+            self.finish(wait=wait)
         return h_logp, h_score
 
 

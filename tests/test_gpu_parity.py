@@ -709,3 +709,15 @@ def test_host_score_pipeline(dx, cuda_device):
             assert torch.equal(hl, logp[:, 0].cpu()) and torch.equal(hs, score.cpu())
         l2, s2 = d.log_prob_and_score_host(hR, chunk_rows=chunk)
         assert torch.equal(l2, logp.cpu()) and torch.equal(s2, score.cpu())
+        # streamed batches: two different batches back to back without joining the streams in between (the second
+        # batch's uploads overlap the first one's drain; slots are guarded by events that persist across calls)
+        R2, eps2 = eset(n, 62)
+        hR2, heps2 = torch.from_numpy(R2).pin_memory(), torch.from_numpy(eps2).pin_memory()
+        hl2, hs2 = torch.empty(n).pin_memory(), torch.empty(n, 3).pin_memory()
+        logp2, score2 = dx.IsotropicGaussianSO3(dev(eps2, cuda_device), mode="auto").log_prob_and_score(dev(R2, cuda_device))
+        hl.zero_(); hs.zero_()
+        pipe.run(hR, heps, hl, hs, mode="auto", wait=False, join=False)
+        pipe.run(hR2, heps2, hl2, hs2, mode="auto", wait=False, join=False)
+        pipe.finish(wait=True)
+        assert torch.equal(hl, logp[:, 0].cpu()) and torch.equal(hs, score.cpu())
+        assert torch.equal(hl2, logp2[:, 0].cpu()) and torch.equal(hs2, score2.cpu())
