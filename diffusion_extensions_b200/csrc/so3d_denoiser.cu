@@ -170,6 +170,7 @@ struct DenoiseArgs {
   const float* post_cdf;
   const float* loc;
   uint64_t seed, rng_offset, row_offset;
+  const uint64_t* seed_dev;  // non-null: the seed lives in device memory (CUDA-graph replays draw fresh noise)
   float* out;
   float* pred_out;
   int64_t n;
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
         }
       } else if (noisy && live) {
         // the step's noise rotation does not depend on the network: drawn by the second thread of the particle
-        const NoiseDraw d = draw_axis_u(a.seed, a.row_offset + (uint64_t)i, a.rng_offset);
+        const uint64_t sd = a.seed_dev ? __ldg(reinterpret_cast<const unsigned long long*>(a.seed_dev)) : a.seed;
+        const NoiseDraw d = draw_axis_u(sd, a.row_offset + (uint64_t)i, a.rng_offset);
         const Quat qn = quat_axis_angle(d.axis, shared_row_angle(s_tab, d.u));
         s_noise[(g * 2 + par) * kM + r] = make_float4(qn.w, qn.x, qn.y, qn.z);
       }
@@ -471,10 +473,10 @@ int so3d_rotpredict_pack_f32(const float* w1, const float* b1, const float* w2, 
   return so3d_host::check_launch("so3d_rotpredict_pack_f32");
 }
 
-int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const float* c1_table, const int64_t* t, const float* recip,
-                                 const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
-                                 const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out,
-                                 float* pred_out, int64_t n, void* stream) {
+static int rotpredict_p_sample_impl(const float* x_t, const float* blob, const float* c1_table, const int64_t* t, const float* recip,
+                                    const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
+                                    const float* loc, uint64_t seed, const uint64_t* seed_dev, uint64_t rng_offset, uint64_t row_offset,
+                                    float* out, float* pred_out, int64_t n, void* stream) {
   SO3D_REQUIRE(n >= 0, "negative n");
   if (n == 0) return 0;
   SO3D_REQUIRE(x_t && blob && c1_table && t && recip && recipm1 && coef1 && coef2, "so3d_rotpredict_p_sample_f32: null pointer");
@@ -490,13 +492,30 @@ int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const floa
   }
   DenoiseArgs a;
   a.x_t = x_t; a.blob = blob; a.c1_table = c1_table; a.t = t; a.recip = recip; a.recipm1 = recipm1; a.coef1 = coef1; a.coef2 = coef2;
-  a.T = T; a.post_cdf = post_cdf; a.loc = loc; a.seed = seed; a.rng_offset = rng_offset; a.row_offset = row_offset;
+  a.T = T; a.post_cdf = post_cdf; a.loc = loc; a.seed = seed; a.seed_dev = seed_dev; a.rng_offset = rng_offset; a.row_offset = row_offset;
   a.out = out; a.pred_out = pred_out; a.n = n;
   const int64_t pairs = ((n + kM - 1) / kM + 1) / 2;
   const int sms = so3d_host::sm_count();
   const int grid = (int)(pairs < sms ? pairs : sms);
   rotpredict_p_sample_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
   return so3d_host::check_launch("so3d_rotpredict_p_sample_f32");
+}
+
+int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const float* c1_table, const int64_t* t, const float* recip,
+                                 const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
+                                 const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out,
+                                 float* pred_out, int64_t n, void* stream) {
+  return rotpredict_p_sample_impl(x_t, blob, c1_table, t, recip, recipm1, coef1, coef2, T, post_cdf, loc, seed, nullptr, rng_offset, row_offset,
+                                  out, pred_out, n, stream);
+}
+
+int so3d_rotpredict_p_sample_dseed_f32(const float* x_t, const float* blob, const float* c1_table, const int64_t* t, const float* recip,
+                                       const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
+                                       const float* loc, const uint64_t* seed_dev, uint64_t rng_offset, uint64_t row_offset, float* out,
+                                       float* pred_out, int64_t n, void* stream) {
+  SO3D_REQUIRE(seed_dev, "so3d_rotpredict_p_sample_dseed_f32: null seed pointer");
+  return rotpredict_p_sample_impl(x_t, blob, c1_table, t, recip, recipm1, coef1, coef2, T, post_cdf, loc, 0, seed_dev, rng_offset, row_offset,
+                                  out, pred_out, n, stream);
 }
 
 }  // extern "C"

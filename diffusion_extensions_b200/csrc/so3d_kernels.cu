@@ -1026,7 +1026,9 @@ struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
 
 // Reverse step.  kSharedT: the whole batch shares t (the reference's semantics, Q7): the posterior CDF row and
 // its guide live in shared memory; otherwise per-row t with table rows (and the optional guide) read through L2.
-template <bool kSharedT, bool kX0>
+// kDevSeed: the Philox seed is read from device memory (CUDA-graph replays with fresh noise, so3d_p_sample_dseed_f32);
+// a separate instantiation, so the by-value kernels' code is untouched.
+template <bool kSharedT, bool kX0, bool kDevSeed = false>
 struct PStepOp {
 #ifndef SO3D_PSS_OUTSTAGES
 #define SO3D_PSS_OUTSTAGES 2
@@ -1053,6 +1055,7 @@ struct PStepOp {
   const uint32_t* post_guide;
   const float* loc;
   uint64_t seed, rng_offset, row_offset;
+  const uint64_t* seed_dev;
   __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
   // shared t: the step's five scalars are staged once per CTA next to the CDF row (broadcast LDS per tile instead of a
   // dependent t -> schedule chain of global loads and 64-bit address math in every tile: -25 issue slots per warp-tile)
@@ -1065,6 +1068,11 @@ struct PStepOp {
       tab[kTabScal + 2] = recipm1[ti];
       tab[kTabScal + 3] = coef1[ti];
       tab[kTabScal + 4] = coef2[ti];
+      if (kDevSeed) {
+        const uint64_t sd = *seed_dev;
+        tab[kTabScal + 5] = __uint_as_float((uint32_t)sd);
+        tab[kTabScal + 6] = __uint_as_float((uint32_t)(sd >> 32));
+      }
     }
   }
   __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3*, const float* tab) const {
@@ -1082,7 +1090,10 @@ struct PStepOp {
     if (post_cdf && ti != 0) {                                                     // diffusion.py:320-326
       // (the launcher-side key schedule the other ops use measured 2 % slower here: ptxas then allocates 46 instead of
       // 63 registers and schedules with less overlap, profiles/r01w_probe_engine.jsonl)
-      const NoiseDraw d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+      const uint64_t sd = (kDevSeed && kSharedT)
+                              ? ((uint64_t)__float_as_uint(tab[kTabScal + 5]) | ((uint64_t)__float_as_uint(tab[kTabScal + 6]) << 32))
+                              : seed;
+      const NoiseDraw d = draw_axis_u(sd, row_offset + (uint64_t)i, rng_offset);
       const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
       qm = qmul(qm, quat_axis_angle(d.axis, ang));
     }
@@ -1454,12 +1465,13 @@ static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_
   return launch_rowwise(op, n, stream, "so3d_q_sample_f32");
 }
 
-template <bool kSharedT, bool kX0>
+template <bool kSharedT, bool kX0, bool kDevSeed = false>
 static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
                          const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint32_t* post_guide,
                          const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
-                         int64_t n, void* stream) {
-  PStepOp<kSharedT, kX0> op;
+                         int64_t n, void* stream, const uint64_t* seed_dev = nullptr) {
+  PStepOp<kSharedT, kX0, kDevSeed> op;
+  op.seed_dev = seed_dev;
   op.in9[0] = x_t; op.in3[0] = pred3; op.out9[0] = out;
   if (kX0) op.out9[kX0 ? 1 : 0] = x0_hat_out;
   op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.T = T;
@@ -1541,6 +1553,17 @@ int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, in
   if (t_stride == 0) return x0_hat_out ? SO3D_PSTEP(true, true) : SO3D_PSTEP(true, false);
   return x0_hat_out ? SO3D_PSTEP(false, true) : SO3D_PSTEP(false, false);
 #undef SO3D_PSTEP
+}
+
+int so3d_p_sample_dseed_f32(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
+                            const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const float* loc,
+                            const uint64_t* seed_dev, uint64_t rng_offset, uint64_t row_offset, float* out, int64_t n, void* stream) {
+  SO3D_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return 0;
+  SO3D_REQUIRE(x_t && pred3 && t && recip && recipm1 && coef1 && coef2 && out && post_cdf && loc && seed_dev, "so3d_p_sample_dseed_f32: null pointer");
+  SO3D_REQUIRE(T > 0, "so3d_p_sample_dseed_f32: T must be positive");
+  return launch_p_step<true, false, true>(x_t, pred3, t, recip, recipm1, coef1, coef2, T, post_cdf, nullptr, loc, 0, rng_offset, row_offset, out,
+                                          nullptr, n, stream, seed_dev);
 }
 
 }  // extern "C"

@@ -192,10 +192,69 @@ class SO3Diffusion(nn.Module):
                                   self.posterior_mean_coef1, self.posterior_mean_coef2, post_cdf=post, post_guide=self.guides()[1],
                                   row_offset=self.row_offset)
 
+    # ---- the whole reverse process as ONE CUDA graph ---------------------------------------------
+    def _p_sample_seeded(self, x, t, seed_buf, step):
+        """p_sample with the Philox seed in device memory (`seed_buf`, int64[1]) and rng_offset = step: capturable,
+        and a replay draws fresh noise once seed_buf has been rewritten."""
+        _, post, _ = self.tables()
+        fused = self._fused_denoiser(x, t)
+        if fused is not None:
+            blob, c1 = fused
+            return ops.rotpredict_p_sample_fused(x, blob, c1, t, *self._sched4(), post_cdf=post, seed=seed_buf, rng_offset=step,
+                                                 row_offset=self.row_offset)
+        return ops.p_sample_fused(x, self._denoise(x, t), t, *self._sched4(), post_cdf=post, seed=seed_buf, rng_offset=step,
+                                  row_offset=self.row_offset)
+
+    def _sched4(self):
+        return (self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.posterior_mean_coef1, self.posterior_mean_coef2)
+
+    def _seeded_steps(self, x, seed_buf, first=None):
+        _, _, t_range = self.tables()
+        steps = list(reversed(range(self.num_timesteps)))
+        for i in steps if first is None else steps[:first]:
+            x = self._p_sample_seeded(x, t_range[i:i + 1], seed_buf, i)
+        return x
+
+    def _p_sample_loop_graph(self, x):
+        """Capture the T launches of the loop once per (batch shape, denoiser, weights) and replay them: the loop is
+        launch-bound for the batch sizes the reference samples (bingham_test.py:25, 20 000 particles: ~10 us of GPU work
+        per step), and a replay costs one launch.  Noise differs between replays because the kernels read the seed
+        from `seed_buf` when they run (so3d_p_sample_dseed_f32 / so3d_rotpredict_p_sample_dseed_f32)."""
+        dev = x.device
+        fn = self.denoise_fn
+        probe = self._fused_denoiser(x, self.tables()[2][:1])          # (re)packs the weights if they changed
+        packed_key = fn._packed[0] if probe is not None else None
+        key = (tuple(x.shape), str(dev), id(fn), packed_key, self.row_offset, bool(self.fuse_denoiser), self.num_timesteps)
+        cache = self.__dict__.setdefault("_loop_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            seed_buf = torch.zeros(1, dtype=torch.int64, device=dev)
+            x_in = x.clone()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                               # warm-up off the capture: lazy init, allocator
+                self._seeded_steps(x_in, seed_buf, first=3)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                x_out = self._seeded_steps(x_in, seed_buf)
+            ent = (graph, x_in, seed_buf, x_out, probe)                 # probe keeps the packed weights alive
+            cache[key] = ent
+        graph, x_in, seed_buf, x_out, _ = ent
+        seed, off = ops.rng.next()
+        mixed = (seed + 0x9E3779B97F4A7C15 * (off + 1)) & 0xFFFFFFFFFFFFFFFF
+        seed_buf.fill_(mixed - (1 << 64) if mixed >= (1 << 63) else mixed)
+        x_in.copy_(x)
+        graph.replay()
+        return x_out.clone()
+
     @torch.no_grad()
-    def p_sample_loop(self, shape, init="igso3_1", progress=False):
+    def p_sample_loop(self, shape, init="igso3_1", progress=False, cuda_graph=False):
         """diffusion.py:328-337.  init='igso3_1' is what the reference does (IGSO3(eps=1) samples,
-        despite its comment); init='haar' starts from Haar-uniform rotations."""
+        despite its comment); init='haar' starts from Haar-uniform rotations.
+        cuda_graph=True replays the whole loop as one captured CUDA graph (same distribution, its own noise stream)."""
         device = self.betas.device
         shape = tuple(shape)
         if init == "igso3_1":
@@ -204,6 +263,8 @@ class SO3Diffusion(nn.Module):
             x = ops.quat_to_rmat(torch.randn(*shape, 4, device=device))
         else:
             raise ValueError("init must be 'igso3_1' or 'haar'")
+        if cuda_graph:
+            return self._p_sample_loop_graph(x.contiguous())
         _, _, t_range = self.tables()
         steps = reversed(range(0, self.num_timesteps))
         if progress:
@@ -250,9 +311,9 @@ class ProjectedSO3Diffusion(SO3Diffusion):
         return self.denoise_fn(self.projection(x), t_full)
 
     @torch.no_grad()
-    def p_sample_loop(self, shape, projection, init="haar", progress=False):
+    def p_sample_loop(self, shape, projection, init="haar", progress=False, cuda_graph=False):
         self.projection = projection
-        return super().p_sample_loop(shape, init=init, progress=progress)
+        return super().p_sample_loop(shape, init=init, progress=progress, cuda_graph=cuda_graph)
 
     def p_losses(self, x_start, t, noise=None):
         if noise is None:

@@ -562,6 +562,15 @@ def pair_kernel_sums(X, Y=None, kernel="gaussian", shard=0, nshards=1):
 # ---------------------------------------------------------------------------------------------
 # L2: fused diffusion steps
 # ---------------------------------------------------------------------------------------------
+def _seed_tensor(seed, dev):
+    """A device-resident seed (one int64 element, its 64 bits are the Philox key) or None for a by-value seed."""
+    if not isinstance(seed, torch.Tensor):
+        return None
+    if seed.device != dev or seed.dtype != torch.int64 or seed.numel() != 1 or not seed.is_contiguous():
+        raise ValueError("a device seed must be a contiguous int64 tensor with one element on the data's device")
+    return seed
+
+
 def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, row_offset=0,
                    want_target=True, want_noise=False, want_score=False, guide=None):
     """-> dict(x_t, target, noise, score) (absent entries are None)."""
@@ -619,10 +628,17 @@ def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, se
             raise ValueError("posterior cdf table must have one row per timestep")
         _check_guide(post_guide, T, "post_guide")
         _, _, trap_loc = cdf_grid(dev)
-        if seed is None or rng_offset is None:
+        if not isinstance(seed, torch.Tensor) and (seed is None or rng_offset is None):
             seed, rng_offset = rng.next()
     out = torch.empty_like(x_t)
     x0_hat = torch.empty_like(x_t) if want_x0_hat else None
+    seed_dev = _seed_tensor(seed, dev)
+    if seed_dev is not None:  # CUDA-graph replayable step: the seed is read on the device when the kernel runs
+        if post_cdf is None or t_stride != 0 or want_x0_hat or rng_offset is None:
+            raise ValueError("a device seed needs a shared step index, post_cdf, an explicit rng_offset and no x0_hat output")
+        call("so3d_p_sample_dseed_f32", ptr(x_t), ptr(pred), ptr(t), ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T, ptr(post_cdf),
+             ptr(trap_loc), ptr(seed_dev), int(rng_offset), int(row_offset), ptr(out), n, device=dev)
+        return out
     call("so3d_p_sample_f32", ptr(x_t), ptr(pred), ptr(t), t_stride, ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T,
          ptr(post_cdf), ptr(post_guide), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(x0_hat), n, device=dev)
     return (out, x0_hat) if want_x0_hat else out
@@ -679,12 +695,21 @@ def rotpredict_p_sample_fused(x_t, blob, c1_table, t, recip, recipm1, coef1, coe
         if post_cdf.numel() != T * CDF_POINTS:
             raise ValueError("posterior cdf table must have one row per timestep")
         _, _, trap_loc = cdf_grid(dev)
-        if seed is None or rng_offset is None:
+        if not isinstance(seed, torch.Tensor) and (seed is None or rng_offset is None):
             seed, rng_offset = rng.next()
     if not (want_out or want_pred):
         raise ValueError("nothing requested")
     out = torch.empty_like(x_t) if want_out else None
     pred = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_pred else None
+    seed_dev = _seed_tensor(seed, dev)
+    if seed_dev is not None:
+        if rng_offset is None:
+            raise ValueError("a device seed needs an explicit rng_offset")
+        call("so3d_rotpredict_p_sample_dseed_f32", ptr(x_t), ptr(blob), ptr(c1_table), ptr(t), ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2),
+             T, ptr(post_cdf), ptr(trap_loc), ptr(seed_dev), int(rng_offset), int(row_offset), ptr(out), ptr(pred), n, device=dev)
+        if want_out and want_pred:
+            return out, pred
+        return out if want_out else pred
     call("so3d_rotpredict_p_sample_f32", ptr(x_t), ptr(blob), ptr(c1_table), ptr(t), ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T,
          ptr(post_cdf), ptr(trap_loc), seed or 0, rng_offset or 0, int(row_offset), ptr(out), ptr(pred), n, device=dev)
     if want_out and want_pred:

@@ -147,6 +147,15 @@ int so3d_p_sample_f32(const float* x_t, const float* pred3, const int64_t* t, in
                       const uint32_t* post_guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
                       float* out, float* x0_hat_out, int64_t n, void* stream);
 
+/* The same step (shared t, noise on, no x0_hat) with the Philox SEED READ FROM DEVICE MEMORY at execution time:
+ * a captured CUDA graph of a whole sampling loop (diffusion.py:328-337, one launch per step with rng_offset = step)
+ * draws fresh noise on every replay once the caller has written a new seed to seed_dev.  Draws equal
+ * so3d_p_sample_f32's at seed = *seed_dev. */
+int so3d_p_sample_dseed_f32(const float* x_t, const float* pred3, const int64_t* t, const float* recip, const float* recipm1,
+                            const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const float* loc,
+                            const uint64_t* seed_dev, uint64_t rng_offset, uint64_t row_offset, float* out, int64_t n,
+                            void* stream);
+
 /* ---- RotPredict denoiser fused with the reverse step ------------------------------------ */
 #define SO3D_ROTPREDICT_D 65              /* so3_train.py:12 d_model */
 #define SO3D_ROTPREDICT_BLOB_FLOATS 39424 /* packed tf32 hi/lo weights in the tensor-core (UMMA) shared-memory layout */
@@ -168,6 +177,13 @@ int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const floa
                                  const float* recip, const float* recipm1, const float* coef1, const float* coef2, int64_t T,
                                  const float* post_cdf, const float* loc, uint64_t seed, uint64_t rng_offset,
                                  uint64_t row_offset, float* out, float* pred_out, int64_t n, void* stream);
+
+/* As above with the seed read from device memory (see so3d_p_sample_dseed_f32). */
+int so3d_rotpredict_p_sample_dseed_f32(const float* x_t, const float* blob, const float* c1_table, const int64_t* t,
+                                       const float* recip, const float* recipm1, const float* coef1, const float* coef2,
+                                       int64_t T, const float* post_cdf, const float* loc, const uint64_t* seed_dev,
+                                       uint64_t rng_offset, uint64_t row_offset, float* out, float* pred_out, int64_t n,
+                                       void* stream);
 
 /* ---- SE(3) arm: diffusion.py SE3Diffusion / distributions.py IGSO3xR3 --------------- */
 /* diffusion.py:498-516 (SE3Diffusion.q_sample + p_losses targets), fused.  Rotation half exactly as

@@ -214,6 +214,51 @@ def test_p_sample_loop_with_fused_denoiser(dx, cuda_device):
     assert (torch.linalg.det(a) - 1).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+def test_p_sample_loop_as_cuda_graph(dx, cuda_device, fuse):
+    """p_sample_loop(cuda_graph=True) replays the whole reverse process as one captured graph whose kernels read the
+    Philox seed from device memory: (1) equal, bit for bit, to the eager loop run with that seed by value, for the fused
+    tensor-core denoiser and for the stock-PyTorch denoiser route; (2) a replay draws fresh noise; (3) a weight update
+    re-captures."""
+    torch.manual_seed(3)
+    T, n = 40, 700
+    net = dx.RotPredict().to(cuda_device)
+    proc = dx.SO3Diffusion(net, timesteps=T).to(cuda_device)
+    proc.fuse_denoiser = fuse
+    sched = (proc.sqrt_recip_alphas_cumprod, proc.sqrt_recipm1_alphas_cumprod, proc.posterior_mean_coef1, proc.posterior_mean_coef2)
+
+    def eager_with_seed(seed_start):
+        dx.ops.manual_seed(seed_start)
+        x = dx.IsotropicGaussianSO3(torch.ones([], device=cuda_device)).sample((n,), row_offset=0)   # the loop's init draw
+        seed, off = dx.ops.rng.next()                                                                # the graph's seed draw
+        mixed = (seed + 0x9E3779B97F4A7C15 * (off + 1)) & 0xFFFFFFFFFFFFFFFF
+        _, post, t_range = proc.tables()
+        with torch.no_grad():
+            for i in reversed(range(T)):
+                t = t_range[i:i + 1]
+                if fuse:
+                    blob, c1 = net.packed(T)
+                    x = dx.ops.rotpredict_p_sample_fused(x, blob, c1, t, *sched, post_cdf=post, seed=mixed, rng_offset=i)
+                else:
+                    x = dx.ops.p_sample_fused(x, net(x, t.expand(n)), t, *sched, post_cdf=post, seed=mixed, rng_offset=i)
+        return x
+
+    dx.ops.manual_seed(31)
+    a = proc.p_sample_loop((n,), cuda_graph=True)
+    assert torch.equal(a, eager_with_seed(31))
+    dx.ops.manual_seed(31)
+    a2 = proc.p_sample_loop((n,), cuda_graph=True)          # replay of the cached graph, same seed
+    b = proc.p_sample_loop((n,), cuda_graph=True)           # replay, next seed: fresh noise
+    assert torch.equal(a, a2) and not torch.equal(a, b)
+    assert len(proc._loop_graphs) == 1
+    assert (b.transpose(-1, -2) @ b - torch.eye(3, device=cuda_device)).abs().max().item() < 5e-6
+    with torch.no_grad():
+        net.net[0].weight.mul_(1.05)                         # a weight update: the fused route must re-pack and re-capture
+    dx.ops.manual_seed(32)
+    c = proc.p_sample_loop((n,), cuda_graph=True)
+    assert torch.equal(c, eager_with_seed(32))
+
+
 def test_errors(dx, cuda_device):
     net = dx.RotPredict().to(cuda_device)
     proc = dx.SO3Diffusion(net).to(cuda_device)
