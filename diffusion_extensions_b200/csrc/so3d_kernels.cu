@@ -941,7 +941,10 @@ struct BinghamOp {
 // ------------------------------------------------------------------------------------------------
 // eps = sqrt_1m_ac[t], noise ~ IGSO3(eps) from cdf row t, x_t = so3_scale(x0, sqrt_ac[t]) @ noise,
 // target = vee(log noise)/eps = angle axis / eps (the noise is built from (axis, angle), so its log is known).
-template <bool kExtra>  // kExtra: the optional noise / score outputs are compiled in (more shared memory per stage)
+// kExtra: the optional noise / score outputs are compiled in (more shared memory per stage).  kDevSeed: the Philox seed
+// is read from device memory when the kernel runs (so3d_q_sample_dseed_f32: a captured training step draws fresh noise
+// on every replay); a separate instantiation, the by-value kernel's code is untouched.
+template <bool kExtra, bool kDevSeed = false>
 struct QSampleOp {
   // per-row table rows are dependent L2 accesses: latency-bound, so favour resident CTAs over output double-buffering
 #ifndef SO3D_QS_OUTSTAGES
@@ -963,6 +966,8 @@ struct QSampleOp {
   const float* loc;
   PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
   uint64_t row_offset;
+  const uint64_t* seed_dev;  // kDevSeed only
+  uint64_t rng_offset;       // kDevSeed only
   __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
   // software pipeline: t two tiles ahead; the draw (a pure function of the global row index), the schedule
   // scalars and the guide record one tile ahead -- the row itself then touches no dependent global memory
@@ -983,7 +988,10 @@ struct QSampleOp {
     p.ti = (int)ti;
     p.eps = __ldg(sqrt_1m_ac + ti);
     p.sc = __ldg(sqrt_ac + ti);
-    p.d = draw_axis_u(key, row_offset + (uint64_t)i);
+    if (kDevSeed)
+      p.d = draw_axis_u((uint64_t)__ldg(reinterpret_cast<const unsigned long long*>(seed_dev)), row_offset + (uint64_t)i, rng_offset);
+    else
+      p.d = draw_axis_u(key, row_offset + (uint64_t)i);
     p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuide + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
     return p;
   }
@@ -1453,11 +1461,12 @@ static int launch_sample(const float* cdf, const uint32_t* guide, const float* l
   return launch_rowwise(op, n, stream, "so3d_igso3_sample_f32");
 }
 
-template <bool kExtra>
+template <bool kExtra, bool kDevSeed = false>
 static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T, const float* cdf,
                            const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
-                           float* target3, float* noise, float* score3, int64_t n, void* stream) {
-  QSampleOp<kExtra> op;
+                           float* target3, float* noise, float* score3, int64_t n, void* stream, const uint64_t* seed_dev = nullptr) {
+  QSampleOp<kExtra, kDevSeed> op;
+  op.seed_dev = seed_dev; op.rng_offset = rng_offset;
   op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
   if (kExtra) { op.out9[kExtra ? 1 : 0] = noise; op.out3[kExtra ? 1 : 0] = score3; }
   op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
@@ -1505,6 +1514,17 @@ int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, c
   if (noise || score3)
     return launch_q_sample<true>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, noise, score3, n, stream);
   return launch_q_sample<false>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, noise, score3, n, stream);
+}
+
+int so3d_q_sample_dseed_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T, const float* cdf,
+                            const uint32_t* guide, const float* loc, const uint64_t* seed_dev, uint64_t rng_offset, uint64_t row_offset,
+                            float* x_t, float* target3, int64_t n, void* stream) {
+  SO3D_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return 0;
+  SO3D_REQUIRE(x0 && t && sqrt_ac && sqrt_1m_ac && cdf && loc && x_t && seed_dev, "so3d_q_sample_dseed_f32: null pointer");
+  SO3D_REQUIRE(T > 0, "so3d_q_sample_dseed_f32: T must be positive");
+  return launch_q_sample<false, true>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, 0, rng_offset, row_offset, x_t, target3, nullptr, nullptr, n,
+                                      stream, seed_dev);
 }
 
 int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt_ac, int64_t T, const float* noise, float* x_t,

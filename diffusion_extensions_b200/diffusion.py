@@ -130,10 +130,68 @@ class SO3Diffusion(nn.Module):
                                       row_offset=self.row_offset, want_target=False, guide=self.guides()[0])["x_t"]
         return ops.q_sample_given(x_start, t, self.sqrt_alphas_cumprod, noise)
 
+    # ---- device-resident noise seed (CUDA-graph capturable training steps) --------------------------
+    def use_device_seed(self, enable=True):
+        """Keep the forward-noising seed in a device tensor that every `noise_and_target` call bumps by one ON THE
+        DEVICE before its launch: the call sequence is then free of host-side RNG state, so a training step captured in
+        a CUDA graph draws fresh noise on every replay (eager calls behave the same way).  Returns the seed tensor."""
+        if not enable:
+            self.__dict__.pop("_device_seed", None)
+            return None
+        dev = self.betas.device
+        if dev.type != "cuda":
+            raise RuntimeError("use_device_seed needs the process on a CUDA device")
+        if self.__dict__.get("_device_seed") is None or self._device_seed.device != dev:
+            seed, off = ops.rng.next()
+            mixed = (seed + 0x9E3779B97F4A7C15 * (off + 1)) & 0x7FFFFFFFFFFFFFFF
+            self._device_seed = torch.full((1,), mixed, dtype=torch.int64, device=dev)
+        return self._device_seed
+
+    def make_graphed_train_step(self, optimizer, example_x, warmup=3):
+        """so3_train.py:70-76 / bingham_train.py:88-95 as ONE CUDA graph: `loss = self(x); loss.backward(); optimizer.step()`
+        is captured once for batches shaped like `example_x` (the optimizer must be constructed with capturable=True) and
+        the returned `step(x) -> loss` copies x into the graph's input and replays it.  At the reference's batch sizes the
+        eager step is launch-bound (~50 launches, 1.05 ms); the replay takes 0.18 ms at batch 256 (tests/tools/probe_train.py).
+        Noise comes from the device-resident seed (use_device_seed), step indices from torch's graph-safe generator."""
+        self.use_device_seed()
+        static_x = example_x.detach().clone()
+        dev = static_x.device
+
+        def one():
+            optimizer.zero_grad(set_to_none=True)
+            loss = self(static_x)
+            loss.backward()
+            optimizer.step()
+            return loss
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                one()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = one()
+
+        def step(x):
+            static_x.copy_(x)
+            graph.replay()
+            return static_loss
+
+        step.graph, step.static_x = graph, static_x
+        return step
+
     def noise_and_target(self, x_start, t, want_noise=False, want_score=False):
         """One fused launch: noise ~ IGSO3(eps_t), x_t, and the 'skewvec' target vee(log noise)/eps_t
         (diffusion.py:349-355)."""
         fwd, _, _ = self.tables()
+        dseed = self.__dict__.get("_device_seed")
+        if dseed is not None and not (want_noise or want_score):
+            dseed.add_(1)                                    # a captured kernel: every replay uses the next seed
+            return ops.q_sample_fused(x_start, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, fwd, seed=dseed, rng_offset=0,
+                                      row_offset=self.row_offset, want_target=True, guide=self.guides()[0])
         return ops.q_sample_fused(x_start, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, fwd,
                                   row_offset=self.row_offset, want_target=True, want_noise=want_noise, want_score=want_score,
                                   guide=self.guides()[0])

@@ -584,10 +584,18 @@ def q_sample_fused(x0, t, sqrt_ac, sqrt_1m_ac, cdf, seed=None, rng_offset=None, 
     if cdf.numel() != T * CDF_POINTS:
         raise ValueError("cdf table must have one row per timestep")
     _, _, trap_loc = cdf_grid(dev)
-    if seed is None or rng_offset is None:
+    seed_dev = _seed_tensor(seed, dev)
+    if seed_dev is None and (seed is None or rng_offset is None):
         seed, rng_offset = rng.next()
     x_t = torch.empty_like(x0)
     target = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_target else None
+    if seed_dev is not None:  # CUDA-graph replayable launch: the seed is read on the device when the kernel runs
+        if want_noise or want_score:
+            raise ValueError("a device seed supports the x_t / target outputs only")
+        _check_guide(guide, T, "guide")
+        call("so3d_q_sample_dseed_f32", ptr(x0), ptr(t), ptr(sqrt_ac), ptr(sqrt_1m_ac), T, ptr(cdf), ptr(guide), ptr(trap_loc), ptr(seed_dev),
+             int(rng_offset or 0), int(row_offset), ptr(x_t), ptr(target), n, device=dev)
+        return {"x_t": x_t, "target": target, "noise": None, "score": None}
     noise = torch.empty_like(x0) if want_noise else None
     score = torch.empty(*bs, 3, dtype=torch.float32, device=dev) if want_score else None
     _check_guide(guide, T, "guide")

@@ -132,6 +132,12 @@ int so3d_igso3_sample_f32(const float* cdf, const uint32_t* guide, const float* 
 int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
                       const float* cdf, const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset,
                       uint64_t row_offset, float* x_t, float* target3, float* noise, float* score3, int64_t n, void* stream);
+/* so3d_q_sample_f32 (x_t and target only) with the Philox SEED READ FROM DEVICE MEMORY when the kernel runs: a training
+ * step captured in a CUDA graph (so3_train.py:70-76: loss = process(x); backward; step) draws fresh noise on every replay
+ * after the caller bumps *seed_dev (a captured `seed.add_(1)`).  Draws equal so3d_q_sample_f32's at seed = *seed_dev. */
+int so3d_q_sample_dseed_f32(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T,
+                            const float* cdf, const uint32_t* guide, const float* loc, const uint64_t* seed_dev,
+                            uint64_t rng_offset, uint64_t row_offset, float* x_t, float* target3, int64_t n, void* stream);
 /* q_sample with the noise supplied by the caller (diffusion.py:339-346 with noise != None). */
 int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt_ac, int64_t T, const float* noise,
                             float* x_t, int64_t n, void* stream);

@@ -662,6 +662,51 @@ def test_warp_schedule_ragged_and_unaligned_pieces(dx, cuda_device):
     assert np.max(np.abs(host(full_q["x_t"]) - ref)) < 5e-6
 
 
+def test_device_seed_and_graphed_train_step(dx, cuda_device):
+    """Forward noising with the Philox seed in device memory: (1) equal to the by-value launch at the same seed, bit for
+    bit; (2) captured in a CUDA graph it follows the seed tensor (replays differ, and each equals the by-value launch at
+    that seed); (3) `make_graphed_train_step` trains the toy model of so3_train.py (loss falls, fresh noise per replay)."""
+    n = 3001
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    x0 = dev(rand_rots(n, 71)[0], cuda_device)
+    t = torch.randint(0, 1000, (n,), device=cuda_device)
+    fwd, _, _ = p.tables()
+    fg, _ = p.guides()
+    args = (p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd)
+    S = 0x1234_5678_9ABC_DEF
+    seed_t = torch.full((1,), S, dtype=torch.int64, device=cuda_device)
+    a = dx.ops.q_sample_fused(x0, t, *args, seed=seed_t, rng_offset=4, row_offset=17, guide=fg)
+    b = dx.ops.q_sample_fused(x0, t, *args, seed=S, rng_offset=4, row_offset=17, guide=fg)
+    assert torch.equal(a["x_t"], b["x_t"]) and torch.equal(a["target"], b["target"])
+    # captured: bump the seed on the device, launch
+    side = torch.cuda.Stream(cuda_device)
+    side.wait_stream(torch.cuda.current_stream(cuda_device))
+    with torch.cuda.stream(side):
+        dx.ops.q_sample_fused(x0, t, *args, seed=seed_t, rng_offset=0, guide=fg)
+    torch.cuda.current_stream(cuda_device).wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        seed_t.add_(1)
+        out = dx.ops.q_sample_fused(x0, t, *args, seed=seed_t, rng_offset=0, guide=fg)
+    for k in (1, 2):
+        g.replay()
+        ref = dx.ops.q_sample_fused(x0, t, *args, seed=S + k, rng_offset=0, guide=fg)
+        assert torch.equal(out["x_t"], ref["x_t"]) and torch.equal(out["target"], ref["target"])
+    # the reference's toy problem (so3_train.py:65-76): two-point target, RotPredict, Adam -- as one graph per step
+    torch.manual_seed(0)
+    net = dx.RotPredict().to(cuda_device)
+    proc = dx.SO3Diffusion(net).to(cuda_device)
+    opt = torch.optim.Adam(net.parameters(), lr=3e-3, capturable=True)
+    z90 = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], device=cuda_device)
+    batch = torch.stack([z90, z90.T]).repeat(128, 1, 1)                      # so3_train.py:65-68, batch 256
+    step = proc.make_graphed_train_step(opt, batch)
+    losses = torch.stack([step(batch).detach().clone() for _ in range(400)]).cpu()
+    assert torch.isfinite(losses).all()
+    assert len(set(losses[:20].tolist())) == 20                              # fresh t and noise on every replay
+    assert losses[-50:].mean() < 0.8 * losses[:50].mean()                    # and it learns
+    assert proc._device_seed.item() > 400
+
+
 def test_guide_table_lookup_is_exact(dx, cuda_device):
     """The guided inverse-CDF search returns exactly the index of the full search: sampling with and
     without the guide table gives bit-identical rotations, for per-row table rows and for the shared row."""

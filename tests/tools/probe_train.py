@@ -4,8 +4,7 @@ reference's CPU path (oracle/ref_port.py, the reference's own op sequence) at ba
 
     python tests/tools/probe_train.py [--cpu] [--graph]
 
-(--graph: the capture currently fails -- the ops take the Philox offset by value from a host-side counter, so a
-captured step would replay the same draws anyway; a graph-safe step needs a device-resident offset.)
+(--graph: also time SO3Diffusion.make_graphed_train_step, the step captured as one CUDA graph.)
 """
 import json
 import os
@@ -31,27 +30,21 @@ def gpu_leg(B, graph):
     x0 = ops.quat_to_rmat(torch.randn(B, 4, device=dev))
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=True)
         loss = proc(x0)
         loss.backward()
         opt.step()
         return loss
 
-    for _ in range(5):
-        loss = step()
-    torch.cuda.synchronize()
     run = step
-    if graph:
-        g = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(3):
-                step()
-        torch.cuda.current_stream().wait_stream(s)
-        with torch.cuda.graph(g):
+    if graph:  # whole-step capture (SO3Diffusion.make_graphed_train_step: device-resident noise seed)
+        stepper = proc.make_graphed_train_step(opt, x0)
+        run = lambda: stepper(x0)
+        loss = run()
+    else:
+        for _ in range(5):
             loss = step()
-        run = g.replay
+    torch.cuda.synchronize()
     reps = 200 if B <= 65536 else 20
     for _ in range(10):
         run()
@@ -74,7 +67,8 @@ for B in (256, 4096, 65536, 1 << 20):
         try:
             print(json.dumps(gpu_leg(B, graph)), flush=True)
         except Exception as e:
-            print(json.dumps({"leg": "gpu", "batch": B, "cuda_graph": graph, "error": repr(e)[:300]}), flush=True)
+            import traceback
+            print(json.dumps({"leg": "gpu", "batch": B, "cuda_graph": graph, "error": repr(e)[:300], "tb": traceback.format_exc()[-1500:]}), flush=True)
 
 if "--cpu" in sys.argv:
     from oracle import ref_port as P
