@@ -442,6 +442,49 @@ def main():
             "mlp_tflops_algorithmic": vd / world * flop_ps * 1e-12}
         del net, procn
 
+        # the launch-bound ends of the same paths, as ONE CUDA graph each (device-resident Philox seed):
+        # the reference's own sampling size (bingham_test.py:25: 20 000 particles x 1000 steps) and its toy training step
+        # (so3_train.py:65-76: batch 256, RotPredict + Adam).  Wall clock, per call, on this rank.
+        if rank == 0:
+            torch.manual_seed(SEED)
+            gnet = dx.RotPredict().to(device)
+            gproc = dx.SO3Diffusion(gnet).to(device)
+            loops = {}
+            for use_graph in (False, True):
+                gproc.p_sample_loop((20000,), cuda_graph=use_graph)          # warm-up / capture
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    gproc.p_sample_loop((20000,), cuda_graph=use_graph)
+                torch.cuda.synchronize()
+                loops["cuda_graph" if use_graph else "eager"] = (time.perf_counter() - t0) / 3 * 1e3
+            extra["reverse_loop_20000_particles_ms"] = {**loops, "unit": "ms per 1000-step loop (wall clock)",
+                                                        "note": "RotPredict + reverse step fused, one launch per step; eager vs one captured CUDA graph"}
+            gopt = torch.optim.Adam(gnet.parameters(), lr=1e-3, capturable=True)
+            xb256 = R[:256].contiguous()
+            steps_ms = {}
+
+            def eager_step():
+                gopt.zero_grad(set_to_none=True)
+                gproc(xb256).backward()
+                gopt.step()
+
+            graphed = gproc.make_graphed_train_step(gopt, xb256)
+            for name, fn in (("eager", eager_step), ("cuda_graph", lambda: graphed(xb256))):
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(200):
+                    fn()
+                torch.cuda.synchronize()
+                steps_ms[name] = (time.perf_counter() - t0) / 200 * 1e3
+            extra["train_step_batch256_ms"] = {**steps_ms, "unit": "ms per step (wall clock)",
+                                               "note": "SO3Diffusion('skewvec') + RotPredict + Adam; eager vs SO3Diffusion.make_graphed_train_step"}
+            del gnet, gproc, gopt, graphed
+        if dist_on:
+            torch.distributed.barrier()
+
         # MMD two-sample statistic at bingham_test.py:29's size (20 000 vs 20 000 rotations), one fused
         # all-pairs launch; multi-GPU: tile pairs dealt round-robin, three doubles all-reduced.
         nm = 20000

@@ -53,12 +53,15 @@ def timeit(fn, reps=10, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+sigma = (0.5 * proc.posterior_log_variance_clipped).exp().contiguous()
 sched = (proc.sqrt_recip_alphas_cumprod, proc.sqrt_recipm1_alphas_cumprod, proc.posterior_mean_coef1, proc.posterior_mean_coef2)
 cases = [
     ("p_sample shared t", 84, lambda: ops.p_sample_fused(R, pred, t1, *sched, post_cdf=post, seed=1, rng_offset=1)),
     ("p_sample per-row t", 92, lambda: ops.p_sample_fused(R, pred, tt, *sched, post_cdf=post, seed=1, rng_offset=1, post_guide=post_guide)),
     ("q_sample per-row t", 92, lambda: ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fwd_guide)),
     ("q_sample + score", 104, lambda: ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fwd_guide, want_score=True)),
+    ("se3 q_sample per-row t", 128, lambda: ops.se3_q_sample_fused(R, v, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, 75.0, seed=1, rng_offset=1, guide=fwd_guide)),
+    ("se3 p_sample shared t", 120, lambda: ops.se3_p_sample_fused(R, v, pred, pred, t1, *sched, sigma, 75.0, post_cdf=post, seed=1, rng_offset=1)),
     ("score auto", 56, lambda: ops.igso3_logp_score(R, eps, mode="auto")),
     ("score closed", 56, lambda: ops.igso3_logp_score(R, eps, mode="closed")),
     ("sample shared row", 48, lambda: ops.igso3_sample(fwd, (n,), row=500, seed=1, rng_offset=1)),
