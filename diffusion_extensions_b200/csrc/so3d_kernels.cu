@@ -28,6 +28,27 @@ namespace {
 
 constexpr int kTile = 256;  // rows per tile == threads per CTA
 
+// Build-time tuning knobs of the fused steps.  A variant library is built with
+//   python tests/tools/build_variant.py NAME -DSO3D_QS_MINCTAS=5 ...
+// and selected at run time with SO3D_LIB_PATH=build/variants/libso3d_NAME.so (tests/tools/probe_engine.py compares them);
+// the defaults are the measured winners (profiles/r01l..r01u_probe_engine.jsonl).  Run-time aids: SO3D_ENGINE=cta|warp
+// overrides the per-op schedule, SO3D_CTAS_PER_SM caps the persistent grid.
+#ifndef SO3D_QS_OUTSTAGES
+#define SO3D_QS_OUTSTAGES 1  // forward noising: output stages (1: more resident CTAs)
+#endif
+#ifndef SO3D_QS_MINCTAS
+#define SO3D_QS_MINCTAS 4    // forward noising: resident CTAs promised to ptxas (4 -> <= 64 registers, no spills)
+#endif
+#ifndef SO3D_PSS_OUTSTAGES
+#define SO3D_PSS_OUTSTAGES 2 // shared-t reverse step: output stages
+#endif
+#ifndef SO3D_PSS_MINCTAS
+#define SO3D_PSS_MINCTAS 1   // shared-t reverse step: no register cap (63 registers schedule 3 % faster than 48)
+#endif
+#ifndef SO3D_PS_MINCTAS
+#define SO3D_PS_MINCTAS 3    // per-row-t reverse step
+#endif
+
 thread_local char g_err[256] = "";
 
 int fail(int code, const char* what) {
@@ -947,12 +968,6 @@ struct BinghamOp {
 template <bool kExtra, bool kDevSeed = false>
 struct QSampleOp {
   // per-row table rows are dependent L2 accesses: latency-bound, so favour resident CTAs over output double-buffering
-#ifndef SO3D_QS_OUTSTAGES
-#define SO3D_QS_OUTSTAGES 1
-#endif
-#ifndef SO3D_QS_MINCTAS
-#define SO3D_QS_MINCTAS 4
-#endif
   SO3D_OP_ARRAYS_S(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1), SO3D_QS_OUTSTAGES)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
   static constexpr int kTab = kGrid;  // loc only
   static constexpr int kMinCtas = SO3D_QS_MINCTAS;  // 4 CTAs (<= 64 registers, no spills) beat 5 CTAs with 56 B of spills: 0.442 vs 0.476 ms (r01m)
@@ -1038,19 +1053,10 @@ struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
 // a separate instantiation, so the by-value kernels' code is untouched.
 template <bool kSharedT, bool kX0, bool kDevSeed = false>
 struct PStepOp {
-#ifndef SO3D_PSS_OUTSTAGES
-#define SO3D_PSS_OUTSTAGES 2
-#endif
   SO3D_OP_ARRAYS_S(1, 1, (kX0 ? 2 : 1), 0, (kSharedT ? SO3D_PSS_OUTSTAGES : 1))  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
   // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
   // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
-#ifndef SO3D_PS_MINCTAS
-#define SO3D_PS_MINCTAS 3
-#endif
-#ifndef SO3D_PSS_MINCTAS
-#define SO3D_PSS_MINCTAS 1
-#endif
   static constexpr int kMinCtas = kSharedT ? SO3D_PSS_MINCTAS : SO3D_PS_MINCTAS;
   static constexpr bool kWarpSchedule = !kSharedT;
   const int64_t* t;
@@ -1164,12 +1170,6 @@ struct SE3PStepOp {
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
   // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
   // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
-#ifndef SO3D_PS_MINCTAS
-#define SO3D_PS_MINCTAS 3
-#endif
-#ifndef SO3D_PSS_MINCTAS
-#define SO3D_PSS_MINCTAS 1
-#endif
   static constexpr int kMinCtas = kSharedT ? SO3D_PSS_MINCTAS : SO3D_PS_MINCTAS;
   static constexpr bool kWarpSchedule = !kSharedT;
   const int64_t* t;
