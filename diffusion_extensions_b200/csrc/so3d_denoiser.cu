@@ -484,7 +484,8 @@ static int rotpredict_p_sample_impl(const float* x_t, const float* blob, const f
   SO3D_REQUIRE(T > 0, "so3d_rotpredict_p_sample_f32: T must be positive");
   SO3D_REQUIRE(!post_cdf || loc, "so3d_rotpredict_p_sample_f32: loc required with post_cdf");
   SO3D_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15u) == 0, "so3d_rotpredict_p_sample_f32: blob must be 16-byte aligned");
-  static bool configured = false;
+  static bool configured_dev[64] = {};  // the dynamic shared-memory limit is a per-device kernel attribute
+  bool& configured = configured_dev[so3d_host::current_device()];
   if (!configured) {
     if (cudaFuncSetAttribute(rotpredict_p_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
       return so3d_host::check_launch("so3d_rotpredict_p_sample_f32 (shared memory)");

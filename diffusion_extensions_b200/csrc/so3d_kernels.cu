@@ -65,16 +65,22 @@ int check_launch(const char* name) {
   return 0;
 }
 
-int g_sm_count = 0;
+// Per-device caches (a process may drive several GPUs: kernel attributes such as the dynamic shared-memory limit are
+// per device, so "configured once" must mean once per device).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+int g_sm_count[kMaxDevices] = {0};
 int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sm_count = n;
-    else
-      g_sm_count = 148;
+  const int dev = current_device();
+  if (g_sm_count[dev] == 0) {
+    int n = 0;
+    g_sm_count[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
-  return g_sm_count;
+  return g_sm_count[dev];
 }
 
 inline int grid_for(int64_t n, int ctas_per_sm) {
@@ -548,7 +554,8 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
   static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
   // Persistent grid = exactly the CTAs that are resident at once (registers and shared memory both count): with
   // a static partition of the tiles, a grid larger than one wave leaves the last, partial wave's SMs idle.
-  static int resident[2] = {0, 0};  // per Op instantiation and schedule
+  static int resident_dev[2][kMaxDevices] = {};  // per Op instantiation, schedule and device
+  int* resident = nullptr;
   static const int cta_sync = [] {  // A/B aid: SO3D_ENGINE=cta|warp overrides the op's own choice
     const char* e = getenv("SO3D_ENGINE");
     if (e && strcmp(e, "cta") == 0) return 1;
@@ -556,11 +563,15 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
     return OpWarpSchedule<Op>::value ? 0 : 1;
   }();
   auto kern = cta_sync ? rowwise_kernel_cta<Op> : rowwise_kernel<Op>;
+  const int dev = current_device();
+  int per_schedule[2] = {resident_dev[0][dev], resident_dev[1][dev]};
+  resident = per_schedule;
   if (resident[cta_sync] == 0) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTile, smem) != cudaSuccess || occ < 1) occ = 1;
     resident[cta_sync] = occ;
+    resident_dev[cta_sync][dev] = occ;
   }
   if (ctas_per_sm <= 0 || ctas_per_sm > resident[cta_sync]) ctas_per_sm = resident[cta_sync];
   if (const char* e = getenv("SO3D_CTAS_PER_SM")) {  // tuning aid: cap the persistent grid (CTAs per SM)
@@ -1235,6 +1246,7 @@ namespace so3d_host {
 int fail(int code, const char* what) { return ::fail(code, what); }
 int check_launch(const char* name) { return ::check_launch(name); }
 int sm_count() { return ::sm_count(); }
+int current_device() { return ::current_device(); }
 }  // namespace so3d_host
 
 // ================================================================================================
