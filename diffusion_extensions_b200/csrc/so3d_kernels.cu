@@ -39,6 +39,9 @@ constexpr int kTile = 256;  // rows per tile == threads per CTA
 #ifndef SO3D_QS_MINCTAS
 #define SO3D_QS_MINCTAS 4    // forward noising: resident CTAs promised to ptxas (4 -> <= 64 registers, no spills)
 #endif
+#ifndef SO3D_QSX_MINCTAS
+#define SO3D_QSX_MINCTAS 4   // forward noising with the noise / score outputs compiled in
+#endif
 #ifndef SO3D_PSS_OUTSTAGES
 #define SO3D_PSS_OUTSTAGES 2 // shared-t reverse step: output stages
 #endif
@@ -981,7 +984,7 @@ struct QSampleOp {
   // per-row table rows are dependent L2 accesses: latency-bound, so favour resident CTAs over output double-buffering
   SO3D_OP_ARRAYS_S(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1), SO3D_QS_OUTSTAGES)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
   static constexpr int kTab = kGrid;  // loc only
-  static constexpr int kMinCtas = SO3D_QS_MINCTAS;  // 4 CTAs (<= 64 registers, no spills) beat 5 CTAs with 56 B of spills: 0.442 vs 0.476 ms (r01m)
+  static constexpr int kMinCtas = kExtra ? SO3D_QSX_MINCTAS : SO3D_QS_MINCTAS;  // 4 CTAs (<= 64 registers, no spills) beat 5 CTAs with 56 B of spills: 0.442 vs 0.476 ms (r01m)
   static constexpr bool kWarpSchedule = true;
   const int64_t* t;
   const float* sqrt_ac;
