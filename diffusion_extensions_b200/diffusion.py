@@ -363,6 +363,10 @@ class SO3Diffusion(nn.Module):
 class ProjectedSO3Diffusion(SO3Diffusion):
     """diffusion.py:377-429: the denoiser sees projection(x) (e.g. a rotated point cloud)."""
 
+    def __init__(self, denoise_fn, timesteps=1000, loss_type="skewvec", betas=None, reference_quirks=False):
+        super().__init__(denoise_fn, timesteps=timesteps, loss_type=loss_type, betas=betas, reference_quirks=reference_quirks)
+        self.register_buffer("identity", torch.eye(3))  # diffusion.py:380 (state-dict compatible)
+
     def _denoise(self, x, t):
         b = x.shape[0]
         t_full = t if t.numel() == b else t.expand(b)
@@ -520,6 +524,10 @@ class SE3Diffusion(SO3Diffusion):
 
 class ProjectedSE3Diffusion(SE3Diffusion):
     """diffusion.py:526-573: the denoiser sees projection(x)."""
+
+    def __init__(self, denoise_fn, timesteps=1000, loss_type="grad_mse", betas=None, shift_scale=75.0, reference_quirks=False):
+        super().__init__(denoise_fn, timesteps=timesteps, loss_type=loss_type, betas=betas, shift_scale=shift_scale, reference_quirks=reference_quirks)
+        self.register_buffer("identity", torch.eye(3))  # diffusion.py:529 (state-dict compatible)
 
     def _denoise(self, x: AffineT, t):
         return self.denoise_fn(self.projection(x), t)

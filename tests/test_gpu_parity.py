@@ -662,6 +662,52 @@ def test_warp_schedule_ragged_and_unaligned_pieces(dx, cuda_device):
     assert np.max(np.abs(host(full_q["x_t"]) - ref)) < 5e-6
 
 
+def test_projected_so3_diffusion(dx, cuda_device):
+    """diffusion.py:377-429 ProjectedSO3Diffusion (row a19): the denoiser sees projection(x) -- here a point cloud rotated
+    by x, as in the reference's jigsaw / aircraft scripts -- through the same fused kernels.  With the identity
+    projection it IS SO3Diffusion (same seed -> same loss, same reverse step); with a real projection the loss is finite,
+    differentiable w.r.t. the denoiser, the reverse loop stays on SO(3); an unknown loss_type raises (Q9)."""
+    torch.manual_seed(1)
+    pts = torch.randn(3, 5, device=cuda_device)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.SiLU(), torch.nn.Linear(64, 3)).to(cuda_device)
+    net9 = torch.nn.Sequential(torch.nn.Linear(10, 64), torch.nn.SiLU(), torch.nn.Linear(64, 3)).to(cuda_device)
+
+    def denoise_cloud(cloud, t):                     # cloud: (B, 3, 5) = x @ pts
+        return net(torch.cat([cloud.flatten(-2), (t.float() / 100)[:, None]], -1))
+
+    def denoise_rot(x, t):
+        return net9(torch.cat([x.flatten(-2), (t.float() / 100)[:, None]], -1))
+
+    x0 = dev(rand_rots(512, 81)[0], cuda_device)
+    plain = dx.SO3Diffusion(denoise_rot, timesteps=100).to(cuda_device)
+    proj_id = dx.ProjectedSO3Diffusion(denoise_rot, timesteps=100).to(cuda_device)
+    assert set(proj_id.state_dict()) == set(plain.state_dict()) | {"identity"}          # diffusion.py:380
+    for seed in (3, 4):
+        torch.manual_seed(seed); dx.ops.manual_seed(seed)
+        la = plain(x0)
+        torch.manual_seed(seed); dx.ops.manual_seed(seed)
+        lb = proj_id(x0, lambda x: x)
+        assert torch.equal(la, lb)
+    t = torch.full((512,), 37, device=cuda_device)
+    dx.ops.manual_seed(9)
+    sa = plain.p_sample(x0, t)
+    dx.ops.manual_seed(9)
+    proj_id.projection = lambda x: x
+    sb = proj_id.p_sample(x0, t)
+    assert torch.equal(sa, sb)
+    proc = dx.ProjectedSO3Diffusion(denoise_cloud, timesteps=100).to(cuda_device)
+    loss = proc(x0, lambda x: x @ pts)
+    loss.backward()
+    assert math.isfinite(loss.item()) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    xs = proc.p_sample_loop((64,), lambda x: x @ pts)
+    xx = host(xs)
+    assert xs.shape == (64, 3, 3) and np.max(np.abs(xx @ np.swapaxes(xx, -1, -2) - np.eye(3))) < 1e-4
+    assert np.max(np.abs(np.linalg.det(xx) - 1)) < 1e-4
+    bad = dx.ProjectedSO3Diffusion(denoise_cloud, timesteps=100, loss_type="l1").to(cuda_device)
+    with pytest.raises(RuntimeError):
+        bad(x0, lambda x: x @ pts)
+
+
 def test_device_seed_and_graphed_train_step(dx, cuda_device):
     """Forward noising with the Philox seed in device memory: (1) equal to the by-value launch at the same seed, bit for
     bit; (2) captured in a CUDA graph it follows the seed tensor (replays differ, and each equals the by-value launch at

@@ -193,6 +193,7 @@ def test_se3_module_end_to_end(dx, cuda_device):
     out = small.p_sample_loop((3, Nres))
     assert out.rot.shape == (3, Nres, 3, 3) and torch.isfinite(out.shift).all()
     pp = dx.ProjectedSE3Diffusion(net, timesteps=12).to(cuda_device)
+    assert "identity" in pp.state_dict()                                   # diffusion.py:529
     assert torch.isfinite(pp(x, lambda a: a))
     out = pp.p_sample_loop((3, Nres), lambda a: a)
     assert out.rot.shape == (3, Nres, 3, 3)
