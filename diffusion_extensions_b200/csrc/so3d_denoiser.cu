@@ -171,6 +171,7 @@ struct DenoiseArgs {
   const float* loc;
   uint64_t seed, rng_offset, row_offset;
   const uint64_t* seed_dev;  // non-null: the seed lives in device memory (CUDA-graph replays draw fresh noise)
+  int64_t t_hi, t_lo;        // kLoop: the kernel runs the steps t_hi, t_hi - 1, ..., t_lo itself (rng_offset = step)
   float* out;
   float* pred_out;
   int64_t n;
@@ -229,6 +230,14 @@ __device__ __forceinline__ void silu_epilogue(uint32_t tmem_lane) {
 // mbarriers: bar_a[g] "A operand written" (8 warp arrivals) -> issuer -> tcgen05.commit -> bar_d[g] "accumulator ready".
 constexpr int kEpiWarps = 16, kThreads = (kEpiWarps + 2) * 32;
 
+// kLoop = false: one reverse step (t = a.t[0]).  kLoop = true: the WHOLE reverse process t_hi .. t_lo in one launch --
+// particles are independent and every particle is always handled by the same thread of the same CTA, so the steps
+// need no grid-wide synchronisation: the CTA keeps the weights in shared memory, restages the step's CDF row and
+// time-embedding column between steps (two CTA barriers), reads its rows back from `out` (written by the same thread
+// one step earlier) and draws the step's noise with rng_offset = step, i.e. exactly the launches of
+// diffusion.py:328-337 with so3d_rotpredict_p_sample_f32(..., rng_offset = t) per step, minus 999 launches, 999 weight
+// loads and the HBM round trip of the state between steps.
+template <bool kLoop>
 __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const DenoiseArgs a) {
   extern __shared__ float4 smem4[];
   float* s_blob = reinterpret_cast<float*>(smem4);
@@ -238,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  int64_t ti = a.t[0];
+  int64_t ti = kLoop ? a.t_hi : a.t[0];
   ti = ti < 0 ? 0 : (ti >= a.T ? a.T - 1 : ti);
-  const bool noisy = a.post_cdf && ti != 0 && a.out;
+  bool noisy = a.post_cdf && ti != 0 && a.out;
 
   if (warp == 0) tmem_alloc(s_tmem, 512);
   if (tid == 0) {
@@ -260,11 +269,30 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
       bulk_load(s_blob + off, a.blob + off, (uint32_t)(cnt * sizeof(float)), &bars[0]);
     }
   }
-  if (noisy) stage_cdf(s_tab, a.post_cdf + ti * kCdf, a.loc);  // posterior CDF row of this step + guide
   mbar_wait(&bars[0], 0);
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t blob_addr = smem_u32(s_blob);
+  const int64_t tiles = (a.n + kM - 1) / kM;
+  uint32_t ph = 0;   // mbarrier phase of this warp's hand-off barrier: runs on across the steps
+  int par = 0;       // parity of the noise staging buffer: likewise
+  const int64_t step_lo = kLoop ? (a.t_lo < 0 ? 0 : a.t_lo) : ti;
+  int64_t step = ti;
+  do {  // kLoop = false: the body runs once and the loop folds away
+  if (kLoop) {
+    if (step != ti) {  // every warp is done with the previous step's tables, bias column and accumulators
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    noisy = a.post_cdf && step != 0 && a.out;
+  }
+  const int64_t ts = step;  // the step index this pass works on
+  const float* __restrict__ src = (kLoop && step != ti) ? a.out : a.x_t;
+  const uint64_t step_offset = kLoop ? (uint64_t)step : a.rng_offset;
+  if (noisy) stage_cdf(s_tab, a.post_cdf + ts * kCdf, a.loc);  // posterior CDF row of this step + guide
   // time embedding of this step folded into layer 1's bias column (k = 9): generic-proxy writes, ordered before the MMAs
   if (tid < kD) {
-    const float c = __ldg(a.c1_table + ti * kD + tid);
+    const float c = __ldg(a.c1_table + ts * kD + tid);
     const uint32_t hi = tf32_hi(c);
     s_blob[kOffL1 + canon_index(tid, kIn, kNPad)] = __uint_as_float(hi);
     s_blob[kOffL1 + kL1Floats + canon_index(tid, kIn, kNPad)] = __uint_as_float(tf32_lo(c, hi));
@@ -273,15 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-  const uint32_t blob_addr = smem_u32(s_blob);
-  const int64_t tiles = (a.n + kM - 1) / kM;
 
   if (warp >= kEpiWarps) {
     // ---- MMA issuer of group g: wait for the A operand, issue the layer, commit to the accumulator barrier ----
     const int g = warp - kEpiWarps;
     const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
-    uint32_t ph = 0;
     for (int64_t tile = (int64_t)blockIdx.x * 2 + g; tile < tiles; tile += (int64_t)gridDim.x * 2) {
       {
 #pragma unroll 1
@@ -309,17 +333,15 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
     const uint32_t tmem_lane = tmem_group + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes of the group's columns
     uint64_t* bar_d = &bars[1 + g];
     uint64_t* bar_a = &bars[3 + g];
-    uint32_t ph = 0;
-    const float k_recip = __ldg(a.recip + ti), k_recipm1 = __ldg(a.recipm1 + ti);
-    const float k_c1 = __ldg(a.coef1 + ti), k_c2 = __ldg(a.coef2 + ti);
+    const float k_recip = __ldg(a.recip + ts), k_recipm1 = __ldg(a.recipm1 + ts);
+    const float k_c1 = __ldg(a.coef1 + ts), k_c2 = __ldg(a.coef2 + ts);
 
     const int64_t tile0 = (int64_t)blockIdx.x * 2 + g, tstride = (int64_t)gridDim.x * 2;
     Mat3 x = identity(), xn = identity();
     if (h == 0 && tile0 < tiles && tile0 * kM + r < a.n) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) x.m[k] = __ldcs(a.x_t + (tile0 * kM + r) * 9 + k);
+      for (int k = 0; k < 9; ++k) x.m[k] = __ldcs(src + (tile0 * kM + r) * 9 + k);
     }
-    int par = 0;
     for (int64_t tile = tile0; tile < tiles; tile += tstride, par ^= 1) {
       const int64_t i = tile * kM + r;
       const bool live = i < a.n;
@@ -347,12 +369,12 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
         xn = identity();
         if (tile + tstride < tiles && in < a.n) {
 #pragma unroll
-          for (int k = 0; k < 9; ++k) xn.m[k] = __ldcs(a.x_t + in * 9 + k);
+          for (int k = 0; k < 9; ++k) xn.m[k] = __ldcs(src + in * 9 + k);
         }
       } else if (noisy && live) {
         // the step's noise rotation does not depend on the network: drawn by the second thread of the particle
         const uint64_t sd = a.seed_dev ? __ldg(reinterpret_cast<const unsigned long long*>(a.seed_dev)) : a.seed;
-        const NoiseDraw d = draw_axis_u(sd, a.row_offset + (uint64_t)i, a.rng_offset);
+        const NoiseDraw d = draw_axis_u(sd, a.row_offset + (uint64_t)i, step_offset);
         const Quat qn = quat_axis_angle(d.axis, shared_row_angle(s_tab, d.u));
         s_noise[(g * 2 + par) * kM + r] = make_float4(qn.w, qn.x, qn.y, qn.z);
       }
@@ -404,6 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
       }
     }
   }
+  } while (kLoop && --step >= step_lo);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -487,7 +510,7 @@ static int rotpredict_p_sample_impl(const float* x_t, const float* blob, const f
   static bool configured_dev[64] = {};  // the dynamic shared-memory limit is a per-device kernel attribute
   bool& configured = configured_dev[so3d_host::current_device()];
   if (!configured) {
-    if (cudaFuncSetAttribute(rotpredict_p_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(rotpredict_p_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
       return so3d_host::check_launch("so3d_rotpredict_p_sample_f32 (shared memory)");
     configured = true;
   }
@@ -498,7 +521,8 @@ static int rotpredict_p_sample_impl(const float* x_t, const float* blob, const f
   const int64_t pairs = ((n + kM - 1) / kM + 1) / 2;
   const int sms = so3d_host::sm_count();
   const int grid = (int)(pairs < sms ? pairs : sms);
-  rotpredict_p_sample_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
+  a.t_hi = a.t_lo = 0;
+  rotpredict_p_sample_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
   return so3d_host::check_launch("so3d_rotpredict_p_sample_f32");
 }
 
@@ -508,6 +532,34 @@ int so3d_rotpredict_p_sample_f32(const float* x_t, const float* blob, const floa
                                  float* pred_out, int64_t n, void* stream) {
   return rotpredict_p_sample_impl(x_t, blob, c1_table, t, recip, recipm1, coef1, coef2, T, post_cdf, loc, seed, nullptr, rng_offset, row_offset,
                                   out, pred_out, n, stream);
+}
+
+int so3d_rotpredict_p_sample_loop_f32(const float* x_t, const float* blob, const float* c1_table, int64_t t_hi, int64_t t_lo, const float* recip,
+                                      const float* recipm1, const float* coef1, const float* coef2, int64_t T, const float* post_cdf,
+                                      const float* loc, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset, float* out, int64_t n,
+                                      void* stream) {
+  SO3D_REQUIRE(n >= 0, "negative n");
+  if (n == 0) return 0;
+  SO3D_REQUIRE(x_t && blob && c1_table && recip && recipm1 && coef1 && coef2 && post_cdf && loc && out, "so3d_rotpredict_p_sample_loop_f32: null pointer");
+  SO3D_REQUIRE(T > 0 && t_lo >= 0 && t_hi >= t_lo && t_hi < T, "so3d_rotpredict_p_sample_loop_f32: need 0 <= t_lo <= t_hi < T");
+  SO3D_REQUIRE(out != x_t, "so3d_rotpredict_p_sample_loop_f32: out must not alias x_t");
+  SO3D_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15u) == 0, "so3d_rotpredict_p_sample_loop_f32: blob must be 16-byte aligned");
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[so3d_host::current_device()];
+  if (!configured) {
+    if (cudaFuncSetAttribute(rotpredict_p_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return so3d_host::check_launch("so3d_rotpredict_p_sample_loop_f32 (shared memory)");
+    configured = true;
+  }
+  DenoiseArgs a;
+  a.x_t = x_t; a.blob = blob; a.c1_table = c1_table; a.t = nullptr; a.recip = recip; a.recipm1 = recipm1; a.coef1 = coef1; a.coef2 = coef2;
+  a.T = T; a.post_cdf = post_cdf; a.loc = loc; a.seed = seed; a.seed_dev = seed_dev; a.rng_offset = 0; a.row_offset = row_offset;
+  a.t_hi = t_hi; a.t_lo = t_lo; a.out = out; a.pred_out = nullptr; a.n = n;
+  const int64_t pairs = ((n + kM - 1) / kM + 1) / 2;
+  const int sms = so3d_host::sm_count();
+  const int grid = (int)(pairs < sms ? pairs : sms);
+  rotpredict_p_sample_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a);
+  return so3d_host::check_launch("so3d_rotpredict_p_sample_loop_f32");
 }
 
 int so3d_rotpredict_p_sample_dseed_f32(const float* x_t, const float* blob, const float* c1_table, const int64_t* t, const float* recip,

@@ -91,6 +91,7 @@ class SO3Diffusion(nn.Module):
         # batch independent of the number of GPUs (set by the multi-GPU harness)
         self.row_offset = 0
         self.fuse_denoiser = True  # p_sample runs a RotPredict denoiser inside the reverse-step kernel when it can
+        self.fused_loop = True       # p_sample_loop(cuda_graph=True) with a fusable RotPredict: all T steps in ONE launch
         self._tables = {}  # device -> (fwd_cdf, post_cdf, t_range)
         self._guides = {}  # device -> (fwd_guide, post_guide)
 
@@ -281,6 +282,12 @@ class SO3Diffusion(nn.Module):
         dev = x.device
         fn = self.denoise_fn
         probe = self._fused_denoiser(x, self.tables()[2][:1])          # (re)packs the weights if they changed
+        if probe is not None and self.fused_loop:
+            # RotPredict on the tensor-core route: no graph needed, the kernel itself runs all T steps in one launch
+            seed, off = ops.rng.next()
+            mixed = (seed + 0x9E3779B97F4A7C15 * (off + 1)) & 0xFFFFFFFFFFFFFFFF
+            return ops.rotpredict_p_sample_loop(x, probe[0], probe[1], self.num_timesteps - 1, 0, *self._sched4(), self.tables()[1], mixed,
+                                                row_offset=self.row_offset)
         packed_key = fn._packed[0] if probe is not None else None
         key = (tuple(x.shape), str(dev), id(fn), packed_key, self.row_offset, bool(self.fuse_denoiser), self.num_timesteps)
         cache = self.__dict__.setdefault("_loop_graphs", {})

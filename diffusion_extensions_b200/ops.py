@@ -723,3 +723,28 @@ def rotpredict_p_sample_fused(x_t, blob, c1_table, t, recip, recipm1, coef1, coe
     if want_out and want_pred:
         return out, pred
     return out if want_out else pred
+
+
+def rotpredict_p_sample_loop(x_t, blob, c1_table, t_hi, t_lo, recip, recipm1, coef1, coef2, post_cdf, seed, row_offset=0):
+    """The reverse steps t_hi .. t_lo (inclusive, descending) with the RotPredict denoiser in ONE launch; step t draws
+    its noise at rng_offset = t.  seed: int (by value) or a device int64[1] tensor.  -> x_{t_lo - 1} (...,3,3)"""
+    x_t, bs, n = _rows9(x_t, "x")
+    dev = x_t.device
+    blob = check_f32(blob, "blob")
+    if blob.numel() != ROTPREDICT_BLOB_FLOATS:
+        raise ValueError("blob must come from rotpredict_pack")
+    recip, recipm1 = check_f32(recip, "sqrt_recip_alphas_cumprod"), check_f32(recipm1, "sqrt_recipm1_alphas_cumprod")
+    coef1, coef2 = check_f32(coef1, "posterior_mean_coef1"), check_f32(coef2, "posterior_mean_coef2")
+    T = recip.numel()
+    c1_table = check_f32(c1_table, "c1_table", (ROTPREDICT_D,))
+    post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
+    if c1_table.numel() != T * ROTPREDICT_D or post_cdf.numel() != T * CDF_POINTS:
+        raise ValueError("c1_table and post_cdf must have one row per timestep")
+    if not (0 <= int(t_lo) <= int(t_hi) < T):
+        raise ValueError("need 0 <= t_lo <= t_hi < T")
+    _, _, trap_loc = cdf_grid(dev)
+    seed_dev = _seed_tensor(seed, dev)
+    out = torch.empty_like(x_t)
+    call("so3d_rotpredict_p_sample_loop_f32", ptr(x_t), ptr(blob), ptr(c1_table), int(t_hi), int(t_lo), ptr(recip), ptr(recipm1), ptr(coef1),
+         ptr(coef2), T, ptr(post_cdf), ptr(trap_loc), 0 if seed_dev is not None else int(seed), ptr(seed_dev), int(row_offset), ptr(out), n, device=dev)
+    return out

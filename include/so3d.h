@@ -191,6 +191,15 @@ int so3d_rotpredict_p_sample_dseed_f32(const float* x_t, const float* blob, cons
                                        uint64_t rng_offset, uint64_t row_offset, float* out, float* pred_out, int64_t n,
                                        void* stream);
 
+/* diffusion.py:328-337 / so3_test.py:26-31: the WHOLE reverse process in one launch -- the steps t_hi, t_hi - 1, ..., t_lo
+ * of so3d_rotpredict_p_sample_f32 with rng_offset = t at step t (bit-identical to that sequence of launches).  Particles
+ * are independent and stay with one thread, so no grid-wide synchronisation is needed; the weights are staged once.
+ * seed_dev non-NULL: the seed is read from device memory instead of `seed`.  out must not alias x_t.  post_cdf required. */
+int so3d_rotpredict_p_sample_loop_f32(const float* x_t, const float* blob, const float* c1_table, int64_t t_hi, int64_t t_lo,
+                                      const float* recip, const float* recipm1, const float* coef1, const float* coef2,
+                                      int64_t T, const float* post_cdf, const float* loc, uint64_t seed,
+                                      const uint64_t* seed_dev, uint64_t row_offset, float* out, int64_t n, void* stream);
+
 /* ---- SE(3) arm: diffusion.py SE3Diffusion / distributions.py IGSO3xR3 --------------- */
 /* diffusion.py:498-516 (SE3Diffusion.q_sample + p_losses targets), fused.  Rotation half exactly as
  * so3d_q_sample_f32 (same Philox block: identical rotation draws at the same seed / rng_offset); translation half

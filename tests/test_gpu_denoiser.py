@@ -214,17 +214,20 @@ def test_p_sample_loop_with_fused_denoiser(dx, cuda_device):
     assert (torch.linalg.det(a) - 1).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("fuse", [True, False])
-def test_p_sample_loop_as_cuda_graph(dx, cuda_device, fuse):
-    """p_sample_loop(cuda_graph=True) replays the whole reverse process as one captured graph whose kernels read the
-    Philox seed from device memory: (1) equal, bit for bit, to the eager loop run with that seed by value, for the fused
-    tensor-core denoiser and for the stock-PyTorch denoiser route; (2) a replay draws fresh noise; (3) a weight update
-    re-captures."""
+@pytest.mark.parametrize("route", ["one_launch", "graph_fused", "graph_stock"])
+def test_p_sample_loop_as_cuda_graph(dx, cuda_device, route):
+    """p_sample_loop(cuda_graph=True) runs the whole reverse process without per-step launches from the host:
+    "one_launch" -- the fused tensor-core kernel iterates all T steps itself (so3d_rotpredict_p_sample_loop_f32);
+    "graph_fused" / "graph_stock" -- one captured CUDA graph of T launches whose kernels read the Philox seed from device
+    memory, with the fused denoiser or the stock-PyTorch denoiser.  Each must (1) equal, bit for bit, the eager loop run
+    with that seed by value, (2) draw fresh noise on the next call, (3) follow a weight update."""
     torch.manual_seed(3)
     T, n = 40, 700
+    fuse = route != "graph_stock"
     net = dx.RotPredict().to(cuda_device)
     proc = dx.SO3Diffusion(net, timesteps=T).to(cuda_device)
     proc.fuse_denoiser = fuse
+    proc.fused_loop = route == "one_launch"
     sched = (proc.sqrt_recip_alphas_cumprod, proc.sqrt_recipm1_alphas_cumprod, proc.posterior_mean_coef1, proc.posterior_mean_coef2)
 
     def eager_with_seed(seed_start):
@@ -250,7 +253,7 @@ def test_p_sample_loop_as_cuda_graph(dx, cuda_device, fuse):
     a2 = proc.p_sample_loop((n,), cuda_graph=True)          # replay of the cached graph, same seed
     b = proc.p_sample_loop((n,), cuda_graph=True)           # replay, next seed: fresh noise
     assert torch.equal(a, a2) and not torch.equal(a, b)
-    assert len(proc._loop_graphs) == 1
+    assert len(getattr(proc, "_loop_graphs", {})) == (0 if route == "one_launch" else 1)
     assert (b.transpose(-1, -2) @ b - torch.eye(3, device=cuda_device)).abs().max().item() < 5e-6
     with torch.no_grad():
         net.net[0].weight.mul_(1.05)                         # a weight update: the fused route must re-pack and re-capture
