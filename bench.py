@@ -46,10 +46,10 @@ FLOP_PER_TERM = 11
 BYTES_PER_EVAL = 56          # 36 R + 4 eps in, 4 logp + 12 score out
 BYTES_PER_PARTICLE_STEP = 84 # 36 x_t + 12 pred in, 36 out
 BYTES_PER_QSAMPLE = 92       # 36 x0 + 8 t in, 36 x_t + 12 target out
-# DRAM traffic of the series kernel per evaluation from the ncu --set full capture (profiles/r02g_series_full.md:
-# 167.92 MB read + 43.45 MB written for 4 194 304 evaluations; the rest of the 16 B/eval of results is still in L2
+# DRAM traffic of the series kernel per evaluation from the ncu --set full capture (profiles/r02p_series_full.md:
+# 169.07 MB read + 43.80 MB written for 4 194 304 evaluations; the rest of the 16 B/eval of results is still in L2
 # when the kernel ends) -- equal to the algorithmic 40 B/eval of inputs: nothing is re-read.
-NCU_DRAM_BYTES_PER_EVAL = (167.923712e6 + 43.451392e6) / 4194304
+NCU_DRAM_BYTES_PER_EVAL = (169.070080e6 + 43.798272e6) / 4194304
 MMD_LANE_INSTR_PER_PAIR = 41  # executed FP32-pipe instructions per pair of the all-pairs kernel (SASS count)
 
 
@@ -523,7 +523,7 @@ def main():
         clk_per_term = sm * 4 * ghz * 1e9 * 32 / (per_gpu * L)
         roofline = {
             "bound": "fp32", "achieved": ach * 1e-12, "peak": issue_peak * 1e-12, "unit": "T lane-instr/s", "frac": ach / issue_peak,
-            "traffic": NCU_DRAM_BYTES_PER_EVAL * n, "traffic_source": "ncu --set full, profiles/r02g_series_full.md (bytes/eval x rows per launch)",
+            "traffic": NCU_DRAM_BYTES_PER_EVAL * n, "traffic_source": "ncu --set full, profiles/r02p_series_full.md (bytes/eval x rows per launch)",
             "definition": "SURVEY 8(d): FP32-issue bound with 10 lane-instr/term (1.86e9 evals/s/GPU); executed mix below",
             "executed_per_term": {"fp32_instr": FP32_INSTR_PER_TERM, "mufu": MUFU_PER_TERM, "uniform_ldc": UNIFORM_PER_TERM, "flop": FLOP_PER_TERM},
             "clk_per_warp_term": clk_per_term, "clk_floor_issue": 9.0, "clk_floor_xu": 8.0, "clk_floor_fp32_operands": 8.8,

@@ -745,7 +745,22 @@ SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out)
 // rho_{l-2} = rho_l 2^(4c) (half the MUFU, +0.5 FMUL per term) is SLOWER, 12.9 vs 12.2 clk per warp-term: the
 // FP32 operand bandwidth is the wall, not the XU pipe.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSeriesBlock = 32;       // unrolled terms per block
+// Source-form knobs of the unrolled block.  The arithmetic is the same in every form; what changes is the order ptxas's
+// list scheduler emits the 9 instructions per term in, and with it how often the FP32 pipe waits for register ports
+// and the MUFU queue.  Measured on B200, L = 2000, 2^24 evaluations (profiles/r02m_series_variants.jsonl):
+//   order 0 / block 32: 11.02 ms (12.22 clk per warp-term)     order 1 / block 64: 10.68 ms (11.85)  <- shipped
+//   order 0 / block 64: 12.01      order 1 / block 32: 10.98      order 2 / block 64: 10.89      order 3 / block 64: 10.69
+//   blocks 16, 48, 56, 72, 80, 96, 128 with the best order: 10.89 .. 11.64
+#ifndef SO3D_SERIES_BLOCK
+#define SO3D_SERIES_BLOCK 64
+#endif
+#ifndef SO3D_SERIES_ORDER
+#define SO3D_SERIES_ORDER 1
+#endif
+#ifndef SO3D_SERIES_ROUNDUP
+#define SO3D_SERIES_ROUNDUP 1
+#endif
+constexpr int kSeriesBlock = SO3D_SERIES_BLOCK;       // unrolled terms per block
 constexpr int kSeriesMaxTerms = 2896;  // m(m+1) is exact in fp32 below this
 
 struct alignas(16) SeriesTab {
@@ -796,6 +811,7 @@ SO3D_HD void igso3_series_run(SeriesState& st, float kap, float kapp, float cexp
 #pragma unroll kUnroll
   for (int i = 0; i < count; ++i) {
     const int l = hi - i;
+#if SO3D_SERIES_ORDER == 0
     const float A = fast_ex2(series_mm(l) * cexp) * series_mh(l);
     const float dn = fmaf(-kap, st.b, A + st.d);
     const float dpn = fmaf(-kap, st.bp, fmaf(-kapp, st.b, st.dp));
@@ -805,6 +821,38 @@ SO3D_HD void igso3_series_run(SeriesState& st, float kap, float kapp, float cexp
     st.bp += dpn;
     st.d = dn;
     st.dp = dpn;
+#elif SO3D_SERIES_ORDER == 1  // derivative chain first
+    const float dpn = fmaf(-kap, st.bp, fmaf(-kapp, st.b, st.dp));
+    const float A = fast_ex2(series_mm(l) * cexp) * series_mh(l);
+    const float dn = fmaf(-kap, st.b, A + st.d);
+    st.b2 = st.b;
+    st.bp2 = st.bp;
+    st.bp += dpn;
+    st.b += dn;
+    st.dp = dpn;
+    st.d = dn;
+#elif SO3D_SERIES_ORDER == 3  // derivative chain first, each chain's updates kept together
+    const float dpn = fmaf(-kap, st.bp, fmaf(-kapp, st.b, st.dp));
+    st.bp2 = st.bp;
+    st.bp += dpn;
+    st.dp = dpn;
+    const float A = fast_ex2(series_mm(l) * cexp) * series_mh(l);
+    const float dn = fmaf(-kap, st.b, A + st.d);
+    st.b2 = st.b;
+    st.b += dn;
+    st.d = dn;
+#else  // kap-products grouped: t = d - kap b, u = dp - kapp b
+    const float t = fmaf(-kap, st.b, st.d);
+    const float u = fmaf(-kapp, st.b, st.dp);
+    const float dn = fmaf(fast_ex2(series_mm(l) * cexp), series_mh(l), t);
+    const float dpn = fmaf(-kap, st.bp, u);
+    st.b2 = st.b;
+    st.bp2 = st.bp;
+    st.b += dn;
+    st.bp += dpn;
+    st.d = dn;
+    st.dp = dpn;
+#endif
   }
 }
 
@@ -816,8 +864,8 @@ SO3D_HD SeriesAcc igso3_series_terms(float w, float eps, int L) {
   const float kap = 4.0f * sh * sh, kapp = 4.0f * sh * ch;
   SeriesState st;
   st.b = st.d = st.bp = st.dp = st.b2 = st.bp2 = 0.f;
-  const int ragged = L % kSeriesBlock;  // top partial block first, so that full blocks are 32-aligned
-  if (ragged) igso3_series_run<1>(st, kap, kapp, cexp, L - 1, ragged);
+  const int ragged = L % kSeriesBlock;  // top partial block first, so that full blocks are block-aligned
+  if (ragged) igso3_series_run<1>(st, kap, kapp, cexp, L - 1, ragged);  // (an unrolled 16-term form of this partial block made the whole kernel 0.3 % slower)
   // block index as the loop variable: table offsets are provably 128-byte aligned -> LDCU.128
   for (int blk = L / kSeriesBlock - 1; blk >= 0; --blk)
     igso3_series_run<kSeriesBlock>(st, kap, kapp, cexp, blk * kSeriesBlock + (kSeriesBlock - 1), kSeriesBlock);
@@ -849,6 +897,11 @@ SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g
       // keep the trip count (and with it the constant-table index) the same across the warp: a lane-varying index
       // would serialise the constant loads.  The extra terms have weight exactly 0, so the result is unchanged.
       terms = __reduce_max_sync(__activemask(), terms);
+#endif
+#if SO3D_SERIES_ROUNDUP
+      // whole blocks only: the extra terms have weight exactly 0 as well, and the partial-block loop is the slow one
+      const int up = (terms + kSeriesBlock - 1) / kSeriesBlock * kSeriesBlock;
+      terms = up <= L ? up : L;
 #endif
     }
     const SeriesAcc a = igso3_series_terms(w, eps, terms);
