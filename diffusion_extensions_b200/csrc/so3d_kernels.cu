@@ -195,11 +195,12 @@ struct OpWarpSchedule<Op, std::void_t<decltype(Op::kWarpSchedule)>> {
   static constexpr bool value = Op::kWarpSchedule;
 };
 
-// Compute-bound ops (the 2000-term series) set Op::kWideIndex: they keep the 64-bit per-tile index arithmetic of
-// the first engine.  The tile loop is noise for them, but ptxas's list schedule of the unrolled 32-term block is
-// sensitive to the surrounding code: with the strength-reduced indices below the SAME instructions come out in an
-// order that runs 2.6 % slower (11.29 vs 11.00 ms per 2^24 evaluations, profiles/r01x_bench.json vs r01q), so the
-// headline kernel's instantiation is kept on the source form that yields the faster schedule.
+// An op may set Op::kWideIndex to keep the 64-bit per-tile index arithmetic of the first engine.  The tile loop is
+// noise for the compute-bound series kernel, but ptxas's list schedule of its unrolled block is sensitive to the
+// surrounding code: with the 32-term source form the strength-reduced indices below made the SAME instructions come
+// out in an order that ran 2.6 % slower (11.29 vs 11.00 ms per 2^24 evaluations, profiles/r01x_bench.json vs r01q);
+// with the shipped 64-term form it is the other way round (10.60 vs 10.70 ms), so the knob is now off
+// (SO3D_SERIES_WIDE_INDEX).
 template <class Op, class = void>
 struct OpWideIndex {
   static constexpr bool value = false;
@@ -766,7 +767,10 @@ struct LogpScoreOp {  // distributions.py:74-77 + score, fused with 
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
   static constexpr int kMinCtas = (kMode == kClosed || kMode == kAuto) ? 5 : 1;  // HBM-bound evaluators: >= 5 CTAs (<= 51 registers)
-  static constexpr bool kWideIndex = (kMode == kSeries || kMode == kSeriesAdaptive);  // see rowwise_kernel_cta
+#ifndef SO3D_SERIES_WIDE_INDEX
+#define SO3D_SERIES_WIDE_INDEX 0  // 1 was 2.6 % faster with the 32-term source form (r01x/r01y); with the 64-term form it is 0.9 % slower
+#endif
+  static constexpr bool kWideIndex = SO3D_SERIES_WIDE_INDEX && (kMode == kSeries || kMode == kSeriesAdaptive);  // see rowwise_kernel_cta
   const float* eps;
   int eps_stride;
   float* logp;
