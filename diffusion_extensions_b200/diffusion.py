@@ -165,16 +165,17 @@ class SO3Diffusion(nn.Module):
             optimizer.step()
             return loss
 
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                one()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
-            static_loss = one()
+        with torch.cuda.device(dev):  # capture on the data's device even if it is not the process's current one
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    one()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_loss = one()
 
         def step(x):
             static_x.copy_(x)
@@ -297,14 +298,15 @@ class SO3Diffusion(nn.Module):
                 cache.pop(next(iter(cache)))
             seed_buf = torch.zeros(1, dtype=torch.int64, device=dev)
             x_in = x.clone()
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):                               # warm-up off the capture: lazy init, allocator
-                self._seeded_steps(x_in, seed_buf, first=3)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                x_out = self._seeded_steps(x_in, seed_buf)
+            with torch.cuda.device(dev):  # capture on the data's device even if it is not the process's current one
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):                           # warm-up off the capture: lazy init, allocator
+                    self._seeded_steps(x_in, seed_buf, first=3)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    x_out = self._seeded_steps(x_in, seed_buf)
             ent = (graph, x_in, seed_buf, x_out, probe)                 # probe keeps the packed weights alive
             cache[key] = ent
         graph, x_in, seed_buf, x_out, _ = ent
