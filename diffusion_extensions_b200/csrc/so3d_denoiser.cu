@@ -45,7 +45,6 @@ namespace {
 // ---- network geometry (RotPredict(d_model=65, out_type="skewvec"), so3_train.py:11-37) ------------------------------
 constexpr int kD = SO3D_ROTPREDICT_D;        // 65: width of every hidden layer
 constexpr int kIn = 9;                       // flattened rotation matrix
-constexpr int kTemb = kD - kIn;              // 56 sinusoidal features
 constexpr int kOut = 3;                      // skew vector
 constexpr int kKPad = 72;                    // 65 activations + 1 bias column, padded to 9 K-steps of 8
 constexpr int kNPad = 80;                    // 65 outputs padded to a legal UMMA N (multiple of 16 at M = 128)
