@@ -56,8 +56,8 @@ SIGNATURES = {
     "so3d_pair_kernel_sums_f32": [_c_f, _i64, _c_f, _i64, _int, _i64, _i64, _c_f, _i64, _c_f, _c_f],
 }
 
-MODE_SERIES, MODE_CLOSED, MODE_AUTO, MODE_SERIES_ADAPTIVE = 0, 1, 2, 3
-MODES = {"series": MODE_SERIES, "closed": MODE_CLOSED, "auto": MODE_AUTO, "series_adaptive": MODE_SERIES_ADAPTIVE}
+MODE_SERIES, MODE_CLOSED, MODE_AUTO, MODE_SERIES_ADAPTIVE, MODE_SERIES_PURE = 0, 1, 2, 3, 4
+MODES = {"series": MODE_SERIES, "closed": MODE_CLOSED, "auto": MODE_AUTO, "series_adaptive": MODE_SERIES_ADAPTIVE, "series_pure": MODE_SERIES_PURE}
 
 PAIR_GAUSSIAN, PAIR_COSINE = 0, 1
 

@@ -770,7 +770,7 @@ struct LogpScoreOp {  // distributions.py:74-77 + score, fused with 
 #ifndef SO3D_SERIES_WIDE_INDEX
 #define SO3D_SERIES_WIDE_INDEX 0  // 1 was 2.6 % faster with the 32-term source form (r01x/r01y); with the 64-term form it is 0.9 % slower
 #endif
-  static constexpr bool kWideIndex = SO3D_SERIES_WIDE_INDEX && (kMode == kSeries || kMode == kSeriesAdaptive);  // see rowwise_kernel_cta
+  static constexpr bool kWideIndex = SO3D_SERIES_WIDE_INDEX && (kMode == kSeries || kMode == kSeriesAdaptive || kMode == kSeriesPure);  // see rowwise_kernel_cta
   const float* eps;
   int eps_stride;
   float* logp;
@@ -1412,14 +1412,14 @@ static int launch_logp_score(const float* R, const float* eps, int eps_stride, f
   op.L = L;
   // The series streams its constant table through the uniform datapath; measured on B200 it runs fastest with few
   // resident warps (3 CTAs/SM: 1.54e9 evals/s, 8 CTAs/SM: 1.26e9): warps at fewer distinct table positions.
-  const int ctas = (kMode == kSeries || kMode == kSeriesAdaptive) ? 3 : 0;
+  const int ctas = (kMode == kSeries || kMode == kSeriesAdaptive || kMode == kSeriesPure) ? 3 : 0;
   return launch_rowwise(op, n, stream, "so3d_igso3_logp_score_f32", ctas);
 }
 
 extern "C" {
 
 static int check_mode(int mode, int L) {
-  if (mode < 0 || mode > 3) return fail(SO3D_EINVAL, "mode must be SO3D_MODE_{SERIES,CLOSED,AUTO,SERIES_ADAPTIVE}");
+  if (mode < 0 || mode > 4) return fail(SO3D_EINVAL, "mode must be SO3D_MODE_{SERIES,CLOSED,AUTO,SERIES_ADAPTIVE,SERIES_PURE}");
   if (mode != SO3D_MODE_CLOSED && (L < 1 || L > 2896)) return fail(SO3D_EINVAL, "series truncation L must be in [1, 2896]");
   return 0;
 }
@@ -1446,6 +1446,7 @@ int so3d_igso3_logp_score_f32(const float* R, const float* eps, int eps_stride, 
     case SO3D_MODE_SERIES: return launch_logp_score<kSeries>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
     case SO3D_MODE_CLOSED: return launch_logp_score<kClosed>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
     case SO3D_MODE_AUTO: return launch_logp_score<kAuto>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
+    case SO3D_MODE_SERIES_PURE: return launch_logp_score<kSeriesPure>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
     default: return launch_logp_score<kSeriesAdaptive>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
   }
 }

@@ -879,8 +879,20 @@ SO3D_HD int igso3_series_live_terms(float eps, int L) {
   return lim < (float)L ? (int)lim : L;
 }
 
-enum IgsoMode { kSeries = 0, kClosed = 1, kAuto = 2, kSeriesAdaptive = 3 };
+enum IgsoMode { kSeries = 0, kClosed = 1, kAuto = 2, kSeriesAdaptive = 3, kSeriesPure = 4 };
 constexpr float kAutoSeriesEps = 1.0f;  // auto: closed form up to eps = 1 (3 images: <= 1e-6 rel, measured), series (<= 12 live terms) above
+
+// Conditioning guard of the fp32 series.  F = sum_l A_l chi_l(w) is an alternating sum whose condition number
+// cond = sum |A_l chi_l| / |F| depends on w/eps only (fp64, eps = 6.4e-3 .. 0.5): 4.5 at w = 3.5 eps, 14 at 4.2 eps,
+// 26 at 4.5 eps, 75 at 5 eps, 155 at 5.3 eps, 386 at 5.66 eps (the edge of the E-set, k = 4).  The fp32 evaluation
+// measures ~4 u cond in the worst row (u = 6e-8): 3.5e-6 at 4.2 eps, 1.2e-5 at 4.9 eps, 6e-5 at 5.66 eps -- and that
+// is not the recurrence's fault: with the recurrence carried in fp64 and only the weights A_l rounded to fp32 the
+// E-set still shows 2.3e-5 at k ~ 4, with exactly rounded weights in the fp32 recurrence 5e-5.
+// north_star's 1e-5 is out of reach of ANY single-precision l-series beyond w ~ 4.8 eps.  The series modes therefore
+// run every row's L terms (the loop is warp-uniform) and then REPLACE the result of the rows with
+// w > kSeriesGuard eps, eps <= 1 by the closed form (the Poisson dual of the same series: 3 images, <= 2e-6 there).
+// kSeriesPure keeps the raw series everywhere.
+constexpr float kSeriesGuard = 4.2f;
 
 // log f_eps(w) and g = d log f / dw by the evaluator kMode (a template parameter, so that a kernel contains one
 // evaluator only and the exact-L series keeps a provably warp-uniform trip count: its table operands must stay
@@ -907,6 +919,8 @@ SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g
     const SeriesAcc a = igso3_series_terms(w, eps, terms);
     *logf_out = logf(2.0f * a.F);
     *g_out = a.dF / a.F;
+    if ((kMode == kSeries || kMode == kSeriesAdaptive) && eps <= kAutoSeriesEps && w > kSeriesGuard * eps)
+      igso3_closed_f32(w, eps, logf_out, g_out);
   }
 }
 
@@ -916,6 +930,7 @@ SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, 
     case kSeries: igso3_logf_g_t<kSeries>(w, eps, L, logf_out, g_out); break;
     case kClosed: igso3_logf_g_t<kClosed>(w, eps, L, logf_out, g_out); break;
     case kAuto: igso3_logf_g_t<kAuto>(w, eps, L, logf_out, g_out); break;
+    case kSeriesPure: igso3_logf_g_t<kSeriesPure>(w, eps, L, logf_out, g_out); break;
     default: igso3_logf_g_t<kSeriesAdaptive>(w, eps, L, logf_out, g_out); break;
   }
 }

@@ -15,8 +15,11 @@ surface, CUDA float32 only, every method one fused sm_100a kernel:
     autograd (distributions.py:186-190).
 
 ``mode`` selects the density evaluator: "closed" (the reference's 3-image closed form in its stable
-rewrite), "series" (L-term truncated series), "auto" (default: closed form up to eps = 1, series
-above; <= 1e-5 relative everywhere), "series_adaptive".
+rewrite), "series" (every row runs the L-term truncated series; rows where that alternating sum is
+ill-conditioned in fp32 -- omega > 4.2 eps, cond > 14 -- are then replaced by the closed form, so the
+result is <= 1e-5 relative on the whole E-set), "series_pure" (the raw fp32 series everywhere: error
+~4 u cond, 6e-5 at omega = 5.66 eps), "auto" (default: closed form up to eps = 1, series above;
+<= 1e-5 relative everywhere), "series_adaptive" (= "series", skipping zero-weight terms).
 ``reference_quirks=True`` builds the CDF table from the reference's literal overflowing expression
 (density zeroed beyond omega > 709 eps^2/pi) so that samples match the reference at
 tiny eps too.  Quirk Q1 (column-0 gather with batched eps) is a plain bug and is not reproduced.

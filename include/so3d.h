@@ -42,10 +42,13 @@ extern "C" {
 #define SO3D_GUIDE_BUCKETS 1024 /* 16-byte records per guide row */
 
 /* evaluator for the IGSO(3) density (mode argument) */
-#define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms                    */
+#define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms per row; rows whose alternating sum is
+                                       ill-conditioned in fp32 (omega > 4.2 eps, eps <= 1: cond > 14) take the closed form
+                                       AFTER their L terms have run -- see kSeriesGuard in csrc/so3d_math.cuh              */
 #define SO3D_MODE_CLOSED 1          /* 3-image closed form, distributions.py:53-72, stable rewrite         */
 #define SO3D_MODE_AUTO 2            /* closed form for eps <= 1, series (live terms only) above             */
 #define SO3D_MODE_SERIES_ADAPTIVE 3 /* series, skipping terms whose fp32 weight is exactly 0 (same result) */
+#define SO3D_MODE_SERIES_PURE 4     /* the raw fp32 series on every row, exactly L terms, no conditioning guard            */
 
 int so3d_version(void);
 const char* so3d_last_error(void);

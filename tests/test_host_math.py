@@ -184,24 +184,45 @@ def test_auto_full_angle_range(hm):
 
 
 def test_series_fp32(hm):
-    """fp32 L=2000 series (character form, Reinsch-Clenshaw recurrence) vs the fp64 series.
-    1e-5 where the alternating sum is well conditioned (omega <= 3.5 eps); beyond that the error
-    of ANY fp32 summation grows with the cancellation (oracle/proto_series_fp32.py), bounded here."""
+    """The raw fp32 L=2000 series (character form, Reinsch-Clenshaw recurrence; mode "series_pure") vs the fp64
+    series.  1e-5 while the alternating sum is well conditioned (cond <= 14: omega <= 4.2 eps, k <= 2.97); beyond
+    that the error of ANY fp32 summation grows like ~4 u cond (oracle/proto_series_fp32.py): measured bounds."""
     n = 6000
     om, eps, k = eset(n, 7)
     om[:20] = 0.0
     k[:20] = 0.0
     F = np.empty(n, np.float32); Fp = np.empty(n, np.float32)
     hm.hm_series(fp(om), fp(eps), fp(F), fp(Fp), ctypes.c_long(n), 2000)
-    ft, gt = O.igso3_series(om.astype(np.float64), eps.astype(np.float64))
+    ft, gt = _truth(om, eps)
     f = 2.0 * F.astype(np.float64)
     g = Fp.astype(np.float64) / F.astype(np.float64)  # hm_series returns dF/dw in its second output
     ef = np.abs(f - ft) / ft
     eg = np.abs(g - gt) / np.maximum(np.abs(gt), 1e-30)
-    well = k <= 2.5
+    well = om <= 4.2 * eps
     assert ef[well].max() < 1e-5 and eg[well & (om > 0)].max() < 1e-5
     assert np.all(g[om == 0] == 0)
-    assert ef[k <= 3.2].max() < 1e-4 and ef.max() < 2e-3
+    assert ef[k <= 3.5].max() < 3e-5 and ef.max() < 2e-4 and eg[om > 0].max() < 2e-4
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+def test_series_guarded_meets_north_star_on_whole_eset(hm, mode):
+    """Modes "series" / "series_adaptive": every row runs its L terms, rows with omega > 4.2 eps (eps <= 1) are then
+    replaced by the closed form -> density AND score <= 1e-5 relative on the whole E-set (k <= 4), and the guard does
+    not touch the rows below it (bit-identical to the raw series there)."""
+    n = 40000
+    om, eps, k = eset(n, 21)
+    om[:50] = 0.0
+    logf = np.empty(n, np.float32); g = np.empty(n, np.float32)
+    hm.hm_logf_g(fp(om), fp(eps), fp(logf), fp(g), ctypes.c_long(n), mode, 2000)
+    ft, gt = _truth(om, eps)
+    assert np.max(np.abs(np.exp(logf.astype(np.float64) - np.log(ft)) - 1)) < 1e-5
+    ok = om > 0
+    assert np.max((np.abs(g - gt) / np.maximum(np.abs(gt), 1e-30))[ok]) < 1e-5
+    lp = np.empty(n, np.float32); gp = np.empty(n, np.float32)
+    hm.hm_logf_g(fp(om), fp(eps), fp(lp), fp(gp), ctypes.c_long(n), 4, 2000)
+    below = om <= 4.2 * eps
+    assert np.array_equal(lp[below], logf[below]) and np.array_equal(gp[below], g[below])
+    assert (~below).mean() > 0.2      # the guard is exercised: ~26 % of the E-set
 
 
 def test_series_short_L(hm):
