@@ -426,7 +426,7 @@ def main():
         # one reverse step WITH the reference's RotPredict denoiser (so3_train.py:11-49) inside the kernel
         # (tcgen05 tf32 3-term split), against the two-kernel route (stock PyTorch MLP + fused step).
         torch.manual_seed(SEED)
-        net = dx.RotPredict().to(device)
+        net = dx.RotPredict(out_type="skewvec").to(device)
         procn = dx.SO3Diffusion(net).to(device)
         procn.row_offset = rank * n
         procn.tables()
@@ -448,7 +448,7 @@ def main():
         if rank == 0:
             try:  # secondary, wall-clock legs built on graph capture: a failure here must not cost the headline line
                 torch.manual_seed(SEED)
-                gnet = dx.RotPredict().to(device)
+                gnet = dx.RotPredict(out_type="skewvec").to(device)
                 gproc = dx.SO3Diffusion(gnet).to(device)
                 loops = {}
                 for mode, use_graph, one_launch in (("eager", False, False), ("cuda_graph", True, False), ("one_launch", True, True)):

@@ -33,18 +33,19 @@ class SinusoidalPosEmb(nn.Module):
 
 
 class RotPredict(nn.Module):
-    """so3_train.py:11-49.  in_type 'rotmat' (9 matrix entries + sinusoidal time features); out_type 'skewvec'
-    (3 outputs).  The 6-D 'rotmat' output head is never selected by the reference's scripts and is
-    not provided."""
+    """so3_train.py:11-49, same constructor defaults.  in_type 'rotmat' (9 matrix entries + sinusoidal time features);
+    out_type 'rotmat' (the reference's default: 6 outputs mapped to a rotation by `six2rmat`, util.py:67-76) or
+    'skewvec' (3 outputs -- what every reference script passes, so3_train.py:60, and the head the fused sampling kernel
+    implements; the 6-D head runs as stock PyTorch)."""
 
-    def __init__(self, d_model=D_MODEL, out_type="skewvec", in_type="rotmat"):
+    def __init__(self, d_model=D_MODEL, out_type="rotmat", in_type="rotmat"):
         super().__init__()
         if in_type != "rotmat":
             raise ValueError("only in_type='rotmat' exists in the reference")
-        if out_type != "skewvec":
-            raise NotImplementedError("out_type='rotmat' (6-D head) is outside the hot path; use 'skewvec'")
+        if out_type not in ("skewvec", "rotmat"):
+            raise RuntimeError(f"Unexpected out_type: {out_type}")  # the reference builds this error but forgets to raise it
         self.in_type, self.out_type = in_type, out_type
-        self.d_out = 3
+        self.d_out = 3 if out_type == "skewvec" else 6
         self.time_embedding = SinusoidalPosEmb(d_model - 9)
         self.net = nn.Sequential(
             nn.Linear(d_model, d_model), nn.SiLU(),
@@ -60,12 +61,17 @@ class RotPredict(nn.Module):
         t_emb = self.time_embedding(t)
         if t_emb.shape[0] == 1:
             t_emb = t_emb.expand(x_flat.shape[0], -1)
-        return self.net(torch.cat((x_flat, t_emb), dim=-1))
+        out = self.net(torch.cat((x_flat, t_emb), dim=-1))
+        if self.out_type == "rotmat":
+            from .util import six2rmat
+
+            out = six2rmat(out)
+        return out
 
     # ---- fused sampling path ------------------------------------------------------------------
     def fusable(self):
         lin = self.net[0]
-        return lin.in_features == D_MODEL and lin.weight.is_cuda and lin.weight.dtype == torch.float32
+        return self.out_type == "skewvec" and lin.in_features == D_MODEL and lin.weight.is_cuda and lin.weight.dtype == torch.float32
 
     def _linears(self):
         return [self.net[i] for i in (0, 2, 4, 6, 8)]

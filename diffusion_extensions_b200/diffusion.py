@@ -92,17 +92,19 @@ class SO3Diffusion(nn.Module):
         self.row_offset = 0
         self.fuse_denoiser = True  # p_sample runs a RotPredict denoiser inside the reverse-step kernel when it can
         self.fused_loop = True       # p_sample_loop(cuda_graph=True) with a fusable RotPredict: all T steps in ONE launch
-        self._tables = {}  # device -> (fwd_cdf, post_cdf, t_range)
-        self._guides = {}  # device -> (fwd_guide, post_guide)
+        self._tables = {}  # schedule key -> (fwd_cdf, post_cdf, t_range)
+        self._guides = {}  # schedule key -> (fwd_guide, post_guide)
 
     # ---- per-schedule CDF tables -----------------------------------------------------------------
     def tables(self):
         """(fwd_cdf (T,999) for eps_t = sqrt(1-abar_t),  post_cdf (T,999) for sigma_t,  arange(T))."""
         dev = self.betas.device
-        key = str(dev)
+        key = self._schedule_key()
         if key not in self._tables:
             if dev.type != "cuda":
                 raise RuntimeError("SO3Diffusion must be moved to a CUDA device (.to('cuda')); there is no CPU path")
+            self._tables.clear()  # a stale schedule's tables (load_state_dict / in-place edits / .to()) are dropped, not kept
+            self._guides.clear()
             fwd = ops.igso3_cdf_table(self.sqrt_one_minus_alphas_cumprod, self.reference_quirks)
             sigma = (0.5 * self.posterior_log_variance_clipped).exp()  # diffusion.py:324
             post = ops.igso3_cdf_table(sigma, self.reference_quirks)
@@ -110,10 +112,17 @@ class SO3Diffusion(nn.Module):
             self._guides[key] = (ops.igso3_cdf_guide(fwd), ops.igso3_cdf_guide(post))
         return self._tables[key]
 
+    def _schedule_key(self):
+        """Identity of the buffers the CDF tables are derived from: device, storage and in-place version counter.
+        `load_state_dict` (copy_ into the buffers), in-place assignment and `.to(device)` all change it, so q_sample /
+        p_sample can never draw noise from the tables of a schedule that is no longer the module's."""
+        a, b = self.sqrt_one_minus_alphas_cumprod, self.posterior_log_variance_clipped
+        return (str(a.device), a.data_ptr(), a._version, b.data_ptr(), b._version, bool(self.reference_quirks))
+
     def guides(self):
         """(fwd_guide, post_guide): the (T, 1024, 4) search records of the two CDF tables."""
         self.tables()
-        return self._guides[str(self.betas.device)]
+        return self._guides[self._schedule_key()]
 
     # ---- forward process ----------------------------------------------------------------------
     def q_mean_variance(self, x_start, t):
@@ -290,7 +299,10 @@ class SO3Diffusion(nn.Module):
             return ops.rotpredict_p_sample_loop(x, probe[0], probe[1], self.num_timesteps - 1, 0, *self._sched4(), self.tables()[1], mixed,
                                                 row_offset=self.row_offset)
         packed_key = fn._packed[0] if probe is not None else None
-        key = (tuple(x.shape), str(dev), id(fn), packed_key, self.row_offset, bool(self.fuse_denoiser), self.num_timesteps)
+        # everything the captured launches bake in: shapes, the denoiser object and its train/eval mode, the packed weights,
+        # the projection closure of the Projected* classes (aircraft_test.py:73 sets a new one per item), the schedule
+        key = (tuple(x.shape), str(dev), id(fn), bool(getattr(fn, "training", False)), packed_key, id(self.__dict__.get("projection")),
+               self.row_offset, bool(self.fuse_denoiser), self.num_timesteps, self._schedule_key())
         cache = self.__dict__.setdefault("_loop_graphs", {})
         ent = cache.get(key)
         if ent is None:
@@ -307,9 +319,9 @@ class SO3Diffusion(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     x_out = self._seeded_steps(x_in, seed_buf)
-            ent = (graph, x_in, seed_buf, x_out, probe)                 # probe keeps the packed weights alive
+            ent = (graph, x_in, seed_buf, x_out, probe, self.__dict__.get("projection"))  # keeps packed weights / the projection alive (ids stay unique)
             cache[key] = ent
-        graph, x_in, seed_buf, x_out, _ = ent
+        graph, x_in, seed_buf, x_out = ent[:4]
         seed, off = ops.rng.next()
         mixed = (seed + 0x9E3779B97F4A7C15 * (off + 1)) & 0xFFFFFFFFFFFFFFFF
         seed_buf.fill_(mixed - (1 << 64) if mixed >= (1 << 63) else mixed)
@@ -420,7 +432,7 @@ class SE3Diffusion(SO3Diffusion):
         self.shift_scale = shift_scale
 
     def _sigma(self):
-        key = str(self.betas.device)
+        key = self._schedule_key()
         if getattr(self, "_sigma_cache", None) is None or self._sigma_cache[0] != key:
             self._sigma_cache = (key, (0.5 * self.posterior_log_variance_clipped).exp().contiguous())  # diffusion.py:481
         return self._sigma_cache[1]

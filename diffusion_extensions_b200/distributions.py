@@ -92,6 +92,10 @@ class IsotropicGaussianSO3(Distribution):
         u / axes: optional explicit uniforms / (un-normalised) axes, for reproducing given draws."""
         sample_shape = tuple(sample_shape)
         shape = sample_shape + tuple(self.eps.shape)
+        if self._mean is not None and self._mean.dim() > 2:
+            # a batched mean broadcasts against the noise like the reference's `self._mean @ rotations`
+            # (distributions.py:50; e.g. IGSO3xR3(eps=sigma[0], mean=model_mean).sample() at diffusion.py:482 -> (B,3,3))
+            shape = tuple(torch.broadcast_shapes(shape, self._mean.shape[:-2]))
         if self.eps.dim() == 0:
             row_idx, row = None, 0
         else:
@@ -202,16 +206,24 @@ class Bingham(MultivariateNormal):
         st = self._unbroadcasted_scale_tril
         return st.is_cuda and st.dtype == torch.float32 and st.shape == (4, 4) and not (torch.is_grad_enabled() and st.requires_grad)
 
+    def _require_cuda(self):
+        if not self._unbroadcasted_scale_tril.is_cuda:
+            raise RuntimeError("Bingham: the covariance must live on a CUDA device; this package has no CPU path "
+                               "(the reference pins bingham_train.py to the CPU generator, bingham_train.py:52)")
+
     def rsample(self, sample_shape=torch.Size(), *, z=None):
+        self._require_cuda()
         if self._fused():
             shape = tuple(sample_shape) + tuple(self.batch_shape)
             return ops.bingham_sample(self._unbroadcasted_scale_tril, shape, z=z, row_offset=self.row_offset)
+        # batched covariances / gradients w.r.t. the covariance (reparameterised sample): torch ops ON THE DEVICE
         vals = super().rsample(sample_shape)
         return vals / vals.norm(dim=-1, keepdim=True)
 
     @torch.no_grad()
     def sample_rmat(self, sample_shape=torch.Size(), *, z=None):
         """quat_to_rmat(self.sample(sample_shape)) in one launch: (*sample_shape, 3, 3)."""
+        self._require_cuda()
         if not self._fused():
             from .util import quat_to_rmat
 

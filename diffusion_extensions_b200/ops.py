@@ -20,23 +20,48 @@ GUIDE_BUCKETS = 1024  # 16-byte records per guide row (include/so3d.h SO3D_GUIDE
 # counter-based RNG state (Philox key/offset), following torch.manual_seed like a torch op would
 # ---------------------------------------------------------------------------------------------
 class _Rng:
+    """(seed, offset) of every sampling launch.
+
+    Two regimes:
+      * after ``dx.manual_seed(s)``: an explicit stream -- seed s, offsets 0, 1, 2, ... (one per launch) -- until
+        ``torch.manual_seed`` installs a different seed;
+      * otherwise the launches FOLLOW TORCH'S CUDA GENERATOR like any torch op: the seed is the generator's seed and
+        the offset is its Philox offset, which the launch advances by 4 (one Philox block per row).  ``torch.manual_seed(s)``
+        therefore resets the stream even when s equals the previous seed (the usual way to reproduce a run), and the
+        draws interleave deterministically with torch's own random ops.
+    While a CUDA graph is being captured the generator's offset cannot be touched from the host; captured launches read
+    their seed from device memory instead (`use_device_seed`, `*_dseed_f32`) and never come through here."""
+
     def __init__(self):
         self.seed = None
         self.offset = 0
         self._torch_seed = None
+        self._explicit = False
 
     def manual_seed(self, seed):
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.offset = 0
         self._torch_seed = torch.initial_seed()
+        self._explicit = True
 
-    def next(self):
+    def next(self, device=None):
         """(seed, offset) for one sampling launch; every launch gets a fresh offset."""
         ts = torch.initial_seed()
-        if self.seed is None or ts != self._torch_seed:  # torch.manual_seed() was called since
-            self.seed = ts & 0xFFFFFFFFFFFFFFFF
-            self.offset = 0
-            self._torch_seed = ts
+        if self._explicit and ts == self._torch_seed:
+            off = self.offset
+            self.offset += 1
+            return self.seed, off
+        self._explicit = False
+        if torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
+            idx = torch.cuda.current_device() if device is None or torch.device(device).index is None else torch.device(device).index
+            gen = torch.cuda.default_generators[idx]
+            off = int(gen.get_offset())
+            gen.set_offset(off + 4)
+            self.seed, self.offset, self._torch_seed = int(gen.initial_seed()) & 0xFFFFFFFFFFFFFFFF, off // 4 + 1, ts
+            return self.seed, off // 4
+        # no CUDA generator to follow (CPU-only unit tests of the host logic) or inside a capture: private counter
+        if self.seed is None or ts != self._torch_seed:
+            self.seed, self.offset, self._torch_seed = ts & 0xFFFFFFFFFFFFFFFF, 0, ts
         off = self.offset
         self.offset += 1
         return self.seed, off
@@ -46,7 +71,8 @@ rng = _Rng()
 
 
 def manual_seed(seed):
-    """Seed the Philox stream used by the sampling kernels (torch.manual_seed also resets it)."""
+    """Seed an explicit Philox stream for the sampling kernels (offsets 0, 1, 2, ... per launch).  Without it the
+    kernels follow torch's CUDA generator, so ``torch.manual_seed(s)`` -- with a new OR the same s -- resets them too."""
     rng.manual_seed(seed)
 
 

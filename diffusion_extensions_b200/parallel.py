@@ -223,16 +223,43 @@ def sample_sharded(process, n_global, init="igso3_1", steps=None):
     return x
 
 
-def train_step_sharded(process, x0_local, optimizer):
+def _step_indices(process, n_global, lo, hi, device):
+    """The step index of every GLOBAL row, drawn identically on all ranks from a generator private to `process`
+    (seeded from torch's seed at first use), then sliced to this rank's shard: t of a row does not depend on how the
+    batch is partitioned, and ranks seeded alike stay in lock-step without consuming torch's default stream."""
+    gen = process.__dict__.get("_t_generator")
+    if gen is None or gen.device != torch.device(device):
+        gen = torch.Generator(device=device)
+        gen.manual_seed(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        process.__dict__["_t_generator"] = gen
+    t = torch.randint(0, process.num_timesteps, (n_global,), device=device, generator=gen)
+    return t[lo:hi]
+
+
+def train_step_sharded(process, x0_local, optimizer, n_global=None):
     """One data-parallel training step on this rank's shard: fused noising + target, denoiser forward/backward
-    (DDP all-reduces the gradients), optimizer step; returns the GLOBAL mean loss (one 2-float all-reduce)."""
-    optimizer.zero_grad(set_to_none=True)
+    (DDP all-reduces the gradients), optimizer step; returns the GLOBAL mean loss (one 2-float all-reduce).
+
+    The shard is placed in the global batch here (no separate `attach()` call to forget): `n_global` rows split by
+    `shard_bounds`; without it the shards are taken to be equal (n_global = world x local rows), which is checked.
+    Noise is keyed by the global row index (`process.row_offset`) and t is drawn per GLOBAL row, so the step's draws are
+    the same for any world size.  With ragged shards DDP's plain average of per-rank gradients is not the global-mean
+    gradient; the local loss is therefore weighted by b_local x world / n_global, which makes it exact."""
+    rank, world = world_info()
     b = x0_local.shape[0]
-    t = torch.randint(0, process.num_timesteps, (b,), device=x0_local.device)
+    if n_global is None:
+        n_global = world * b
+    lo, hi = shard_bounds(n_global, rank, world)
+    if hi - lo != b:
+        raise ValueError(f"rank {rank}: shard has {b} rows but rows [{lo}, {hi}) of a {n_global}-row batch are expected "
+                         "(pass n_global for ragged shards; equal shards otherwise)")
+    process.row_offset = lo
+    optimizer.zero_grad(set_to_none=True)
+    t = _step_indices(process, n_global, lo, hi, x0_local.device)
     fused = process.noise_and_target(x0_local, t)
     pred = process.denoise_fn(fused["x_t"], t)
     sq = (pred - fused["target"]) ** 2
-    loss = sq.mean()  # DDP averages gradients over ranks: equal shard sizes give the global-mean gradient
+    loss = sq.mean() * (b * world / n_global)  # == sq.mean() for equal shards
     loss.backward()
     optimizer.step()
     return global_loss(sq.detach())

@@ -12,6 +12,7 @@ Deliberate deviations from the reference:
     (0,0,1) with angle 0 at the identity instead of NaN (Q10).
 """
 import inspect
+from collections import namedtuple
 from itertools import product
 from math import log
 from typing import Iterable, Tuple
@@ -54,6 +55,15 @@ class AffineT(object):
 
     def detach(self):
         return AffineT(self.rot.detach(), self.shift.detach())
+
+    def clone(self):
+        """(not in the reference) a deep copy: what graph-captured steps use for their static input"""
+        return AffineT(self.rot.clone(), self.shift.clone())
+
+    def copy_(self, other):
+        self.rot.copy_(other.rot)
+        self.shift.copy_(other.shift)
+        return self
 
 
 class AffineGrad(object):
@@ -383,14 +393,23 @@ __all__ = [
 
 
 # ---------------------------------------------------------------------------------------------
-# small helpers the reference's scripts import from util (util.py:426-481)
+# small helpers the reference's scripts import from util (util.py:59, 426-481).  REFERENCE-DERIVED API SHIMS, not part
+# of the hot path: `from util import *` in the reference's scripts pulls these names in, so they are restated here
+# (same names, arguments and behaviour; plain host-side Python, no kernels).  The same holds for the `AffineT` /
+# `AffineGrad` containers at the top of this file (util.py:10-56): their attribute surface IS the interface.
 # ---------------------------------------------------------------------------------------------
+ProtData = namedtuple("ProtData", ["residues", "positions", "angles"])  # util.py:59 (the docking scripts' batch record)
+
+
 def to_device(device, *objects, non_blocking=False):
-    """util.py:426-437: move tensors / AffineT / nested iterables of them to `device`, keeping the structure."""
+    """util.py:426-437: move tensors / AffineT / ProtData / nested iterables of them to `device`, keeping the structure
+    (a ProtData comes back as a ProtData, like the reference)."""
     out = []
     for obj in objects:
         if isinstance(obj, (torch.Tensor, AffineT)):
             out.append(obj.to(device, non_blocking=non_blocking) if isinstance(obj, torch.Tensor) else obj.to(device))
+        elif isinstance(obj, ProtData):
+            out.append(ProtData(*to_device(device, *obj, non_blocking=non_blocking)))
         elif isinstance(obj, Iterable) and not isinstance(obj, (str, bytes)):
             out.append(to_device(device, *obj, non_blocking=non_blocking))
         else:

@@ -200,6 +200,7 @@ def main_se3():
     t = torch.randint(0, 1000, (B,), generator=g)
     t[:4] = torch.tensor([0, 1, 998, 999])
     eps_t = bufs["sqrt_one_minus_alphas_cumprod"][t]
+    torch.manual_seed(4322)  # the reference's sampler draws from the GLOBAL generators (distributions.py:35,38): seed them, so the fixture regenerates bit for bit
     noise_rot = torch.stack([rdist.IsotropicGaussianSO3(e).sample()[0] for e in eps_t])
     z = torch.randn(B, 3, generator=g)
     noise = rutil.AffineT(noise_rot, z * (eps_t * ss)[:, None])

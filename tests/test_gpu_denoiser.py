@@ -29,7 +29,7 @@ def dx(cuda_device):
 
 
 def golden_net(dx, g, device):
-    net = dx.RotPredict()
+    net = dx.RotPredict(out_type="skewvec")
     net.load_state_dict({f"net.{i}.{k}": torch.as_tensor(g[f"net_{i}_{k}"]) for i in LAYERS for k in ("weight", "bias")})
     return net.to(device)
 
@@ -62,7 +62,7 @@ def forward64_same_features(net, x, tval):
 def test_state_dict_names_match_reference(dx, golden):
     g = golden("rotpredict")
     want = {f"net.{i}.{k}" for i in LAYERS for k in ("weight", "bias")}
-    assert set(dx.RotPredict().state_dict().keys()) == want
+    assert set(dx.RotPredict(out_type="skewvec").state_dict().keys()) == want
     assert {k.replace("_", ".", 2) for k in g if k.startswith("net_")} == want
 
 
@@ -104,7 +104,7 @@ def test_fused_prediction_against_fp64(dx, cuda_device, n):
     """Ragged and multi-tile sizes, large-ish weights (activations of size ~3): the tf32 hi/lo split must hold
     fp32-level accuracy (<= 1e-5 abs) against an fp64 forward given the same time features."""
     torch.manual_seed(n)
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     with torch.no_grad():
         for p in net.parameters():
             p.mul_(3.0)
@@ -123,7 +123,7 @@ def test_fused_step_equals_step_algebra_on_its_own_prediction(dx, cuda_device):
     noise switched off), <= 1e-5 rad."""
     torch.manual_seed(3)
     n = 3000
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     with torch.no_grad():
         for p in net.parameters():
             p.mul_(2.0)
@@ -143,7 +143,7 @@ def test_fused_p_sample_matches_two_kernel_route(dx, cuda_device):
     Philox draws, predictions equal to ~1e-6, so samples agree to <= 1e-5 rad geodesic; t = 0 adds no noise."""
     torch.manual_seed(5)
     n = 5000
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     with torch.no_grad():
         for p in net.parameters():
             p.mul_(2.0)
@@ -173,7 +173,7 @@ def test_fused_draws_are_shard_invariant(dx, cuda_device):
     """row_offset makes a shard's draws those of the same global rows."""
     torch.manual_seed(9)
     n = 2048
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     proc = dx.SO3Diffusion(net).to(cuda_device)
     _, post, _ = proc.tables()
     x = dx.ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device))
@@ -189,7 +189,7 @@ def test_fused_draws_are_shard_invariant(dx, cuda_device):
 
 def test_packed_weights_follow_parameter_updates(dx, cuda_device):
     torch.manual_seed(1)
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     proc = dx.SO3Diffusion(net).to(cuda_device)
     x = dx.ops.quat_to_rmat(torch.randn(256, 4, device=cuda_device))
     p0 = fused_pred(dx, proc, net, x, 100)
@@ -202,7 +202,7 @@ def test_packed_weights_follow_parameter_updates(dx, cuda_device):
 def test_p_sample_loop_with_fused_denoiser(dx, cuda_device):
     """so3_test.py:24-33: the full reverse loop (shortened schedule) stays on SO(3) and is reproducible."""
     torch.manual_seed(2)
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     proc = dx.SO3Diffusion(net, timesteps=50).to(cuda_device)
     dx.ops.manual_seed(21)
     a = proc.p_sample_loop((512,))
@@ -224,7 +224,7 @@ def test_p_sample_loop_as_cuda_graph(dx, cuda_device, route):
     torch.manual_seed(3)
     T, n = 40, 700
     fuse = route != "graph_stock"
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     proc = dx.SO3Diffusion(net, timesteps=T).to(cuda_device)
     proc.fuse_denoiser = fuse
     proc.fused_loop = route == "one_launch"
@@ -263,7 +263,7 @@ def test_p_sample_loop_as_cuda_graph(dx, cuda_device, route):
 
 
 def test_errors(dx, cuda_device):
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     proc = dx.SO3Diffusion(net).to(cuda_device)
     x = dx.ops.quat_to_rmat(torch.randn(8, 4, device=cuda_device))
     blob, c1 = net.packed(proc.num_timesteps)
@@ -272,5 +272,12 @@ def test_errors(dx, cuda_device):
         dx.ops.rotpredict_p_sample_fused(x, blob, c1, torch.zeros(8, dtype=torch.int64, device=cuda_device), *args)
     with pytest.raises(ValueError):
         dx.ops.rotpredict_p_sample_fused(x, blob[:-1], c1, torch.zeros(1, dtype=torch.int64, device=cuda_device), *args)
-    with pytest.raises(NotImplementedError):
-        dx.RotPredict(out_type="rotmat")
+    # the reference's default head (6-D -> six2rmat, so3_train.py:12,46-47) runs as stock PyTorch and is never fused
+    rm = dx.RotPredict().to(cuda_device)
+    assert rm.out_type == "rotmat" and rm.d_out == 6 and not rm.fusable()
+    out = rm(x, torch.zeros(8, dtype=torch.int64, device=cuda_device))
+    assert out.shape == (8, 3, 3)
+    eye = torch.eye(3, device=cuda_device).expand(8, 3, 3)
+    assert torch.allclose(out @ out.transpose(-1, -2), eye, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        dx.RotPredict(out_type="euler")

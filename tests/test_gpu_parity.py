@@ -752,7 +752,7 @@ def test_device_seed_and_graphed_train_step(dx, cuda_device):
         assert torch.equal(out["x_t"], ref["x_t"]) and torch.equal(out["target"], ref["target"])
     # the reference's toy problem (so3_train.py:65-76): two-point target, RotPredict, Adam -- as one graph per step
     torch.manual_seed(0)
-    net = dx.RotPredict().to(cuda_device)
+    net = dx.RotPredict(out_type="skewvec").to(cuda_device)
     proc = dx.SO3Diffusion(net).to(cuda_device)
     opt = torch.optim.Adam(net.parameters(), lr=3e-3, capturable=True)
     z90 = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], device=cuda_device)

@@ -113,6 +113,50 @@ def _worker(rank, world, port, n, tmp):
     cover = sorted(tp for sh in range(world) for tp in P.pair_tiles_of_shard(len(A), len(B), sh, world))
     assert cover == sorted(P.pair_tiles_of_shard(len(A), len(B), 0, 1))
 
+    # ---- train_step_sharded places the shard itself (row_offset, per-GLOBAL-row t) and, with ragged shards, weights the
+    # local loss so that DDP's plain average is the global-mean gradient.  Stand-in process: the fused noising launch is
+    # replaced by a CPU function of (global row, t), everything else is the real host logic.
+    class FakeProcess:
+        num_timesteps = 1000
+        row_offset = -1
+
+        def __init__(self, fn):
+            self.denoise_fn, self.seen = fn, None
+
+        def noise_and_target(self, x0, t):
+            rows = torch.arange(self.row_offset, self.row_offset + x0.shape[0], dtype=torch.float32)
+            self.seen = (self.row_offset, t.clone())
+            return {"x_t": x0 + 0.001 * t[:, None].float(), "target": torch.sin(rows)[:, None] * torch.ones(1, 3)}
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(3, 3)
+
+        def forward(self, xx, tt):
+            return self.lin(xx)
+
+    torch.manual_seed(3)
+    netd, netr = Net(), Net()
+    netr.load_state_dict(netd.state_dict())
+    fp_ = FakeProcess(P.wrap_denoiser(netd))
+    opt = torch.optim.SGD(fp_.denoise_fn.parameters(), lr=0.0)
+    loss = P.train_step_sharded(fp_, x[lo2:hi2], opt, n_global=n)
+    assert fp_.row_offset == lo2 and fp_.seen[0] == lo2
+    single = FakeProcess(netr)
+    single.row_offset = 0
+    gen = torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+    t_all = torch.randint(0, 1000, (n,), generator=gen)
+    assert torch.equal(fp_.seen[1], t_all[lo2:hi2])            # t of a row does not depend on the partition
+    out = single.noise_and_target(x, t_all)
+    sq = (netr(out["x_t"], t_all) - out["target"]) ** 2
+    sq.mean().backward()
+    assert abs(float(loss) - float(sq.mean())) < 1e-6
+    for pa, pb in zip(netd.parameters(), netr.parameters()):    # ragged shards (n = 1001): still the global-mean gradient
+        assert torch.allclose(pa.grad, pb.grad, atol=1e-6)
+    with pytest.raises(ValueError):
+        P.train_step_sharded(fp_, x[: (hi2 - lo2) + 1], opt, n_global=n)
+
     # ---- attach(): row_offset bookkeeping on a stand-in process object
     class Proc:
         row_offset = 0

@@ -11,7 +11,7 @@ from diffusion_extensions_b200 import ops
 
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
-net = dx.RotPredict().to(dev)
+net = dx.RotPredict(out_type="skewvec").to(dev)
 proc = dx.SO3Diffusion(net).to(dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 x = ops.quat_to_rmat(torch.randn(n, 4, device=dev))
@@ -21,7 +21,7 @@ for tval in (500, 0, 999):
     pred = ops.rotpredict_p_sample_fused(x, blob, c1, t, proc.sqrt_recip_alphas_cumprod, proc.sqrt_recipm1_alphas_cumprod,
                                          proc.posterior_mean_coef1, proc.posterior_mean_coef2, want_out=False, want_pred=True)
     torch.cuda.synchronize()
-    net64 = dx.RotPredict().double()
+    net64 = dx.RotPredict(out_type="skewvec").double()
     net64.load_state_dict({k: v.double().cpu() for k, v in net.state_dict().items()})
     ref = net64(x.double().cpu(), t.cpu().expand(n)).detach()
     ref32 = net(x, t.expand(n)).detach().cpu().double()

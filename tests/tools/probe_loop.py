@@ -12,7 +12,7 @@ import diffusion_extensions_b200 as dx
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-net = dx.RotPredict().to(dev)
+net = dx.RotPredict(out_type="skewvec").to(dev)
 proc = dx.SO3Diffusion(net).to(dev)
 for n in (1024, 20000, 1 << 18, 1 << 22):
     for fuse in (True, False):

@@ -23,7 +23,7 @@ torch.manual_seed(0)
 
 
 def gpu_leg(B, graph):
-    net = dx.RotPredict().to(dev)
+    net = dx.RotPredict(out_type="skewvec").to(dev)
     proc = dx.SO3Diffusion(net).to(dev)
     proc.tables(); proc.guides()
     opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=graph)
@@ -74,7 +74,7 @@ if "--cpu" in sys.argv:
     from oracle import ref_port as P
 
     torch.set_num_threads(os.cpu_count() or 1)
-    net = dx.RotPredict()
+    net = dx.RotPredict(out_type="skewvec")
     port = P.SO3DiffusionPort(net)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     B = 256

@@ -15,11 +15,11 @@ torch.manual_seed(0)
 n = 5000
 q = torch.randn(n, 4)
 pred = torch.randn(n, 3) * 0.3
-net_cpu = dx.RotPredict()
+net_cpu = dx.RotPredict(out_type="skewvec")
 outs = []
 for d in (0, 1, 0):
     dev = torch.device("cuda", d)
-    net = dx.RotPredict().to(dev)
+    net = dx.RotPredict(out_type="skewvec").to(dev)
     net.load_state_dict(net_cpu.state_dict())
     proc = dx.SO3Diffusion(net).to(dev)
     x = ops.quat_to_rmat(q.to(dev))
