@@ -157,20 +157,41 @@ class SO3Diffusion(nn.Module):
             self._device_seed = torch.full((1,), mixed, dtype=torch.int64, device=dev)
         return self._device_seed
 
-    def make_graphed_train_step(self, optimizer, example_x, warmup=3):
+    def make_graphed_train_step(self, optimizer, example_x, warmup=3, sync_grads=None):
         """so3_train.py:70-76 / bingham_train.py:88-95 as ONE CUDA graph: `loss = self(x); loss.backward(); optimizer.step()`
         is captured once for batches shaped like `example_x` (the optimizer must be constructed with capturable=True) and
         the returned `step(x) -> loss` copies x into the graph's input and replays it.  At the reference's batch sizes the
         eager step is launch-bound (~50 launches, 1.05 ms); the replay takes 0.18 ms at batch 256 (tests/tools/probe_train.py).
-        Noise comes from the device-resident seed (use_device_seed), step indices from torch's graph-safe generator."""
+        Noise comes from the device-resident seed (use_device_seed), step indices from torch's graph-safe generator.
+
+        Data-parallel training (BASELINE cfg 4): with `sync_grads` (default: a process group with more than one rank is
+        initialised) the gradients are flattened into ONE bucket, all-reduced over the ranks by a captured NCCL launch and
+        averaged before the optimizer step -- what DistributedDataParallel does with its hooks, but inside the graph, so
+        a replay is still one host call.  The denoiser must then be the bare module (not a DDP wrapper), initialised
+        identically on every rank; every rank must use its own `row_offset`."""
+        import torch.distributed as dist
+
+        if sync_grads is None:
+            sync_grads = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        world = dist.get_world_size() if sync_grads else 1
         self.use_device_seed()
         static_x = example_x.detach().clone()
         dev = static_x.device
+        params = [p for group in optimizer.param_groups for p in group["params"]]
 
         def one():
             optimizer.zero_grad(set_to_none=True)
             loss = self(static_x)
             loss.backward()
+            if sync_grads:
+                live = [p for p in params if p.grad is not None]
+                flat = torch.cat([p.grad.reshape(-1) for p in live])
+                dist.all_reduce(flat)                                   # captured: one bucket, one NCCL launch
+                flat.mul_(1.0 / world)
+                off = 0
+                for p in live:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                    off += p.numel()
             optimizer.step()
             return loss
 
@@ -191,7 +212,7 @@ class SO3Diffusion(nn.Module):
             graph.replay()
             return static_loss
 
-        step.graph, step.static_x = graph, static_x
+        step.graph, step.static_x, step.sync_grads = graph, static_x, bool(sync_grads)
         return step
 
     def noise_and_target(self, x_start, t, want_noise=False, want_score=False):

@@ -5,8 +5,10 @@ op for op -- torch.matrix_exp for exponentials, SVD re-orthogonalisation, the fp
 density over a (1000, B) grid rebuilt on every call, the compare-and-sum CDF search, autograd for
 the score -- so that timing it on the host cores reproduces what running the reference's CPU path
 costs (the reference itself cannot travel to the GPU box).  It is used only by
-``bench.py`` (``cpu_baseline`` and ``--impl reference``) and by ``tests/test_ref_port.py``, which pins
-it against the golden vectors generated from the real reference.  Never imported by the product.
+``bench.py`` (``cpu_baseline``, ``--impl reference`` and the same-box ``torch_cuda_eager`` legs, where the very same
+op sequence runs on ``cuda`` tensors -- what "running the reference on the B200" would dispatch) and by
+``tests/test_ref_port.py``, which pins it against the golden vectors generated from the real reference.
+Never imported by the product.
 
 Citations are file:line of qazwsxal/diffusion-extensions @ f100885d.
 """
@@ -99,7 +101,7 @@ class IGSO3:
     def sample(self, shape=()):  # distributions.py:33-51 (per-row gather: the intended behaviour, not bug Q1)
         axes = torch.randn((*shape, *self.eps.shape, 3)).to(self.eps)
         axes = axes / axes.norm(dim=-1, keepdim=True)
-        u = torch.rand((*shape, *self.eps.shape))
+        u = torch.rand((*shape, *self.eps.shape), device=self.trap.device)  # distributions.py:38: on the table's device
         i1 = (self.trap <= u[None, ...]).sum(dim=0)
         i0 = torch.clamp(i1 - 1, min=0)
         trap = self.trap if self.trap.dim() == u.dim() + 1 else self.trap.reshape(999, *([1] * u.dim()))
@@ -148,12 +150,12 @@ def cosine_betas(T, s=0.008):  # denoising_diffusion_pytorch.py:278-288
 class SO3DiffusionPort:
     """diffusion.py:280-374, stock CPU path."""
 
-    def __init__(self, denoise_fn, T=1000):
+    def __init__(self, denoise_fn, T=1000, device="cpu"):
         b = cosine_betas(T)
         a = 1.0 - b
         ac = np.cumprod(a)
         acp = np.append(1.0, ac[:-1])
-        f = lambda x: torch.tensor(x, dtype=torch.float32)
+        f = lambda x: torch.tensor(x, dtype=torch.float32, device=device)  # (the reference's registered buffers after .to(device))
         self.T = T
         self.denoise_fn = denoise_fn
         self.sqrt_ac, self.sqrt_1m_ac = f(np.sqrt(ac)), f(np.sqrt(1 - ac))

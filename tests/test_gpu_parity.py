@@ -611,6 +611,37 @@ def test_full_size_properties(dx, cuda_device):
     assert ((score - g[:, None] * axis).norm(dim=-1)).max().item() < 1e-6 * g.abs().max().item()
 
 
+def test_logp_score_at_2pow28_rows_with_64bit_offsets(dx, cuda_device):
+    """BASELINE config[1]'s largest size: 2^28 rotations in ONE launch (9.7 GB of matrices: element offsets beyond 2^31,
+    byte offsets beyond 2^33).  The E-set is built on the device (itself a 2^28-row aa_to_rmat launch); a strided sample
+    of the results -- including the very last rows -- is compared with the fp64 oracle at the north-star tolerance, for
+    the HBM-bound `auto` evaluator and for the L = 2000 series."""
+    n = 1 << 28
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    if free < 60e9:
+        pytest.skip("needs ~30 GB of free device memory")
+    g = torch.Generator(device=cuda_device).manual_seed(2028)
+    eps = torch.exp(torch.empty(n, device=cuda_device).uniform_(math.log(6.4e-3), 0.0, generator=g))
+    k = torch.empty(n, device=cuda_device).uniform_(0.0, 4.0, generator=g)
+    omega = torch.clamp(eps * math.sqrt(2.0) * k, max=3.0)
+    del k
+    axis = torch.randn(n, 3, device=cuda_device, generator=g)
+    R = dx.ops.aa_to_rmat(axis, omega)
+    del axis, omega
+    idx = torch.cat([torch.arange(0, n, n // 8192, device=cuda_device), torch.arange(n - 4096, n, device=cuda_device)])
+    Rs, es = R[idx].cpu().numpy(), eps[idx].cpu().numpy()
+    om, ax, ft, gt = truth_from_R(Rs, es)
+    for mode in ("auto", "series"):
+        logp, score, _ = dx.ops.igso3_logp_score(R, eps, mode=mode, L=2000)
+        lp, sc = host(logp[idx]), host(score[idx])
+        del logp, score
+        assert np.max(np.abs(np.exp(lp - np.log(ft)) - 1)) < 1e-5, mode
+        gk = (sc * ax).sum(-1)
+        assert np.max((np.abs(gk - gt) / np.maximum(np.abs(gt), 1e-30))[om > 1e-4]) < 1e-5, mode
+    del R, eps
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------------
 # sharding invariance, guide tables, host-buffer pipeline
 # ---------------------------------------------------------------------------------------------
