@@ -548,7 +548,7 @@ def main():
             try:
                 def one_launch():
                     dx.ops.p_sample_loop_fused(la, None, 999, 0, proc.sqrt_recip_alphas_cumprod, proc.sqrt_recipm1_alphas_cumprod, proc.posterior_mean_coef1,
-                                               proc.posterior_mean_coef2, post, seed=SEED, rng_offset=1000, row_offset=rank * n_loop, out=lb)
+                                               proc.posterior_mean_coef2, post, post_guide, seed=SEED, rng_offset=1000, row_offset=rank * n_loop, out=lb)
 
                 m1 = time_loop(one_launch, 1, 1, dist_on)
                 v1 = world * n_loop * 1000 / (m1 * 1e-3)

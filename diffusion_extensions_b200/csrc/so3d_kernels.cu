@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel_ct
     mbar_init(&bars[1], 1);
     fence_barrier_init();
   }
+  __syncthreads();  // barrier objects exist for every thread (and for compute-sanitizer's racecheck, which otherwise
+                    // reports thread 0's own init -> expect_tx sequence as a hazard); costs nothing at kernel start
 
   // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
   // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
     released[1] = 0;
     fence_barrier_init();
   }
+  __syncthreads();  // see rowwise_kernel_cta
 
   // Tile k of this CTA starts at row first_row + k stride_rows.  Only the globally last tile can be ragged, and it is
   // the last tile of the CTA that owns it, so "tile k is full" is the 32-bit test k < my_full and the row index is

@@ -521,6 +521,21 @@ SO3D_HD Quat p_mean_quat(const Mat3& x_t, Vec3 pred, float a, float b, float c1,
   return qmul(q3, q4);
 }
 
+// The same step with pred = 0 (no denoiser / zero score: so3d_p_sample_loop_f32 with pred3 == NULL): exp(0) is the identity
+// quaternion (1, 0, 0, 0) and q1 (x) (1, 0, 0, 0) = q1 exactly in floating point, so skipping the product gives the
+// bits p_mean_quat() produces for pred = (0, 0, 0) (up to the sign of zero components, which no later operation sees).
+SO3D_HD Quat p_mean_quat_nopred(const Mat3& x_t, float a, float c1, float c2, Quat* x0h) {
+  const AxisAngleF ax = axis_angle_fast(x_t);
+  const Quat qh = quat_axis_angle(ax.axis, a * ax.theta);
+  Vec3 n0;
+  float h0;
+  quat_axis_halfangle(qh, &n0, &h0);
+  const Quat q3 = quat_axis_angle(n0, 2.0f * c1 * h0);
+  const Quat q4 = quat_axis_angle(ax.axis, c2 * ax.theta);
+  *x0h = qh;
+  return qmul(q3, q4);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward pieces (what autograd through the reference's torch ops yields, in closed form).
 // ------------------------------------------------------------------------------------------------
@@ -752,10 +767,10 @@ SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out)
 //   order 0 / block 64: 12.01      order 1 / block 32: 10.98      order 2 / block 64: 10.89      order 3 / block 64: 10.69
 //   blocks 16, 48, 56, 72, 80, 96, 128 with the best order: 10.89 .. 11.64
 #ifndef SO3D_SERIES_BLOCK
-#define SO3D_SERIES_BLOCK 64
+#define SO3D_SERIES_BLOCK 32
 #endif
 #ifndef SO3D_SERIES_ORDER
-#define SO3D_SERIES_ORDER 1
+#define SO3D_SERIES_ORDER 0
 #endif
 #ifndef SO3D_SERIES_ROUNDUP
 #define SO3D_SERIES_ROUNDUP 1
@@ -897,13 +912,29 @@ constexpr float kSeriesGuard = 4.2f;
 // log f_eps(w) and g = d log f / dw by the evaluator kMode (a template parameter, so that a kernel contains one
 // evaluator only and the exact-L series keeps a provably warp-uniform trip count: its table operands must stay
 // uniform-register loads).
+// Where the guard's closed form is evaluated relative to the L-term loop, and whether it is inlined.  The arithmetic is
+// the same in every form; what changes is ptxas's register allocation and list schedule of the unrolled series block,
+// which moves the kernel by +-15 % (measured, profiles/r03b_series_variants.jsonl; see the source-form knobs above):
+//   0: after the loop, inlined        1: after the loop, out of line (__noinline__)
+//   2: before the loop, inlined       3: before the loop, out of line
+#ifndef SO3D_SERIES_GUARD_FORM
+#define SO3D_SERIES_GUARD_FORM 3
+#endif
+#if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
+static __host__ __device__ __noinline__ void igso3_closed_f32_outofline(float w, float eps, float* logf_out, float* g_out) {
+  igso3_closed_f32(w, eps, logf_out, g_out);
+}
+#else
+inline void igso3_closed_f32_outofline(float w, float eps, float* logf_out, float* g_out) { igso3_closed_f32(w, eps, logf_out, g_out); }
+#endif
+
 template <int kMode>
 SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g_out) {
   if (kMode == kClosed || (kMode == kAuto && eps <= kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
   } else {
     int terms = L;
-    if (kMode != kSeries) {
+    if (kMode == kAuto || kMode == kSeriesAdaptive) {
       terms = igso3_series_live_terms(eps, L);
 #if defined(__CUDA_ARCH__)
       // keep the trip count (and with it the constant-table index) the same across the warp: a lane-varying index
@@ -916,11 +947,21 @@ SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g
       terms = up <= L ? up : L;
 #endif
     }
+    constexpr bool kGuarded = (kMode == kSeries || kMode == kSeriesAdaptive);
+    const bool guard = kGuarded && eps <= kAutoSeriesEps && w > kSeriesGuard * eps;
+    float lf_c = 0.f, g_c = 0.f;
+    if (kGuarded && (SO3D_SERIES_GUARD_FORM == 2 || SO3D_SERIES_GUARD_FORM == 3) && guard) {
+      if (SO3D_SERIES_GUARD_FORM == 3) igso3_closed_f32_outofline(w, eps, &lf_c, &g_c);
+      else igso3_closed_f32(w, eps, &lf_c, &g_c);
+    }
     const SeriesAcc a = igso3_series_terms(w, eps, terms);
     *logf_out = logf(2.0f * a.F);
     *g_out = a.dF / a.F;
-    if ((kMode == kSeries || kMode == kSeriesAdaptive) && eps <= kAutoSeriesEps && w > kSeriesGuard * eps)
-      igso3_closed_f32(w, eps, logf_out, g_out);
+    if (kGuarded && guard) {
+      if (SO3D_SERIES_GUARD_FORM == 0) igso3_closed_f32(w, eps, logf_out, g_out);
+      else if (SO3D_SERIES_GUARD_FORM == 1) igso3_closed_f32_outofline(w, eps, logf_out, g_out);
+      else { *logf_out = lf_c; *g_out = g_c; }
+    }
   }
 }
 
@@ -1092,17 +1133,80 @@ SO3D_HD U4 philox4x32_10(const PhiloxKey& k, uint64_t row) {
   return c;
 }
 
-// 24-bit uniform in [0, 1), the same lattice torch.rand(float32) uses.
-SO3D_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// The generator with the ten round keys (functions of the seed only) supplied by the caller -- kernels that change the
+// stream offset while they run (one offset per step of a multi-step launch) take them as kernel parameters:
+// bit-identical to philox4x32_10(seed, row, offset).
+struct PhiloxRoundKeys {
+  uint32_t k0[10], k1[10];
+};
+SO3D_HD PhiloxRoundKeys make_philox_round_keys(uint64_t seed) {
+  PhiloxRoundKeys k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    k.k0[i] = a;
+    k.k1[i] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return k;
+}
+SO3D_HD U4 philox4x32_10(const PhiloxRoundKeys& k, uint64_t row, uint64_t offset) {
+  U4 c{(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k.k0[i], lo1, hi0 ^ c.w ^ k.k1[i], lo0};
+  }
+  return c;
+}
+
+// 24-bit uniform in [0, 1), the same lattice torch.rand(float32) uses.  Device: one round-toward-zero conversion of the
+// whole word (keeps exactly the top 24 bits) and a multiply -- the same value as (x >> 8) 2^-24 without the shift.
+SO3D_HD float u01(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __uint2float_rz(x) * (1.0f / 4294967296.0f);
+#else
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+#endif
+}
+
+// The random-number side of the fused kernels is pure instruction issue (the kernels are issue-bound), and
+// nothing downstream depends on a DRAWN direction or normal beyond its distribution -- so on the device these use the
+// hardware approximations (MUFU.SIN / MUFU.COS / MUFU.LG2: absolute error 2^-20.9, i.e. a 5e-7 perturbation of a random
+// variate) instead of the 22-instruction polynomial sincos and libdevice's logf.  The noise ANGLE and everything
+// computed from an existing rotation keep the accurate primitives.  SO3D_DRAW_MUFU=0 restores the polynomial versions
+// (the host build always uses them).
+#ifndef SO3D_DRAW_MUFU
+#define SO3D_DRAW_MUFU 1
+#endif
+SO3D_HD void sincos_draw(float x, float* s, float* c) {  // x in [-pi, pi]
+#if defined(__CUDA_ARCH__) && SO3D_DRAW_MUFU
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
+#else
+  sincos_fast(x, s, c);
+#endif
+}
+SO3D_HD float neg2_log_draw(float u) {  // -2 ln u for u in (0, 1]
+#if defined(__CUDA_ARCH__) && SO3D_DRAW_MUFU
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+  return -1.3862943611198906f * l;
+#else
+  return -2.0f * logf(u);
+#endif
+}
 
 // Uniform point on S^2 from two uniforms (same law as the reference's normalised N(0, I3) draw,
-// distributions.py:35-36).
+// distributions.py:35-36).  The azimuth is 2 pi ub - pi in [-pi, pi): uniform on the circle like 2 pi ub, and inside
+// the range where MUFU.SIN / MUFU.COS are specified to 2^-20.9.
 SO3D_HD Vec3 sphere_from_uniforms(float ua, float ub) {
   const float z = fmaf(-2.0f, ua, 1.0f);
   const float t = 4.0f * ua * (1.0f - ua);  // 1 - z^2 without cancellation
   const float r = t * rsqrt_approx(fmaxf(t, 1e-30f));
   float sp, cp;
-  sincos_fast(kTwoPi * ub, &sp, &cp);
+  sincos_draw(fmaf(kTwoPi, ub, -kPi), &sp, &cp);
   return Vec3{r * cp, r * sp, z};
 }
 
@@ -1114,11 +1218,11 @@ struct Normal4 {
 SO3D_HD Normal4 normal4_from_u4(const U4& r) {
   const float ua = (float)((r.x >> 8) + 1u) * (1.0f / 16777216.0f);
   const float ub = (float)((r.z >> 8) + 1u) * (1.0f / 16777216.0f);
-  const float ta = -2.0f * logf(ua), tb = -2.0f * logf(ub);
+  const float ta = neg2_log_draw(ua), tb = neg2_log_draw(ub);
   const float ra = ta * rsqrt_approx(fmaxf(ta, 1e-30f)), rb = tb * rsqrt_approx(fmaxf(tb, 1e-30f));
   float sa, ca, sb, cb;
-  sincos_fast(kTwoPi * u01(r.y), &sa, &ca);
-  sincos_fast(kTwoPi * u01(r.w), &sb, &cb);
+  sincos_draw(fmaf(kTwoPi, u01(r.y), -kPi), &sa, &ca);
+  sincos_draw(fmaf(kTwoPi, u01(r.w), -kPi), &sb, &cb);
   return Normal4{ra * ca, ra * sa, rb * cb, rb * sb};
 }
 
@@ -1134,5 +1238,6 @@ SO3D_HD NoiseDraw draw_from_block(const U4& r) {
 }
 SO3D_HD NoiseDraw draw_axis_u(uint64_t seed, uint64_t row, uint64_t offset) { return draw_from_block(philox4x32_10(seed, row, offset)); }
 SO3D_HD NoiseDraw draw_axis_u(const PhiloxKey& k, uint64_t row) { return draw_from_block(philox4x32_10(k, row)); }
+SO3D_HD NoiseDraw draw_axis_u(const PhiloxRoundKeys& k, uint64_t row, uint64_t offset) { return draw_from_block(philox4x32_10(k, row, offset)); }
 
 }  // namespace so3d

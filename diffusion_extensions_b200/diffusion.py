@@ -375,6 +375,17 @@ class SO3Diffusion(nn.Module):
             x = self.p_sample(x, t_range[i:i + 1])  # device-resident step index: no H2D copy per step
         return x
 
+    @torch.no_grad()
+    def reverse_process(self, x, pred=None, t_hi=None, t_lo=0):
+        """The reverse chain x_{t_hi} -> x_{t_lo - 1} of `p_sample_loop` (diffusion.py:328-337) WITHOUT a denoiser in the loop:
+        `pred` is None (zero prediction) or one fixed (...,3) prediction per particle.  With nothing but the manifold
+        step between two steps, all of them run in ONE launch with the particles resident on chip
+        (ops.p_sample_loop_fused); the result is bit-identical to p_sample_fused step by step.  This is the path
+        BASELINE configs[2] times ("1000 steps x 2^24 particles", denoiser excluded); with a denoiser use p_sample_loop."""
+        _, post, _ = self.tables()
+        t_hi = self.num_timesteps - 1 if t_hi is None else int(t_hi)
+        return ops.p_sample_loop_fused(x, pred, t_hi, int(t_lo), *self._sched4(), post, self.guides()[1], row_offset=self.row_offset)
+
     # ---- training loss ------------------------------------------------------------------------
     def p_losses(self, x_start, t, noise=None):
         """diffusion.py:348-369."""

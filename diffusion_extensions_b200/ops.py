@@ -678,6 +678,37 @@ def p_sample_fused(x_t, pred, t, recip, recipm1, coef1, coef2, post_cdf=None, se
     return (out, x0_hat) if want_x0_hat else out
 
 
+def p_sample_loop_fused(x_t, pred, t_hi, t_lo, recip, recipm1, coef1, coef2, post_cdf, post_guide, seed=None, rng_offset=0, row_offset=0,
+                        out=None):
+    """The reverse steps t_hi .. t_lo in ONE launch (so3d_p_sample_loop_f32): `pred` is None (no denoiser: zero prediction)
+    or a fixed (...,3) prediction per particle; step t draws its noise at rng_offset + t.  Bit-identical to calling
+    p_sample_fused(x, pred, [t], ..., seed=seed, rng_offset=rng_offset + t) for t = t_hi .. t_lo.  -> x_{t_lo - 1}"""
+    x_t, bs, n = _rows9(x_t, "x")
+    dev = x_t.device
+    if pred is not None:
+        pred = check_f32(pred, "predict", (3,)).expand(*bs, 3).contiguous()
+    recip, recipm1 = check_f32(recip, "sqrt_recip_alphas_cumprod"), check_f32(recipm1, "sqrt_recipm1_alphas_cumprod")
+    coef1, coef2 = check_f32(coef1, "posterior_mean_coef1"), check_f32(coef2, "posterior_mean_coef2")
+    T = recip.numel()
+    post_cdf = check_f32(post_cdf, "post_cdf", (CDF_POINTS,))
+    if post_cdf.numel() != T * CDF_POINTS:
+        raise ValueError("posterior cdf table must have one row per timestep")
+    if post_guide is None:
+        raise ValueError("post_guide (ops.igso3_cdf_guide(post_cdf)) is required")
+    _check_guide(post_guide, T, "post_guide")
+    _, _, trap_loc = cdf_grid(dev)
+    if seed is None:
+        seed, base = rng.next()
+        rng_offset = int(rng_offset) + (base << 20)   # a fresh block of step offsets per call
+    if out is None:
+        out = torch.empty_like(x_t)
+    elif out.shape != x_t.shape or out.dtype != torch.float32 or out.device != dev or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 tensor shaped like x")
+    call("so3d_p_sample_loop_f32", ptr(x_t), ptr(pred), int(t_hi), int(t_lo), ptr(recip), ptr(recipm1), ptr(coef1), ptr(coef2), T, ptr(post_cdf),
+         ptr(post_guide), ptr(trap_loc), int(seed), int(rng_offset), int(row_offset), ptr(out), n, device=dev)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # RotPredict denoiser fused with the reverse step (SURVEY 8f-4)
 # ---------------------------------------------------------------------------------------------

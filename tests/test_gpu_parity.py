@@ -611,6 +611,44 @@ def test_full_size_properties(dx, cuda_device):
     assert ((score - g[:, None] * axis).norm(dim=-1)).max().item() < 1e-6 * g.abs().max().item()
 
 
+@pytest.mark.parametrize("n", [1, 255, 257, 1300, 70001])
+def test_one_launch_reverse_process_equals_step_launches(dx, cuda_device, n):
+    """so3d_p_sample_loop_f32 (all steps in one launch, particles resident in shared memory) is bit-identical to the
+    per-step launches of so3d_p_sample_f32 with rng_offset = rng_offset0 + t: without a prediction (pred3 == NULL ==
+    zero prediction), with a fixed per-particle prediction, through t == 0 (no noise at the last step), in place, and for
+    a shard with a global row offset."""
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    _, post, t_range = p.tables()
+    pg = p.guides()[1]
+    sched = (p.sqrt_recip_alphas_cumprod, p.sqrt_recipm1_alphas_cumprod, p.posterior_mean_coef1, p.posterior_mean_coef2)
+    x0 = dx.ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(n)))
+    zeros = torch.zeros(n, 3, device=cuda_device)
+    pred = torch.randn(n, 3, device=cuda_device) * 0.2
+    for t_hi, t_lo, pr, row_off in ((999, 992, None, 0), (6, 0, None, 12345), (500, 495, pred, 7), (3, 0, pred, 0)):
+        x = x0
+        for t in range(t_hi, t_lo - 1, -1):
+            x = dx.ops.p_sample_fused(x, zeros if pr is None else pr, t_range[t:t + 1], *sched, post_cdf=post, seed=91, rng_offset=1000 + t,
+                                      row_offset=row_off)
+        got = dx.ops.p_sample_loop_fused(x0, pr, t_hi, t_lo, *sched, post, pg, seed=91, rng_offset=1000, row_offset=row_off)
+        assert torch.equal(got, x), (t_hi, t_lo, pr is None)
+    inplace = x0.clone()
+    dx.ops.p_sample_loop_fused(inplace, None, 6, 0, *sched, post, pg, seed=91, rng_offset=1000, row_offset=12345, out=inplace)
+    want = dx.ops.p_sample_loop_fused(x0, None, 6, 0, *sched, post, pg, seed=91, rng_offset=1000, row_offset=12345)
+    assert torch.equal(inplace, want)
+    # the module-level entry point (SO3Diffusion.reverse_process) and argument errors
+    if n == 257:
+        p.row_offset = 5
+        dx.manual_seed(3)
+        a = p.reverse_process(x0, t_hi=20)
+        dx.manual_seed(3)
+        b = p.reverse_process(x0, t_hi=20)
+        assert torch.equal(a, b) and torch.isfinite(a).all() and not torch.equal(a, x0)
+        with pytest.raises(RuntimeError):
+            dx.ops.p_sample_loop_fused(x0, None, 1000, 0, *sched, post, pg, seed=1)      # t_hi out of range: C-ABI argument error
+        with pytest.raises(ValueError):
+            dx.ops.p_sample_loop_fused(x0, None, 5, 0, *sched, post, None, seed=1)
+
+
 def test_logp_score_at_2pow28_rows_with_64bit_offsets(dx, cuda_device):
     """BASELINE config[1]'s largest size: 2^28 rotations in ONE launch (9.7 GB of matrices: element offsets beyond 2^31,
     byte offsets beyond 2^33).  The E-set is built on the device (itself a 2^28-row aa_to_rmat launch); a strided sample
