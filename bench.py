@@ -526,7 +526,7 @@ def main():
 
         # BASELINE configs[2]: the whole reverse process, 1000 fused steps over this GPU's share of 2^24 particles
         # (pred = 0: the denoiser is excluded).  Two routes: one launch per step from the host (x ping-pongs
-        # between two buffers), and so3d_p_sample_loop_f32 -- ALL steps in one launch, particles resident in registers.
+        # between two buffers), and so3d_p_sample_loop_f32 -- ALL steps in one launch, particles resident in shared memory.
         n_loop = max(1, (1 << 24) // world)
         la, lb = R[:n_loop].clone(), torch.empty_like(R[:n_loop])
         pz = pred[:n_loop]
@@ -554,8 +554,9 @@ def main():
                 v1 = world * n_loop * 1000 / (m1 * 1e-3)
                 sm_n = torch.cuda.get_device_properties(device).multi_processor_count
                 loop_entry["one_launch"] = {"value": v1, "unit": "particle-steps/s", "seconds": m1 * 1e-3,
-                                            "note": "so3d_p_sample_loop_f32: every particle stays in registers for all 1000 steps (x_T read once, x_0 written once), the step's CDF "
-                                                    "row + guide are re-staged per step; bit-identical to the per-step launches; issue-bound, not HBM-bound",
+                                            "note": "so3d_p_sample_loop_f32: ONE launch for all 1000 steps -- a CTA keeps its chunk of particles resident in shared memory "
+                                                    "(x_T read from HBM once, x_0 written once), per step and particle one 16-byte guide record comes from the L2-resident "
+                                                    "posterior table; bit-identical to the per-step launches; no HBM traffic to speak of, bound by instruction issue",
                                             "equivalent_hbm_gbs_per_gpu": v1 / world * BYTES_PER_PARTICLE_STEP / 1e9,
                                             "thread_instr_budget_per_particle_step": sm_n * 128 * pk["sm_max_mhz"] * 1e6 / (v1 / world)}
             except Exception as e:

@@ -134,8 +134,13 @@ __device__ __forceinline__ float silu(float x) {
   return x * rcp_approx(1.0f + e);
 }
 
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_bounded_addr(uint32_t addr, uint32_t parity);
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) { mbar_wait_bounded_addr(smem_u32(bar), parity); }
+// the barrier's shared-memory address as an opaque register value: ptxas otherwise folds it into another pointer plus a
+// NEGATIVE immediate ([R44 + -0x68] in the multi-step kernel), an addressing form compute-sanitizer's synccheck does not
+// resolve -- it then reports the (initialised) barrier as "Missing init" (profiles/r03c_sanitizer_synccheck_*.log)
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }  // (a PTX mov is folded away again)
+__device__ __forceinline__ void mbar_wait_bounded_addr(uint32_t addr, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
   do {
@@ -305,11 +310,12 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
     // ---- MMA issuer of group g: wait for the A operand, issue the layer, commit to the accumulator barrier ----
     const int g = warp - kEpiWarps;
     const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
+    const uint32_t bar_a_addr = opaque_u32(smem_u32(&bars[3 + g]));
     for (int64_t tile = (int64_t)blockIdx.x * 2 + g; tile < tiles; tile += (int64_t)gridDim.x * 2) {
       {
 #pragma unroll 1
         for (int layer = 1; layer <= 5; ++layer) {
-          mbar_wait_bounded(&bars[3 + g], ph);
+          mbar_wait_bounded_addr(bar_a_addr, ph);
           ph ^= 1;
           if (!elect_one()) continue;
           if (layer == 1) {

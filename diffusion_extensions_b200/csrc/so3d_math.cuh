@@ -778,6 +778,32 @@ SO3D_HD void igso3_closed_f32(float w, float eps, float* logf_out, float* g_out)
 constexpr int kSeriesBlock = SO3D_SERIES_BLOCK;       // unrolled terms per block
 constexpr int kSeriesMaxTerms = 2896;  // m(m+1) is exact in fp32 below this
 
+// Table layout.  0 (shipped): two float arrays, one LDCU.64 per term ({mh, mh'} and {mm, mm'} alternately).
+// 1: one 16-byte record per PAIR of terms, {m+1/2, m(m+1)} for m = 2j and 2j+1, read with one ld.const.v4 -- meant to
+// halve the constant loads (LDCU.128 per two terms, 9 -> 8.5 issue slots per term), but ptxas 12.9 splits the vector load
+// into two LDCU.64 again (it keeps uniform-register live ranges short), so the layout buys nothing; kept as a knob.
+#ifndef SO3D_SERIES_TAB4
+#define SO3D_SERIES_TAB4 0
+#endif
+#if SO3D_SERIES_TAB4
+struct alignas(16) SeriesPair {
+  float x, y, z, w;  // mh(2j), mm(2j), mh(2j+1), mm(2j+1)
+};
+struct alignas(16) SeriesTab {
+  SeriesPair pair[(kSeriesMaxTerms + kSeriesBlock) / 2 + 1];
+};
+constexpr SeriesTab make_series_tab() {
+  SeriesTab t{};
+  for (int j = 0; j < (kSeriesMaxTerms + kSeriesBlock) / 2 + 1; ++j) {
+    const int m = 2 * j;
+    t.pair[j].x = (float)m + 0.5f;
+    t.pair[j].y = (float)((double)m * (double)(m + 1));
+    t.pair[j].z = (float)(m + 1) + 0.5f;
+    t.pair[j].w = (float)((double)(m + 1) * (double)(m + 2));
+  }
+  return t;
+}
+#else
 struct alignas(16) SeriesTab {
   float mh[kSeriesMaxTerms + kSeriesBlock];  // m + 1/2
   float mm[kSeriesMaxTerms + kSeriesBlock];  // m (m + 1)
@@ -790,11 +816,30 @@ constexpr SeriesTab make_series_tab() {
   }
   return t;
 }
+#endif
 #if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
 __constant__ SeriesTab c_series_tab = make_series_tab();
 #endif
 static constexpr SeriesTab h_series_tab = make_series_tab();
 
+#if SO3D_SERIES_TAB4
+SO3D_HD SeriesPair series_pair(int j) {
+#if defined(__CUDA_ARCH__)
+  const float4 v = *reinterpret_cast<const float4*>(&c_series_tab.pair[j]);  // one ld.const.v4 -> LDCU.128
+  return SeriesPair{v.x, v.y, v.z, v.w};
+#else
+  return h_series_tab.pair[j];
+#endif
+}
+SO3D_HD float series_mh(int m) {
+  const SeriesPair p = series_pair(m >> 1);
+  return (m & 1) ? p.z : p.x;
+}
+SO3D_HD float series_mm(int m) {
+  const SeriesPair p = series_pair(m >> 1);
+  return (m & 1) ? p.w : p.y;
+}
+#else
 SO3D_HD float series_mh(int m) {
 #if defined(__CUDA_ARCH__)
   return c_series_tab.mh[m];
@@ -809,6 +854,7 @@ SO3D_HD float series_mm(int m) {
   return h_series_tab.mm[m];
 #endif
 }
+#endif
 
 struct SeriesAcc {
   float F, dF;  // sum (l+1/2) e_l chi_l  and its derivative w.r.t. w:  f = 2 F,  d log f / dw = dF / F

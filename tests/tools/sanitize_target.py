@@ -49,8 +49,8 @@ for n in (sizes if want("rows") else []):
         ops.se3_p_sample_fused(R, v, v, v, t1, *sched, sig, 75.0, post_cdf=post, seed=1, rng_offset=5)
         ops.se3_p_sample_fused(R, v, v, v, tt, *sched, sig, 75.0, post_cdf=post, seed=1, rng_offset=5, post_guide=pg)
         if hasattr(ops, "p_sample_loop_fused"):
-            ops.p_sample_loop_fused(R.contiguous(), None, T - 1, 0, *sched, post, seed=1, rng_offset=100)
-            ops.p_sample_loop_fused(R.contiguous(), v, T - 1, T - 6, *sched, post, seed=1, rng_offset=100)
+            ops.p_sample_loop_fused(R.contiguous(), None, T - 1, 0, *sched, post, pg, seed=1, rng_offset=100)
+            ops.p_sample_loop_fused(R.contiguous(), v, T - 1, T - 6, *sched, post, pg, seed=1, rng_offset=100)
     ops.bingham_sample(torch.eye(4, device=dev), (n,), seed=2, rng_offset=0, want_rmat=True)
     ops.pair_kernel_sums(Rfull[:n], Rfull[1:], "gaussian")
     ops.pair_kernel_sums(Rfull[:n], None, "cosine")
