@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SRCS = [os.path.join(CSRC, f) for f in ("so3d_kernels.cu", "so3d_pairwise.cu", "so3d_denoiser.cu", "so3d_loop.cu")]
-DEPS = SRCS + [os.path.join(CSRC, f) for f in ("so3d_math.cuh", "so3d_tma.cuh", "so3d_common.cuh", "so3d_cdf_smem.cuh")] + [os.path.join(HERE, "..", "include", "so3d.h")]
+DEPS = SRCS + [os.path.join(CSRC, f) for f in ("so3d_math.cuh", "so3d_lanes.cuh", "so3d_tma.cuh", "so3d_common.cuh", "so3d_cdf_smem.cuh")] + [os.path.join(HERE, "..", "include", "so3d.h")]
 LIB = os.path.join(HERE, "libso3d.so")
 
 NVCC_FLAGS = [

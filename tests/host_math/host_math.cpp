@@ -118,3 +118,59 @@ extern "C" void hm_normal4(unsigned long long seed, unsigned long long row0, uns
 extern "C" void hm_logf_g(const float* w, const float* eps, float* logf, float* g, long n, int mode, int L) {
   for (long i = 0; i < n; ++i) igso3_logf_g(w[i], eps[i], mode, L, logf + i, g + i);
 }
+
+// ---- so3d_lanes.cuh: the one-lane and two-lane instantiations must equal the scalar functions they restate, bit for bit ----
+#include "../../diffusion_extensions_b200/csrc/so3d_lanes.cuh"
+static inline unsigned fbits(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+// returns the number of mismatching output words over n (pairs of) rotations; mean/x0h (n x 9) receive the L2 results
+extern "C" long hm_lanes_p_mean(const float* x, const float* pred, const float* a, const float* b, const float* c1, const float* c2,
+                                float* mean, float* x0h, long n, int has_pred) {
+  long bad = 0;
+  for (long i = 0; i + 1 < n; i += 2) {
+    Mat3 r0 = ld(x + 9 * i), r1 = ld(x + 9 * (i + 1));
+    // the step scalars are shared by the two lanes: use row i's
+    Quat qh0, qh1;
+    Quat q0, q1;
+    if (has_pred) {
+      q0 = p_mean_quat(r0, Vec3{pred[3*i], pred[3*i+1], pred[3*i+2]}, a[i], b[i], c1[i], c2[i], &qh0);
+      q1 = p_mean_quat(r1, Vec3{pred[3*i+3], pred[3*i+4], pred[3*i+5]}, a[i], b[i], c1[i], c2[i], &qh1);
+    } else {
+      q0 = p_mean_quat_nopred(r0, a[i], c1[i], c2[i], &qh0);
+      q1 = p_mean_quat_nopred(r1, a[i], c1[i], c2[i], &qh1);
+    }
+    const Mat3 m0 = quat_to_mat_unit(q0), m1 = quat_to_mat_unit(q1), h0 = quat_to_mat_unit(qh0), h1 = quat_to_mat_unit(qh1);
+    // two lanes
+    QuatL<L2> qh2;
+    const Vec3L<L2> p2{L2{pred[3*i], pred[3*i+3]}, L2{pred[3*i+1], pred[3*i+4]}, L2{pred[3*i+2], pred[3*i+5]}};
+    const QuatL<L2> q2 = has_pred ? p_mean_quat_l<L2, true>(lanes_of(r0, r1), p2, a[i], b[i], c1[i], c2[i], &qh2)
+                                  : p_mean_quat_l<L2, false>(lanes_of(r0, r1), p2, a[i], b[i], c1[i], c2[i], &qh2);
+    const Mat3L<L2> m2 = quat_to_mat_unit_l(q2), h2 = quat_to_mat_unit_l(qh2);
+    // one lane
+    QuatL<L1> qh1l;
+    const Vec3L<L1> p1{L1{pred[3*i]}, L1{pred[3*i+1]}, L1{pred[3*i+2]}};
+    const QuatL<L1> q1l = has_pred ? p_mean_quat_l<L1, true>(lanes_of(r0), p1, a[i], b[i], c1[i], c2[i], &qh1l)
+                                   : p_mean_quat_l<L1, false>(lanes_of(r0), p1, a[i], b[i], c1[i], c2[i], &qh1l);
+    const Mat3L<L1> m1l = quat_to_mat_unit_l(q1l);
+    for (int k = 0; k < 9; ++k) {
+      bad += fbits(m2.m[k].x) != fbits(m0.m[k]);
+      bad += fbits(m2.m[k].y) != fbits(m1.m[k]);
+      bad += fbits(h2.m[k].x) != fbits(h0.m[k]);
+      bad += fbits(h2.m[k].y) != fbits(h1.m[k]);
+      bad += fbits(m1l.m[k].x) != fbits(m0.m[k]);
+      mean[9 * i + k] = m2.m[k].x; mean[9 * (i + 1) + k] = m2.m[k].y;
+      x0h[9 * i + k] = h2.m[k].x; x0h[9 * (i + 1) + k] = h2.m[k].y;
+    }
+  }
+  return bad;
+}
+extern "C" long hm_lanes_sphere(const float* ua, const float* ub, float* axis, long n) {
+  long bad = 0;
+  for (long i = 0; i + 1 < n; i += 2) {
+    const Vec3 a0 = sphere_from_uniforms(ua[i], ub[i]), a1 = sphere_from_uniforms(ua[i + 1], ub[i + 1]);
+    const Vec3L<L2> v = sphere_from_uniforms_l(L2{ua[i], ua[i + 1]}, L2{ub[i], ub[i + 1]});
+    bad += (fbits(v.x.x) != fbits(a0.x)) + (fbits(v.y.x) != fbits(a0.y)) + (fbits(v.z.x) != fbits(a0.z));
+    bad += (fbits(v.x.y) != fbits(a1.x)) + (fbits(v.y.y) != fbits(a1.y)) + (fbits(v.z.y) != fbits(a1.z));
+    axis[3*i] = v.x.x; axis[3*i+1] = v.y.x; axis[3*i+2] = v.z.x; axis[3*i+3] = v.x.y; axis[3*i+4] = v.y.y; axis[3*i+5] = v.z.y;
+  }
+  return bad;
+}

@@ -448,3 +448,31 @@ def test_box_muller_normals(hm):
     # Kolmogorov distance to the normal CDF
     from scipy.stats import kstest
     assert kstest(z[:200000, 2], "norm").statistic < 4e-3
+
+
+def test_lanes_header_restates_the_scalar_arithmetic_bit_for_bit(hm):
+    """csrc/so3d_lanes.cuh (one rotation or TWO rotations per thread through the same IEEE operations, the two-lane form
+    packed as FFMA2 / FMUL2 / FADD2 on the device): its one-lane and two-lane instantiations of the reverse step's mean and
+    of the drawn direction equal the scalar functions of so3d_math.cuh bit for bit on the host build."""
+    n = 20000
+    R, _, _ = rand_rots(n, 77)
+    R[:8] = np.eye(3, dtype=np.float32)                       # identity rows
+    R[8:16] = O.rodrigues(np.tile([[0.6, 0.0, 0.8]], (8, 1)), np.full(8, math.pi)).astype(np.float32)   # rotations by pi
+    rng = np.random.default_rng(78)
+    pred = f32(rng.standard_normal((n, 3)) * 0.4)
+    s = O.schedule_buffers(1000)
+    t = rng.integers(0, 1000, n)
+    a, b = f32(s["sqrt_recip_alphas_cumprod"][t]), f32(s["sqrt_recipm1_alphas_cumprod"][t])
+    c1, c2 = f32(s["posterior_mean_coef1"][t]), f32(s["posterior_mean_coef2"][t])
+    mean = np.empty((n, 9), np.float32); x0h = np.empty((n, 9), np.float32)
+    hm.hm_lanes_p_mean.restype = ctypes.c_long
+    for has_pred in (1, 0):
+        bad = hm.hm_lanes_p_mean(fp(R), fp(pred), fp(a), fp(b), fp(c1), fp(c2), fp(mean), fp(x0h), ctypes.c_long(n), has_pred)
+        assert bad == 0, (has_pred, bad)
+        assert np.isfinite(mean).all()
+    ua, ub = f32(rng.uniform(0, 1, n)), f32(rng.uniform(0, 1, n))
+    ua[:4] = [0.0, 1.0 - 2 ** -24, 0.5, 2 ** -24]
+    axis = np.empty((n, 3), np.float32)
+    hm.hm_lanes_sphere.restype = ctypes.c_long
+    assert hm.hm_lanes_sphere(fp(ua), fp(ub), fp(axis), ctypes.c_long(n)) == 0
+    assert np.max(np.abs(np.linalg.norm(axis.astype(np.float64), axis=-1) - 1)) < 1e-6

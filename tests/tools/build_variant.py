@@ -12,8 +12,9 @@ sys.path.insert(0, ROOT)
 from diffusion_extensions_b200 import build as B
 
 args = sys.argv[1:]
-kernels_only = "--kernels-only" in args
-args = [a for a in args if a != "--kernels-only"]
+kernels_only = "--kernels-only" in args or any(a.startswith("--tu=") for a in args)
+tu = next((a[5:] for a in args if a.startswith("--tu=")), "so3d_kernels.cu")   # the translation unit that gets the flags
+args = [a for a in args if a != "--kernels-only" and not a.startswith("--tu=")]
 name, flags = args[0], args[1:]
 out_dir = os.path.join(ROOT, "build", "variants")
 os.makedirs(out_dir, exist_ok=True)
@@ -26,10 +27,13 @@ else:
     obj_dir = os.path.join(ROOT, "build", "obj")
     os.makedirs(obj_dir, exist_ok=True)
     objs = []
-    for src in B.SRCS[1:]:
+    main = next(s for s in B.SRCS if os.path.basename(s) == tu)
+    for src in B.SRCS:
+        if src == main:
+            continue
         o = os.path.join(obj_dir, os.path.basename(src) + ".o")
-        if not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(d) for d in B.DEPS):
+        if not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(d) for d in B.DEPS + [os.path.join(B.CSRC, "so3d_lanes.cuh")]):
             subprocess.check_call([nvcc, *base, "-c", "-o", o, src])
         objs.append(o)
-    subprocess.check_call([nvcc, *base, "-shared", *flags, "-o", out, B.SRCS[0], *objs])
+    subprocess.check_call([nvcc, *base, "-shared", *flags, "-o", out, main, *objs])
     print(out)
