@@ -19,6 +19,7 @@
 
 #include "../../include/so3d.h"
 #include "so3d_math.cuh"
+#include "so3d_lanes.cuh"
 #include "so3d_tma.cuh"
 #include "so3d_cdf_smem.cuh"
 
@@ -589,6 +590,195 @@ int launch_rowwise(const Op& op, int64_t n, void* stream, const char* name, int 
   return check_launch(name);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two rows per thread (so3d_lanes.cuh).  The same two schedules with tiles of 2 x kTile = 512 rows moved by 256 threads:
+// thread `tid` owns rows `tid` and `tid + 256` of a tile and carries them through the op's arithmetic as the two lanes of
+// packed FP32 instructions (FFMA2 / FMUL2 / FADD2): half the issue slots for the ~45 % of a fused step that is FP32
+// arithmetic.  These are separate kernel templates, not a parameter of the ones above: the one-row kernels' code
+// (and with it ptxas's schedule of the compute-bound series kernel) stays exactly as it was.
+//   Op2 provides kIn9 / kIn3 / kOut9 / kOut3 / kOutStages / kTab / setup() like a one-row op, and
+//     __device__ void row2(int64_t i0, const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const
+//   for the rows i0 (lane 0) and i0 + kTile (lane 1); a lane beyond the end of the data computes on stale values and its
+//   results are dropped.
+// ------------------------------------------------------------------------------------------------
+#ifndef SO3D_LANES2_THREADS
+#define SO3D_LANES2_THREADS 128  // threads per CTA of the two-row kernels: 128 -> 256-row tiles like the one-row kernels (same shared
+#endif                           // memory per CTA, 4 resident CTAs of 4 warps); 256 -> 512-row tiles, 2 resident CTAs of 8 warps
+constexpr int kT2 = SO3D_LANES2_THREADS;  // thread `tid` owns rows `tid` and `tid + kT2` of a tile
+constexpr int kRows2 = 2 * kT2;
+template <int W>
+__device__ __forceinline__ void coop_load2(float* __restrict__ sm, const float* __restrict__ g, int rows) {
+  for (int i = threadIdx.x; i < rows * W; i += kT2) sm[i] = __ldcs(g + i);
+}
+template <int W>
+__device__ __forceinline__ void coop_store2(float* __restrict__ g, const float* __restrict__ sm, int rows) {
+  for (int i = threadIdx.x; i < rows * W; i += kT2) __stcs(g + i, sm[i]);
+}
+
+template <class Op>
+struct OpLayout2 {
+  static constexpr int kInWords = Op::kIn9 * 9 + Op::kIn3 * 3;
+  static constexpr int kOutWords = Op::kOut9 * 9 + Op::kOut3 * 3;
+  static constexpr int kOutStages = Op::kOutStages;
+  static constexpr int kInFloats = kRows2 * kInWords;
+  static constexpr int kOutFloats = kRows2 * kOutWords;
+  static constexpr int kTabFloats = (Op::kTab + 3) & ~3;
+  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kInFloats + kOutStages * kOutFloats + kTabFloats) + 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_cta2(const Op op, const int64_t n, const int use_tma) {
+  extern __shared__ float4 smem4[];
+  constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
+  using Lay = OpLayout2<Op>;
+  float* smem = reinterpret_cast<float*>(smem4);
+  float* s_out = smem + 2 * Lay::kInFloats;
+  float* s_tab = s_out + Lay::kOutStages * Lay::kOutFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t tiles = (n + kRows2 - 1) / kRows2;
+  const int my_tiles = (tiles > (int64_t)blockIdx.x) ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int my_full = my_tiles - (((n % kRows2) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
+  const int64_t first_row = (int64_t)blockIdx.x * kRows2, stride_rows = (int64_t)gridDim.x * kRows2;
+  auto issue_load = [&](int k, int64_t row0) {  // thread 0 only
+    if (kI9 + kI3 == 0) return;
+    const int st = k & 1;
+    float* base = smem + st * Lay::kInFloats;
+    mbar_expect_tx(&bars[st], (uint32_t)(kRows2 * Lay::kInWords * sizeof(float)));
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) bulk_load(base + a * kRows2 * 9, op.in9[a] + row0 * 9, kRows2 * 9 * sizeof(float), &bars[st]);
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kRows2 * 9 + a * kRows2 * 3, op.in3[a] + row0 * 3, kRows2 * 3 * sizeof(float), &bars[st]);
+  };
+  if (tid == 0 && use_tma) {
+    if (my_full > 0) issue_load(0, first_row);
+    if (my_full > 1) issue_load(1, first_row + stride_rows);
+  }
+  op.setup(s_tab);
+  __syncthreads();
+
+  int64_t row0 = first_row;
+  for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
+    const int st = k & 1;
+    const int rows = k < my_full ? kRows2 : (int)(n - row0);
+    const bool tma = use_tma && rows == kRows2;
+    float* s_i9 = smem + st * Lay::kInFloats;
+    float* s_i3 = s_i9 + kI9 * kRows2 * 9;
+    float* s_o9 = s_out + (Lay::kOutStages == 2 ? st : 0) * Lay::kOutFloats;
+    float* s_o3 = s_o9 + kO9 * kRows2 * 9;
+    if (kI9 + kI3 > 0) {
+      if (tma) {
+        mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+      } else {
+#pragma unroll
+        for (int a = 0; a < kI9; ++a) coop_load2<9>(s_i9 + a * kRows2 * 9, op.in9[a] + row0 * 9, rows);
+#pragma unroll
+        for (int a = 0; a < kI3; ++a) coop_load2<3>(s_i3 + a * kRows2 * 3, op.in3[a] + row0 * 3, rows);
+        __syncthreads();
+      }
+    }
+    Mat3 a9[kI9 > 0 ? kI9 : 1][2];
+    Vec3 a3[kI3 > 0 ? kI3 : 1][2];
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) {
+      a9[a][0] = sm_mat(s_i9 + a * kRows2 * 9, tid);
+      a9[a][1] = sm_mat(s_i9 + a * kRows2 * 9, tid + kT2);
+    }
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) {
+      a3[a][0] = sm_vec(s_i3 + a * kRows2 * 3, tid);
+      a3[a][1] = sm_vec(s_i3 + a * kRows2 * 3, tid + kT2);
+    }
+    if (Lay::kOutStages == 2 && tid == 0) bulk_wait_read<1>();
+    __syncthreads();  // A
+    if (tid == 0 && use_tma && k + 2 < my_full) issue_load(k + 2, row0 + 2 * stride_rows);
+
+    Mat3 o9[kO9 > 0 ? kO9 : 1][2];
+    Vec3 o3[kO3 > 0 ? kO3 : 1][2];
+    if (tid < rows) op.row2(row0 + tid, a9, a3, o9, o3, s_tab);
+    if (Lay::kOutStages == 1 && kO9 + kO3 > 0) {
+      if (tid == 0) bulk_wait_read<0>();
+      __syncthreads();  // C
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (tid + j * kT2 < rows) {
+#pragma unroll
+        for (int a = 0; a < kO9; ++a) sm_put_mat(s_o9 + a * kRows2 * 9, tid + j * kT2, o9[a][j]);
+#pragma unroll
+        for (int a = 0; a < kO3; ++a) sm_put_vec(s_o3 + a * kRows2 * 3, tid + j * kT2, o3[a][j]);
+      }
+    }
+    if (kO9 + kO3 > 0) {
+      if (tma) {
+        fence_proxy_async();
+        __syncthreads();  // B
+        if (tid == 0) {
+#pragma unroll
+          for (int a = 0; a < kO9; ++a)
+            if (op.out9[a]) bulk_store(op.out9[a] + row0 * 9, s_o9 + a * kRows2 * 9, kRows2 * 9 * sizeof(float));
+#pragma unroll
+          for (int a = 0; a < kO3; ++a)
+            if (op.out3[a]) bulk_store(op.out3[a] + row0 * 3, s_o3 + a * kRows2 * 3, kRows2 * 3 * sizeof(float));
+          bulk_commit();
+        }
+      } else {
+        __syncthreads();  // B
+#pragma unroll
+        for (int a = 0; a < kO9; ++a)
+          if (op.out9[a]) coop_store2<9>(op.out9[a] + row0 * 9, s_o9 + a * kRows2 * 9, rows);
+#pragma unroll
+        for (int a = 0; a < kO3; ++a)
+          if (op.out3[a]) coop_store2<3>(op.out3[a] + row0 * 3, s_o3 + a * kRows2 * 3, rows);
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_read<0>();
+}
+
+template <class Op>
+int launch_rowwise2(const Op& op, int64_t n, void* stream, const char* name) {
+  if (n < 0) return fail(SO3D_EINVAL, "negative n");
+  if (n == 0) return 0;
+  int use_tma = 1;
+  for (int a = 0; a < Op::kIn9; ++a) {
+    if (!op.in9[a]) return fail(SO3D_EINVAL, "null input pointer");
+    use_tma &= aligned16(op.in9[a]);
+  }
+  for (int a = 0; a < Op::kIn3; ++a) {
+    if (!op.in3[a]) return fail(SO3D_EINVAL, "null input pointer");
+    use_tma &= aligned16(op.in3[a]);
+  }
+  for (int a = 0; a < Op::kOut9; ++a) use_tma &= aligned16(op.out9[a]);
+  for (int a = 0; a < Op::kOut3; ++a) use_tma &= aligned16(op.out3[a]);
+  constexpr size_t smem = OpLayout2<Op>::kSmemBytes;
+  static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
+  static int resident_dev[kMaxDevices] = {};
+  auto kern = rowwise_kernel_cta2<Op>;
+  const int dev = current_device();
+  if (resident_dev[dev] == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kT2, smem) != cudaSuccess || occ < 1) occ = 1;
+    resident_dev[dev] = occ;
+  }
+  int ctas_per_sm = resident_dev[dev];
+  if (const char* e = getenv("SO3D_CTAS_PER_SM")) {
+    const int v = atoi(e);
+    if (v > 0 && v < ctas_per_sm) ctas_per_sm = v;
+  }
+  const int64_t tiles = (n + kRows2 - 1) / kRows2;
+  const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  kern<<<(int)(tiles < cap ? tiles : cap), kT2, smem, (cudaStream_t)stream>>>(op, n, use_tma);
+  return check_launch(name);
+}
+
 // dummy arrays for ops without a given kind of operand (zero-length arrays are not allowed)
 #define SO3D_OP_ARRAYS(I9, I3, O9, O3) SO3D_OP_ARRAYS_S(I9, I3, O9, O3, 2)
 // S = output stages: 2 (double-buffered) or 1 (less shared memory -> more resident CTAs, for latency-bound ops)
@@ -1055,6 +1245,10 @@ struct QSampleOp {
   }
 };
 
+// (Forward noising was also tried on two rows per thread with the CTA-synchronous two-row kernel, the step indices
+// travelling with the tile: bit-identical, but SLOWER than the warp-autonomous one-row kernel above -- 0.432 vs 0.395 ms per
+// 2^24 rows, and 0.688 vs 0.486 ms with the score output (profiles/r03l_qsample_lanes_negative.jsonl): this kernel lives
+// on hiding its dependent L2 accesses across tiles, which the CTA-synchronous schedule does not do.  Removed again.)
 struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
   SO3D_OP_ARRAYS(2, 0, 1, 0)
   SO3D_OP_NO_TAB
@@ -1134,6 +1328,73 @@ struct PStepOp {
     }
     o9[0] = quat_to_mat_unit(qm);
     if (kX0) o9[kX0 ? 1 : 0] = quat_to_mat_unit(qh);
+  }
+};
+
+// The shared-t reverse step on two rows per thread (rowwise_kernel_cta2): the arithmetic of PStepOp<true, false> through the
+// two-lane instantiations of so3d_lanes.cuh -- the same IEEE operations per row, hence the same bits.
+// Measured on B200, 2^24 rows (profiles/r03k_pstep_lanes.jsonl): one row per thread 0.3446 ms; two rows per thread with
+// 256 threads / 512-row tiles (2 resident CTAs) 0.3478; 128 threads / 256-row tiles, two output stages (4 CTAs) 0.3346; one
+// output stage (44 KB of shared memory -> 5 CTAs of 4 warps) 0.3217 ms = 0.67 of the HBM roofline.
+#ifndef SO3D_PSS2_OUTSTAGES
+#define SO3D_PSS2_OUTSTAGES 1
+#endif
+#ifndef SO3D_PSS2_MINCTAS
+#define SO3D_PSS2_MINCTAS 5
+#endif
+template <bool kDevSeed>
+struct PStep2Op {
+  SO3D_OP_ARRAYS_S(1, 1, 1, 0, SO3D_PSS2_OUTSTAGES)  // in: x_t, pred;  out9: x_{t-1}
+  static constexpr int kTab = kTabCdfFloats;
+  static constexpr int kMinCtas = SO3D_PSS2_MINCTAS;
+  const int64_t* t;
+  const float* recip;
+  const float* recipm1;
+  const float* coef1;
+  const float* coef2;
+  int64_t T;
+  const float* post_cdf;
+  const float* loc;
+  uint64_t seed, rng_offset, row_offset;
+  const uint64_t* seed_dev;
+  __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
+  __device__ void setup(float* tab) const {
+    if (post_cdf) stage_cdf(tab, post_cdf + clamp_t(t[0]) * kCdf, loc);
+    if (threadIdx.x == 0) {
+      const int64_t ti = clamp_t(t[0]);
+      tab[kTabScal] = __int_as_float((int)ti);
+      tab[kTabScal + 1] = recip[ti];
+      tab[kTabScal + 2] = recipm1[ti];
+      tab[kTabScal + 3] = coef1[ti];
+      tab[kTabScal + 4] = coef2[ti];
+      if (kDevSeed) {
+        const uint64_t sd = *seed_dev;
+        tab[kTabScal + 5] = __uint_as_float((uint32_t)sd);
+        tab[kTabScal + 6] = __uint_as_float((uint32_t)(sd >> 32));
+      }
+    }
+  }
+  __device__ void row2(int64_t i0, const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*)[2], const float* tab) const {
+    const int ti = __float_as_int(tab[kTabScal]);
+    const float k_recip = tab[kTabScal + 1], k_recipm1 = tab[kTabScal + 2], k_c1 = tab[kTabScal + 3], k_c2 = tab[kTabScal + 4];
+    const Mat3L<L2> x = lanes_of(a9[0][0], a9[0][1]);
+    const Vec3L<L2> pred{L2{a3[0][0].x, a3[0][1].x}, L2{a3[0][0].y, a3[0][1].y}, L2{a3[0][0].z, a3[0][1].z}};
+    QuatL<L2> qh;
+    QuatL<L2> qm = p_mean_quat_l<L2, true>(x, pred, k_recip, k_recipm1, k_c1, k_c2, &qh);
+    if (post_cdf && ti != 0) {  // diffusion.py:320-326
+      const uint64_t sd = kDevSeed ? ((uint64_t)__float_as_uint(tab[kTabScal + 5]) | ((uint64_t)__float_as_uint(tab[kTabScal + 6]) << 32)) : seed;
+      const uint64_t row = row_offset + (uint64_t)i0;
+      const U4 r0 = philox4x32_10(sd, row, rng_offset), r1 = philox4x32_10(sd, row + kT2, rng_offset);
+      const Vec3L<L2> axis = sphere_from_uniforms_l(L2{u01(r0.x), u01(r1.x)}, L2{u01(r0.y), u01(r1.y)});
+      const L2 ang{shared_row_angle(tab, u01(r0.z)), shared_row_angle(tab, u01(r1.z))};
+      qm = qmul_l(qm, quat_axis_angle_l(axis, ang));
+    }
+    const Mat3L<L2> o = quat_to_mat_unit_l(qm);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      o9[0][0].m[k] = o.m[k].x;
+      o9[0][1].m[k] = o.m[k].y;
+    }
   }
 };
 
@@ -1502,6 +1763,18 @@ static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t,
                          const float* coef1, const float* coef2, int64_t T, const float* post_cdf, const uint32_t* post_guide,
                          const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* out, float* x0_hat_out,
                          int64_t n, void* stream, const uint64_t* seed_dev = nullptr) {
+  if constexpr (kSharedT && !kX0) {
+    // the hot shared-t step: two rows per thread with packed FP32 (SO3D_PSTEP_LANES=1 selects the one-row kernel for A/B runs)
+    static const bool one_lane = [] { const char* e = getenv("SO3D_PSTEP_LANES"); return e && atoi(e) == 1; }();
+    if (!one_lane && post_cdf) {
+      PStep2Op<kDevSeed> op2;
+      op2.seed_dev = seed_dev;
+      op2.in9[0] = x_t; op2.in3[0] = pred3; op2.out9[0] = out;
+      op2.t = t; op2.recip = recip; op2.recipm1 = recipm1; op2.coef1 = coef1; op2.coef2 = coef2; op2.T = T;
+      op2.post_cdf = post_cdf; op2.loc = loc; op2.seed = seed; op2.rng_offset = rng_offset; op2.row_offset = row_offset;
+      return launch_rowwise2(op2, n, stream, "so3d_p_sample_f32");
+    }
+  }
   PStepOp<kSharedT, kX0, kDevSeed> op;
   op.seed_dev = seed_dev;
   op.in9[0] = x_t; op.in3[0] = pred3; op.out9[0] = out;
