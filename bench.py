@@ -479,6 +479,19 @@ def main():
             extra[f"score_evals_per_sec_{mode_name}"] = {"value": v, "ms_per_step": m}
             if mode_name == "auto":
                 extra[f"score_evals_per_sec_{mode_name}"]["roofline"] = hbm_roof(v / world, BYTES_PER_EVAL, pk)
+        # small batches of the same evaluator (north_star: "warp-shuffle reductions for the per-omega series partial sums"):
+        # below ~96 rows per SM the library runs ONE WARP per rotation, the 2000 terms split over the lanes
+        if rank == 0:
+            sb = {}
+            for nb in (256, 4096, 9472, 16384):
+                ms_b = time_loop(lambda: lib_call("so3d_igso3_logp_score_f32", ptr(R), ptr(eps), 1, ptr(logp), ptr(score), None, nb, dx._lib.MODE_SERIES, L,
+                                                  device=device), 50, 5, False) / 50
+                sb[str(nb)] = {"us_per_call": ms_b * 1e3, "evals_per_s": nb / (ms_b * 1e-3)}
+            extra["series_small_batch"] = {"rows": sb, "note": "back-to-back launches through the Python binding, device-timed (~13 us of host launch overhead per call "
+                                                               "bounds the small sizes; kernel durations are in profiles/*_launches.md); <= 9472 rows (64 per SM): one warp per "
+                                                               "rotation (series_warp_kernel), above: one thread per rotation (16384 shown for contrast)"}
+        if dist_on:
+            torch.distributed.barrier()
         proc = dx.SO3Diffusion(None).to(device)
         proc.row_offset = rank * n
         fwd, post, t_range = proc.tables()

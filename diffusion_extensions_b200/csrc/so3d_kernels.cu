@@ -1008,6 +1008,46 @@ __global__ void __launch_bounds__(256) density_kernel(const float* __restrict__ 
   }
 }
 
+// Small batches of the series evaluator: ONE WARP per rotation, the L terms split over the 32 lanes (so3d_math.cuh,
+// igso3_series_lane): a 4096-row call is 4096 independent 64-term chains instead of 128 warps running 2000-term chains.
+template <int kMode>
+__global__ void __launch_bounds__(256) series_warp_kernel(const float* __restrict__ R, const float* __restrict__ eps, int eps_stride,
+                                                          float* __restrict__ logp, float* __restrict__ score3, float* __restrict__ dlogf,
+                                                          int64_t n, int L) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int B = igso3_series_lane_terms(L);
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    Mat3 m;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m.m[k] = __ldg(R + row * 9 + k);  // same address in every lane: one broadcast transaction each
+    const AxisAngleF a = axis_angle_fast(m);
+    const float e = __ldg(eps + row * eps_stride);
+    float kap, kapp, cexp;
+    igso3_series_lane_setup(a.theta, e, &kap, &kapp, &cexp);
+    SeriesLaneState st = igso3_series_lane(kap, kapp, cexp, lane, B, L);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      st.b += __shfl_xor_sync(0xffffffffu, st.b, off);
+      st.d += __shfl_xor_sync(0xffffffffu, st.d, off);
+      st.bp += __shfl_xor_sync(0xffffffffu, st.bp, off);
+      st.dp += __shfl_xor_sync(0xffffffffu, st.dp, off);
+    }
+    if (lane == 0) {
+      const float F = 2.0f * st.b - st.d, dF = 2.0f * st.bp - st.dp;
+      float lf = logf(2.0f * F), g = dF / F;
+      if ((kMode == kSeries || kMode == kSeriesAdaptive) && e <= kAutoSeriesEps && a.theta > kSeriesGuard * e) igso3_closed_f32(a.theta, e, &lf, &g);
+      logp[row] = lf;
+      if (dlogf) dlogf[row] = g;
+      if (score3) {
+        score3[row * 3] = g * a.axis.x;
+        score3[row * 3 + 1] = g * a.axis.y;
+        score3[row * 3 + 2] = g * a.axis.z;
+      }
+    }
+  }
+}
+
 // distributions.py:15-30.  One CTA per eps row: fp64 density at the 1000 grid points -> fp32, times
 // the Haar weight (fp32), trapezoid increments (fp32), prefix sum accumulated in double and rounded
 // to float per entry (what ATen's CPU cumsum does for float), normalised by the last entry.
@@ -1706,6 +1746,22 @@ int so3d_igso3_logp_score_f32(const float* R, const float* eps, int eps_stride, 
   SO3D_REQUIRE(n == 0 || (R && eps && logp), "so3d_igso3_logp_score_f32: null pointer");
   SO3D_REQUIRE(eps_stride == 0 || eps_stride == 1, "eps_stride must be 0 or 1");
   if (int rc = check_mode(mode, L)) return rc;
+  // small batches of the series: one warp per rotation (up to 64 rows per SM -- one full wave of warps -- the
+  // one-thread-per-rotation kernel is a handful of warps running 2000-term dependent chains; measured cross-over ~14 000 rows
+  // on 148 SMs, profiles/r03m_bench.json; SO3D_SERIES_WARP_ROWS overrides the threshold, 0 disables)
+  if (n > 0 && (mode == SO3D_MODE_SERIES || mode == SO3D_MODE_SERIES_ADAPTIVE || mode == SO3D_MODE_SERIES_PURE)) {
+    static const int64_t rows_per_sm = [] { const char* e = getenv("SO3D_SERIES_WARP_ROWS"); return e ? (int64_t)atoll(e) : (int64_t)64; }();
+    if (n <= rows_per_sm * sm_count()) {
+      const int64_t blocks = (n * 32 + 255) / 256;
+      const int64_t cap = (int64_t)sm_count() * 8;
+      const int grid = (int)(blocks < cap ? blocks : cap);
+      if (mode == SO3D_MODE_SERIES_PURE)
+        series_warp_kernel<kSeriesPure><<<grid, 256, 0, (cudaStream_t)stream>>>(R, eps, eps_stride, logp, score3, dlogf, n, L);
+      else
+        series_warp_kernel<kSeries><<<grid, 256, 0, (cudaStream_t)stream>>>(R, eps, eps_stride, logp, score3, dlogf, n, L);
+      return check_launch("so3d_igso3_logp_score_f32");
+    }
+  }
   switch (mode) {
     case SO3D_MODE_SERIES: return launch_logp_score<kSeries>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);
     case SO3D_MODE_CLOSED: return launch_logp_score<kClosed>(R, eps, eps_stride, logp, score3, dlogf, n, L, stream);

@@ -174,3 +174,7 @@ extern "C" long hm_lanes_sphere(const float* ua, const float* ub, float* axis, l
   }
   return bad;
 }
+// the warp-split series (one warp per rotation), emulated lane by lane with the kernel's reduction order
+extern "C" void hm_series_warp(const float* w, const float* eps, float* logf, float* g, long n, int L, int guarded) {
+  for (long i = 0; i < n; ++i) igso3_series_warp_host(w[i], eps[i], L, logf + i, g + i, guarded != 0);
+}

@@ -318,6 +318,29 @@ def test_logp_score_series_L2000(dx, cuda_device):
     assert ef3.max() > 1e-5                  # the reason the guard exists
 
 
+def test_logp_score_series_small_batch_warp_split(dx, cuda_device):
+    """Small batches of the series evaluator run one WARP per rotation (the L terms split over the lanes, partial results
+    combined with warp shuffles): same 1e-5 bound against the fp64 series on the whole E-set, within a few 1e-6 of the
+    one-thread-per-rotation kernel (the same rows evaluated inside a large batch), ragged sizes, per-row and shared eps."""
+    big_n = 1 << 16
+    R, eps = eset(big_n, 29)
+    om, axis, ft, gt = truth_from_R(R, eps)
+    Rd, ed = dev(R, cuda_device), dev(eps, cuda_device)
+    lp_big, sc_big, _ = dx.ops.igso3_logp_score(Rd, ed, mode="series", L=2000)          # one thread per rotation
+    for n in (1, 33, 4096, 10000):
+        lp, sc, _ = dx.ops.igso3_logp_score(Rd[:n].contiguous(), ed[:n].contiguous(), mode="series", L=2000)   # one warp per rotation
+        ef = np.abs(np.exp(host(lp) - np.log(ft[:n])) - 1)
+        gk = (host(sc) * axis[:n]).sum(-1)
+        eg = np.abs(gk - gt[:n]) / np.maximum(np.abs(gt[:n]), 1e-30)
+        assert ef.max() < 1e-5 and eg[om[:n] > 1e-4].max(initial=0.0) < 1e-5, n
+        assert np.max(np.abs(np.exp(host(lp) - host(lp_big[:n])) - 1)) < 8e-6, n
+    # shared eps, and the raw sum
+    e0 = torch.tensor(0.9, device=cuda_device)     # (every E-set angle is inside 4.2 eps for this eps: the raw sum stays positive)
+    a, _, _ = dx.ops.igso3_logp_score(Rd[:500].contiguous(), e0, mode="series_pure", L=2000)
+    b, _, _ = dx.ops.igso3_logp_score(Rd[:500].contiguous(), e0.expand(500).contiguous(), mode="series_pure", L=2000)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
 def test_scalar_vs_per_row_eps(dx, cuda_device):
     R, _ = eset(5000, 19)
     Rd = dev(R, cuda_device)

@@ -476,3 +476,38 @@ def test_lanes_header_restates_the_scalar_arithmetic_bit_for_bit(hm):
     hm.hm_lanes_sphere.restype = ctypes.c_long
     assert hm.hm_lanes_sphere(fp(ua), fp(ub), fp(axis), ctypes.c_long(n)) == 0
     assert np.max(np.abs(np.linalg.norm(axis.astype(np.float64), axis=-1) - 1)) < 1e-6
+
+
+def test_series_warp_split(hm):
+    """The one-warp-per-rotation form of the series (small batches: the L terms split over the 32 lanes, block results
+    propagated by powers of the homogeneous transfer matrix, butterfly sum), emulated lane by lane in the kernel's reduction
+    order: same 1e-5 bound against the fp64 series as the one-thread recurrence -- below the conditioning guard for the raw
+    sum, on the whole E-set with the guard -- and within a few 1e-6 of the one-thread result."""
+    n = 12000
+    om, eps, k = eset(n, 23)
+    om[:20] = 0.0
+    ft, gt = _truth(om, eps)
+    hm.hm_series_warp.restype = None
+    for L in (2000, 1999, 64, 2896):
+        lf = np.empty(n, np.float32); g = np.empty(n, np.float32)
+        hm.hm_series_warp(fp(om), fp(eps), fp(lf), fp(g), ctypes.c_long(n), L, 1)
+        if L < 1999:
+            continue   # short truncations are only checked for finiteness below (the truth above is the full series)
+        ef = np.abs(np.exp(lf.astype(np.float64) - np.log(ft)) - 1)
+        eg = np.abs(g - gt) / np.maximum(np.abs(gt), 1e-30)
+        assert ef.max() < 1e-5 and eg[om > 0].max() < 1e-5, L
+        assert np.all(g[om == 0] == 0)
+    # short truncations (one or two terms per lane; a truncated series is only meaningful once it has converged: eps >= 0.5)
+    eb = np.maximum(eps, 0.5).astype(np.float32)
+    for L in (33, 64):
+        lw = np.empty(n, np.float32); gw = np.empty(n, np.float32); l1 = np.empty(n, np.float32); g1 = np.empty(n, np.float32)
+        hm.hm_series_warp(fp(om), fp(eb), fp(lw), fp(gw), ctypes.c_long(n), L, 0)
+        hm.hm_logf_g(fp(om), fp(eb), fp(l1), fp(g1), ctypes.c_long(n), 4, L)
+        ok = om <= 4.2 * eb     # (beyond the guard both sums are rounding noise times the condition number)
+        assert np.max(np.abs(np.exp(lw.astype(np.float64) - l1.astype(np.float64)) - 1)[ok]) < 3e-6, L
+    # raw sum: against the one-thread recurrence (mode series_pure)
+    lw = np.empty(n, np.float32); gw = np.empty(n, np.float32); l1 = np.empty(n, np.float32); g1 = np.empty(n, np.float32)
+    hm.hm_series_warp(fp(om), fp(eps), fp(lw), fp(gw), ctypes.c_long(n), 2000, 0)
+    hm.hm_logf_g(fp(om), fp(eps), fp(l1), fp(g1), ctypes.c_long(n), 4, 2000)
+    well = om <= 4.2 * eps
+    assert np.max(np.abs(np.exp(lw.astype(np.float64) - l1.astype(np.float64)) - 1)[well]) < 8e-6
