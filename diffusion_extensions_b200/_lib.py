@@ -107,11 +107,22 @@ def check_f32(t, name, last=None):
     return t.contiguous()
 
 
+_fn_cache = {}
+
+
 def call(name, *args, device=None):
-    """Invoke an entry point on the current stream of `device`; raise RuntimeError on failure."""
-    lib = load()
-    with torch.cuda.device(device):
-        rc = getattr(lib, name)(*args, stream_ptr(device))
+    """Invoke an entry point on the current stream of `device`; raise RuntimeError on failure.
+    The launch happens under `device` as the current CUDA device; the context switch (a few microseconds of host time
+    per call, which small launches feel) is skipped when `device` already is the current one."""
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    idx = None if device is None else torch.device(device).index
+    if idx is None or idx == torch.cuda.current_device():
+        rc = fn(*args, torch.cuda.current_stream().cuda_stream)
+    else:
+        with torch.cuda.device(idx):
+            rc = fn(*args, torch.cuda.current_stream(idx).cuda_stream)
     if rc != 0:
-        msg = lib.so3d_last_error().decode("utf-8", "replace")
+        msg = load().so3d_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")
