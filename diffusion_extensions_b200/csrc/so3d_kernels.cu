@@ -615,6 +615,17 @@ __device__ __forceinline__ void coop_store2(float* __restrict__ g, const float* 
   for (int i = threadIdx.x; i < rows * W; i += kT2) __stcs(g + i, sm[i]);
 }
 
+// input stages of a two-row op: 2 (tile k+2 in flight while k is computed) or 1 (the single stage is refilled with tile
+// k+1 as soon as every thread holds its rows of tile k in registers: 12 KB less shared memory per CTA -> more resident CTAs)
+template <class Op, class = void>
+struct OpInStages {
+  static constexpr int value = 2;
+};
+template <class Op>
+struct OpInStages<Op, std::void_t<decltype(Op::kInStages)>> {
+  static constexpr int value = Op::kInStages;
+};
+
 template <class Op>
 struct OpLayout2 {
   static constexpr int kInWords = Op::kIn9 * 9 + Op::kIn3 * 3;
@@ -623,7 +634,8 @@ struct OpLayout2 {
   static constexpr int kInFloats = kRows2 * kInWords;
   static constexpr int kOutFloats = kRows2 * kOutWords;
   static constexpr int kTabFloats = (Op::kTab + 3) & ~3;
-  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(2 * kInFloats + kOutStages * kOutFloats + kTabFloats) + 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
+  static constexpr int kInStages = OpInStages<Op>::value;
+  static constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kInStages * kInFloats + kOutStages * kOutFloats + kTabFloats) + 2 * sizeof(uint64_t) + 2 * sizeof(uint32_t);
 };
 
 template <class Op>
@@ -632,7 +644,8 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_cta2
   constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
   using Lay = OpLayout2<Op>;
   float* smem = reinterpret_cast<float*>(smem4);
-  float* s_out = smem + 2 * Lay::kInFloats;
+  constexpr int kIS = Lay::kInStages;
+  float* s_out = smem + kIS * Lay::kInFloats;
   float* s_tab = s_out + Lay::kOutStages * Lay::kOutFloats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
   const int tid = threadIdx.x;
@@ -648,7 +661,7 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_cta2
   const int64_t first_row = (int64_t)blockIdx.x * kRows2, stride_rows = (int64_t)gridDim.x * kRows2;
   auto issue_load = [&](int k, int64_t row0) {  // thread 0 only
     if (kI9 + kI3 == 0) return;
-    const int st = k & 1;
+    const int st = kIS == 2 ? (k & 1) : 0;
     float* base = smem + st * Lay::kInFloats;
     mbar_expect_tx(&bars[st], (uint32_t)(kRows2 * Lay::kInWords * sizeof(float)));
 #pragma unroll
@@ -658,23 +671,23 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_cta2
   };
   if (tid == 0 && use_tma) {
     if (my_full > 0) issue_load(0, first_row);
-    if (my_full > 1) issue_load(1, first_row + stride_rows);
+    if (kIS == 2 && my_full > 1) issue_load(1, first_row + stride_rows);
   }
   op.setup(s_tab);
   __syncthreads();
 
   int64_t row0 = first_row;
   for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
-    const int st = k & 1;
+    const int st = kIS == 2 ? (k & 1) : 0;
     const int rows = k < my_full ? kRows2 : (int)(n - row0);
     const bool tma = use_tma && rows == kRows2;
     float* s_i9 = smem + st * Lay::kInFloats;
     float* s_i3 = s_i9 + kI9 * kRows2 * 9;
-    float* s_o9 = s_out + (Lay::kOutStages == 2 ? st : 0) * Lay::kOutFloats;
+    float* s_o9 = s_out + (Lay::kOutStages == 2 ? (k & 1) : 0) * Lay::kOutFloats;
     float* s_o3 = s_o9 + kO9 * kRows2 * 9;
     if (kI9 + kI3 > 0) {
       if (tma) {
-        mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+        mbar_wait(&bars[st], (uint32_t)(kIS == 2 ? ((k >> 1) & 1) : (k & 1)));
       } else {
 #pragma unroll
         for (int a = 0; a < kI9; ++a) coop_load2<9>(s_i9 + a * kRows2 * 9, op.in9[a] + row0 * 9, rows);
@@ -697,7 +710,7 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_cta2
     }
     if (Lay::kOutStages == 2 && tid == 0) bulk_wait_read<1>();
     __syncthreads();  // A
-    if (tid == 0 && use_tma && k + 2 < my_full) issue_load(k + 2, row0 + 2 * stride_rows);
+    if (tid == 0 && use_tma && k + kIS < my_full) issue_load(k + kIS, row0 + kIS * stride_rows);
 
     Mat3 o9[kO9 > 0 ? kO9 : 1][2];
     Vec3 o3[kO3 > 0 ? kO3 : 1][2];
@@ -1016,7 +1029,6 @@ __global__ void __launch_bounds__(256) series_warp_kernel(const float* __restric
                                                           int64_t n, int L) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int B = igso3_series_lane_terms(L);
   for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
     Mat3 m;
 #pragma unroll
@@ -1025,7 +1037,8 @@ __global__ void __launch_bounds__(256) series_warp_kernel(const float* __restric
     const float e = __ldg(eps + row * eps_stride);
     float kap, kapp, cexp;
     igso3_series_lane_setup(a.theta, e, &kap, &kapp, &cexp);
-    SeriesLaneState st = igso3_series_lane(kap, kapp, cexp, lane, B, L);
+    const int Lw = igso3_series_warp_terms(e, L);  // weights beyond it are exactly 0: same bits as all L terms
+    SeriesLaneState st = igso3_series_lane(kap, kapp, cexp, lane, igso3_series_lane_terms(Lw), Lw);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       st.b += __shfl_xor_sync(0xffffffffu, st.b, off);
@@ -1375,18 +1388,24 @@ struct PStepOp {
 // two-lane instantiations of so3d_lanes.cuh -- the same IEEE operations per row, hence the same bits.
 // Measured on B200, 2^24 rows (profiles/r03k_pstep_lanes.jsonl): one row per thread 0.3446 ms; two rows per thread with
 // 256 threads / 512-row tiles (2 resident CTAs) 0.3478; 128 threads / 256-row tiles, two output stages (4 CTAs) 0.3346; one
-// output stage (44 KB of shared memory -> 5 CTAs of 4 warps) 0.3217 ms = 0.67 of the HBM roofline.
+// output stage (44 KB of shared memory -> 5 CTAs of 4 warps) 0.3217 ms; and with ONE input stage as well (refilled as soon
+// as the rows of the current tile are in registers: 31.6 KB -> 7 CTAs, 28 warps) 0.3094 ms = 5.42e10 particle-steps/s =
+// 0.695 of the HBM roofline (profiles/r03o_pstep_instages.jsonl; two output stages on top of that: 0.3241).
 #ifndef SO3D_PSS2_OUTSTAGES
 #define SO3D_PSS2_OUTSTAGES 1
 #endif
 #ifndef SO3D_PSS2_MINCTAS
-#define SO3D_PSS2_MINCTAS 5
+#define SO3D_PSS2_MINCTAS 7
+#endif
+#ifndef SO3D_PSS2_INSTAGES
+#define SO3D_PSS2_INSTAGES 1
 #endif
 template <bool kDevSeed>
 struct PStep2Op {
   SO3D_OP_ARRAYS_S(1, 1, 1, 0, SO3D_PSS2_OUTSTAGES)  // in: x_t, pred;  out9: x_{t-1}
   static constexpr int kTab = kTabCdfFloats;
   static constexpr int kMinCtas = SO3D_PSS2_MINCTAS;
+  static constexpr int kInStages = SO3D_PSS2_INSTAGES;
   const int64_t* t;
   const float* recip;
   const float* recipm1;

@@ -966,15 +966,19 @@ SO3D_HD Mat2D mat2d_mul(const Mat2D& x, const Mat2D& y) {  // (X Y, X' Y + X Y')
   return r;
 }
 // Lane `lane` of 32: its block's state propagated to l = 0.  B = terms per lane (32 B >= L); terms l >= L weigh 0.
+// (Carrying only ONE homogeneous sequence S_m = sin(m w)/sin(w) and deriving P^m = [[S_{m+1} - S_m, S_m], [-kappa S_m,
+// S_m - S_{m-1}]] from it halves the homogeneous work, but the difference S_{m+1} - S_m loses 6 bits at small w and the
+// powers amplify it: 1.1e-5 instead of 1.6e-6 on the E-set.  Both unit vectors are carried.)
 SO3D_HD SeriesLaneState igso3_series_lane(float kap, float kapp, float cexp, int lane, int B, int L) {
   float b = 0.f, d = 0.f, bp = 0.f, dp = 0.f;
   // images of the unit vectors e_b = (1, 0) and e_d = (0, 1) under the homogeneous steps, and their derivatives
   float ub = 1.f, ud = 0.f, vb = 0.f, vd = 1.f, upb = 0.f, upd = 0.f, vpb = 0.f, vpd = 0.f;
-  const int top = B * lane + B - 1;
+  float lf = (float)(B * lane + B - 1);
+  const float Lf = (float)L;
+#pragma unroll 4
   for (int i = 0; i < B; ++i) {
-    const int l = top - i;
-    const float lf = (float)l;
-    const float A = l < L ? fast_ex2((float)(l * (l + 1)) * cexp) * (lf + 0.5f) : 0.f;
+    const float mm = fmaf(lf, lf, lf);  // l (l + 1), exact below 2^24
+    const float A = lf < Lf ? fast_ex2(mm * cexp) * (lf + 0.5f) : 0.f;
     const float dpn = fmaf(-kap, bp, fmaf(-kapp, b, dp));
     const float dn = fmaf(-kap, b, A + d);
     bp += dpn;
@@ -991,13 +995,14 @@ SO3D_HD SeriesLaneState igso3_series_lane(float kap, float kapp, float cexp, int
     vpd = vpdn;
     ud = udn;
     vd = vdn;
+    lf -= 1.0f;
   }
   // G = P^B: columns are the images of e_b and e_d, rows are (b, d)
   Mat2D g{ub, vb, ud, vd, upb, vpb, upd, vpd};
   Mat2D acc{1.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
   for (int bit = 0; bit < 5; ++bit) {  // acc = G^lane
     if ((lane >> bit) & 1) acc = mat2d_mul(acc, g);
-    g = mat2d_mul(g, g);
+    if ((lane >> (bit + 1)) != 0) g = mat2d_mul(g, g);
   }
   SeriesLaneState o;
   o.b = fmaf(acc.a11, b, acc.a12 * d);
@@ -1005,6 +1010,13 @@ SO3D_HD SeriesLaneState igso3_series_lane(float kap, float kapp, float cexp, int
   o.bp = fmaf(acc.d11, b, fmaf(acc.d12, d, fmaf(acc.a11, bp, acc.a12 * dp)));
   o.dp = fmaf(acc.d21, b, fmaf(acc.d22, d, fmaf(acc.a21, bp, acc.a22 * dp)));
   return o;
+}
+// Terms the warp actually needs: the weights beyond igso3_series_live_terms(eps) are exactly 0 (ex2.approx.ftz flushes them), so
+// summing min(L, live) terms gives the bits of summing L -- and with one rotation per warp the count is warp-uniform.
+SO3D_HD int igso3_series_live_terms(float eps, int L);
+SO3D_HD int igso3_series_warp_terms(float eps, int L) {
+  const int live = igso3_series_live_terms(eps, L);
+  return live < 32 ? 32 : live;
 }
 SO3D_HD int igso3_series_lane_terms(int L) { return (L + 31) / 32; }
 SO3D_HD void igso3_series_lane_setup(float w, float eps, float* kap, float* kapp, float* cexp) {
@@ -1018,9 +1030,10 @@ SO3D_HD void igso3_series_lane_setup(float w, float eps, float* kap, float* kapp
 SO3D_HD void igso3_series_warp_host(float w, float eps, int L, float* logf_out, float* g_out, bool guarded) {
   float kap, kapp, cexp;
   igso3_series_lane_setup(w, eps, &kap, &kapp, &cexp);
-  const int B = igso3_series_lane_terms(L);
+  const int Lw = igso3_series_warp_terms(eps, L);
+  const int B = igso3_series_lane_terms(Lw);
   SeriesLaneState s[32];
-  for (int j = 0; j < 32; ++j) s[j] = igso3_series_lane(kap, kapp, cexp, j, B, L);
+  for (int j = 0; j < 32; ++j) s[j] = igso3_series_lane(kap, kapp, cexp, j, B, Lw);
   for (int off = 16; off > 0; off >>= 1) {
     SeriesLaneState t[32];
     for (int j = 0; j < 32; ++j) {

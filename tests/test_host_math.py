@@ -504,7 +504,7 @@ def test_series_warp_split(hm):
         hm.hm_series_warp(fp(om), fp(eb), fp(lw), fp(gw), ctypes.c_long(n), L, 0)
         hm.hm_logf_g(fp(om), fp(eb), fp(l1), fp(g1), ctypes.c_long(n), 4, L)
         ok = om <= 4.2 * eb     # (beyond the guard both sums are rounding noise times the condition number)
-        assert np.max(np.abs(np.exp(lw.astype(np.float64) - l1.astype(np.float64)) - 1)[ok]) < 3e-6, L
+        assert np.max(np.abs(np.exp(lw.astype(np.float64) - l1.astype(np.float64)) - 1)[ok]) < 8e-6, L   # (cond 14 at the guard: ~4 u cond each)
     # raw sum: against the one-thread recurrence (mode series_pure)
     lw = np.empty(n, np.float32); gw = np.empty(n, np.float32); l1 = np.empty(n, np.float32); g1 = np.empty(n, np.float32)
     hm.hm_series_warp(fp(om), fp(eps), fp(lw), fp(gw), ctypes.c_long(n), 2000, 0)
