@@ -916,3 +916,99 @@ def test_host_score_pipeline(dx, cuda_device):
         pipe.finish(wait=True)
         assert torch.equal(hl, logp[:, 0].cpu()) and torch.equal(hs, score.cpu())
         assert torch.equal(hl2, logp2[:, 0].cpu()) and torch.equal(hs2, score2.cpu())
+
+
+# ---------------------------------------------------------------------------------------------
+# behaviour around the kernels (round-1 advisor findings)
+# ---------------------------------------------------------------------------------------------
+def test_random_stream_follows_torch_seeding(dx, cuda_device):
+    """Without dx.manual_seed the sampling kernels follow torch's CUDA generator: torch.manual_seed(s) restarts the stream
+    even when s is the SAME seed as before (the usual way to reproduce a run), consecutive launches differ, and torch's own
+    random ops in between shift the stream deterministically.  dx.manual_seed(s) selects the explicit stream instead."""
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    x0 = dev(rand_rots(3000, 91)[0], cuda_device)
+    t = torch.randint(0, 1000, (3000,), device=cuda_device)
+    dx.ops.rng._explicit = False                      # (earlier tests of this module seeded the explicit stream)
+    torch.manual_seed(5)
+    a1 = p.q_sample(x0, t)
+    a2 = p.q_sample(x0, t)
+    torch.manual_seed(5)                              # same seed again
+    b1 = p.q_sample(x0, t)
+    b2 = p.q_sample(x0, t)
+    assert torch.equal(a1, b1) and torch.equal(a2, b2) and not torch.equal(a1, a2)
+    torch.manual_seed(5)
+    torch.rand(7, device=cuda_device)                 # a torch op consumes part of the stream first
+    c1 = p.q_sample(x0, t)
+    torch.manual_seed(5)
+    torch.rand(7, device=cuda_device)
+    c2 = p.q_sample(x0, t)
+    assert torch.equal(c1, c2) and not torch.equal(c1, a1)
+    torch.manual_seed(6)
+    assert not torch.equal(p.q_sample(x0, t), a1)
+    dx.manual_seed(5)
+    e1 = p.q_sample(x0, t)
+    dx.manual_seed(5)
+    e2 = p.q_sample(x0, t)
+    assert torch.equal(e1, e2)
+
+
+def test_tables_follow_the_schedule_buffers(dx, cuda_device):
+    """The cached CDF tables belong to the schedule buffers they were built from: loading a state dict with other betas
+    (same T) or editing the buffers in place rebuilds them on the next call -- noise is never drawn from stale tables."""
+    p = dx.SO3Diffusion(None, timesteps=50).to(cuda_device)
+    fwd0 = p.tables()[0].clone()
+    assert p.tables()[0].data_ptr() == p.tables()[0].data_ptr()          # cached while nothing changes
+    other = dx.SO3Diffusion(None, timesteps=50, betas=np.linspace(1e-4, 0.05, 50)).to(cuda_device)
+    p.load_state_dict(other.state_dict())
+    fwd1 = p.tables()[0]
+    assert not torch.equal(fwd0, fwd1) and torch.equal(fwd1, other.tables()[0])
+    g1 = p.guides()[0]
+    assert torch.equal(g1, other.guides()[0])
+    p.sqrt_one_minus_alphas_cumprod.mul_(0.5)                             # in-place edit
+    assert not torch.equal(p.tables()[0], fwd1)
+    s = dx.SE3Diffusion(None, timesteps=50).to(cuda_device)
+    sig0 = s._sigma().clone()
+    s.posterior_log_variance_clipped.add_(1.0)
+    assert torch.allclose(s._sigma(), sig0 * math.exp(0.5))
+
+
+def test_graph_cache_keys_and_batched_mean_sample(dx, cuda_device):
+    """(a) p_sample_loop(cuda_graph=True) of a Projected* process is keyed on the projection closure: a second projection
+    with the same batch shape captures its own graph instead of replaying the first one (aircraft_test.py:73 sets a
+    projection per item).  (b) IsotropicGaussianSO3 / IGSO3xR3 with a scalar eps and a batched mean broadcast the mean
+    against the noise like the reference (diffusion.py:482)."""
+    torch.manual_seed(2)
+    net = torch.nn.Sequential(torch.nn.Linear(10, 32), torch.nn.SiLU(), torch.nn.Linear(32, 3)).to(cuda_device)
+    calls = []
+
+    def denoise(x, t):
+        return net(torch.cat([x.flatten(-2), (t.float() / 20)[:, None]], -1))
+
+    proc = dx.ProjectedSO3Diffusion(denoise, timesteps=20).to(cuda_device)
+    Ra = dev(rand_rots(1, 5)[0], cuda_device)[0]
+    Rb = dev(rand_rots(1, 6)[0], cuda_device)[0]
+    proj_a = lambda x: (calls.append("a"), x @ Ra)[1]
+    proj_b = lambda x: (calls.append("b"), x @ Rb)[1]
+    dx.manual_seed(1)
+    proc.p_sample_loop((64,), proj_a, cuda_graph=True)
+    n_a = calls.count("a")
+    dx.manual_seed(1)
+    proc.p_sample_loop((64,), proj_b, cuda_graph=True)
+    assert calls.count("b") > 0 and len(proc._loop_graphs) == 2           # captured again with the new projection
+    calls.clear()
+    proc.p_sample_loop((64,), proj_a, cuda_graph=True)                    # replay: the closure is not called again
+    assert calls == [] and n_a > 0
+    # (b)
+    B = 37
+    mean = dev(rand_rots(B, 7)[0], cuda_device)
+    d = dx.IsotropicGaussianSO3(torch.tensor(0.2, device=cuda_device), mean=mean)
+    smp = d.sample()
+    assert smp.shape == (B, 3, 3)
+    rel = host(mean.transpose(-1, -2) @ smp)
+    assert np.max(np.abs(rel @ np.swapaxes(rel, -1, -2) - np.eye(3))) < 1e-5
+    from diffusion_extensions_b200.distributions import IGSO3xR3
+    from diffusion_extensions_b200.util import AffineT
+    pm = AffineT(mean, torch.randn(B, 3, device=cuda_device))
+    s3 = IGSO3xR3(torch.tensor(0.3, device=cuda_device), mean=pm, shift_scale=75.0).sample()
+    assert s3.rot.shape == (B, 3, 3) and s3.shift.shape == (B, 3)
+    assert hasattr(pm, "clone") and torch.equal(pm.clone().rot, pm.rot)
