@@ -65,7 +65,7 @@ static_assert(kBlobFloats == SO3D_ROTPREDICT_BLOB_FLOATS, "so3d.h out of sync");
 // TMEM columns of a group: accumulator, A hi, A lo
 constexpr uint32_t kColD = 0, kColAhi = 96, kColAlo = 176, kColsPerGroup = 256;
 
-constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kBlobFloats + ((kTabCdfFloats + 3) & ~3)) + 2 * 2 * 128 * 16 /* noise quaternions */ + 64;
+constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kBlobFloats + ((kTabCdfFloats + 3) & ~3)) + 2 * 2 * 128 * 16 /* noise quaternions */ + 64;  // 5 barriers, TMEM base, 2 counters
 
 __device__ __forceinline__ int canon_index(int n, int k, int N) { return (k >> 2) * (N * 4) + n * 4 + (k & 3); }
 
@@ -232,7 +232,15 @@ __device__ __forceinline__ void silu_epilogue(uint32_t tmem_lane) {
 // inside a group warp w handles TMEM lanes 32 (w % 4) .. +31 (the hardware's lane-quarter rule) and column half
 // h = (w / 4) % 2 -- two threads per particle.  Warps 16 and 17 issue the MMAs of group 0 and 1.  Hand-offs are
 // mbarriers: bar_a[g] "A operand written" (8 warp arrivals) -> issuer -> tcgen05.commit -> bar_d[g] "accumulator ready".
-constexpr int kEpiWarps = 16, kThreads = (kEpiWarps + 2) * 32;
+// (SO3D_DENOISER_ISSUER_WARPS=0 builds the variant without issuer warps: the LAST of the group's 8 warps to finish a
+// layer's operand -- an acq_rel counter in shared memory tells it -- issues the MMAs itself; see the knob above.)
+#ifndef SO3D_DENOISER_ISSUER_WARPS
+#define SO3D_DENOISER_ISSUER_WARPS 1  // 1 (shipped): two dedicated issuer warps (18 warps: 96 registers per thread, 12-40 B of spills);
+#endif                                // 0: the last epilogue warp to finish a layer's operand issues the next layer's MMAs itself (16 warps,
+                                      //    128 registers) -- measured SLOWER, 3.93 vs 3.33 ms per 2^24-particle step
+                                      //    (profiles/r03q_denoiser_issuer_negative.jsonl): the 27 MMA issues per layer then sit on an epilogue
+                                      //    warp's critical path instead of overlapping the other group's epilogue
+constexpr int kEpiWarps = 16, kThreads = (kEpiWarps + (SO3D_DENOISER_ISSUER_WARPS ? 2 : 0)) * 32;
 
 // kLoop = false: one reverse step (t = a.t[0]).  kLoop = true: the WHOLE reverse process t_hi .. t_lo in one launch --
 // particles are independent and every particle is always handled by the same thread of the same CTA, so the steps
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
   float4* s_noise = reinterpret_cast<float4*>(s_tab + ((kTabCdfFloats + 3) & ~3));   // [group][parity][particle]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_noise + 2 * 2 * kM);  // [0] weights, [1..2] bar_d, [3..4] bar_a
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+  uint32_t* s_cnt = s_tmem + 2;  // [group]: warps that have finished the current layer's A operand (runs on, mod 8)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   int64_t ti = kLoop ? a.t_hi : a.t[0];
@@ -262,6 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], 8);
     mbar_init(&bars[4], 8);
+    s_cnt[0] = 0;
+    s_cnt[1] = 0;
     fence_barrier_init();
   }
   __syncthreads();
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= kEpiWarps) {
+  if (SO3D_DENOISER_ISSUER_WARPS && warp >= kEpiWarps) {
     // ---- MMA issuer of group g: wait for the A operand, issue the layer, commit to the accumulator barrier ----
     const int g = warp - kEpiWarps;
     const uint32_t tmem_group = tmem_base + (uint32_t)g * kColsPerGroup;
@@ -338,6 +349,31 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
     const uint32_t tmem_lane = tmem_group + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes of the group's columns
     uint64_t* bar_d = &bars[1 + g];
     uint64_t* bar_a = &bars[3 + g];
+    // this warp's part of layer `layer`'s A operand is in tensor memory: tell the issuer -- or BE the issuer, if last
+    auto operand_done = [&](int layer) {
+      tc_fence_before();
+      __syncwarp();
+      if (SO3D_DENOISER_ISSUER_WARPS) {
+        if (lane == 0) mbar_arrive(bar_a);
+        return;
+      }
+      uint32_t old = 0;
+      if (lane == 0) asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&s_cnt[g])) : "memory");
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if ((old & 7u) != 7u) return;
+      if (elect_one()) {  // (issue_layer starts with tcgen05.fence::after_thread_sync)
+        if (layer == 1) {
+          issue_layer(tmem_group, blob_addr + kOffL1 * 4, blob_addr + (kOffL1 + kL1Floats) * 4, kNPad, kK1 / 8, bar_d);
+        } else if (layer < 5) {
+          const uint32_t b = blob_addr + (uint32_t)(kOffLh + (layer - 2) * 2 * kLhFloats) * 4u;
+          issue_layer(tmem_group, b, b + kLhFloats * 4u, kNPad, kKPad / 8, bar_d);
+        } else {
+          const uint32_t b = blob_addr + (uint32_t)kOffL5 * 4u;
+          issue_layer(tmem_group, b, b + kL5Floats * 4u, kN5, kKPad / 8, bar_d);
+        }
+      }
+      __syncwarp();
+    };
     const float k_recip = __ldg(a.recip + ts), k_recipm1 = __ldg(a.recipm1 + ts);
     const float k_c1 = __ldg(a.coef1 + ts), k_c2 = __ldg(a.coef2 + ts);
 
@@ -365,9 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
         SO3D_TMEM_ST8(tmem_lane + kColAlo + 8, lo, 8);
         tc_wait_st();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a);
+      operand_done(1);
       if (h == 0) {
         // prefetch the next tile's rotation while this tile runs through the network
         const int64_t in = (tile + tstride) * kM + r;
@@ -392,9 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) rotpredict_p_sample_kernel(const 
           silu_epilogue<0>(tmem_lane);
         else
           silu_epilogue<1>(tmem_lane);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a);
+        operand_done(layer);
       }
       // ---- output of layer 5 = predicted skew vector; fused reverse step (diffusion.py:291-326) ----
       mbar_wait_bounded(bar_d, ph);
