@@ -1473,6 +1473,10 @@ struct SE3QSampleOp {
   SO3D_OP_ARRAYS_S(1, 1, 1, 3, 1)  // in: rot0 | shift0;  out: rot_t | target_rot, shift_t, target_shift
   static constexpr int kTab = kGrid;
   static constexpr bool kWarpSchedule = true;
+#ifndef SO3D_SE3QS_MINCTAS
+#define SO3D_SE3QS_MINCTAS 3
+#endif
+  static constexpr int kMinCtas = SO3D_SE3QS_MINCTAS;
   const int64_t* t;
   const float* sqrt_ac;
   const float* sqrt_1m_ac;
@@ -1484,12 +1488,48 @@ struct SE3QSampleOp {
   PhiloxKey key, key_shift;  // (seed, rng_offset) and its translation stream (rng_offset | 2^63), built by the launcher
   uint64_t row_offset;
   __device__ void setup(float* tab) const { stage_cdf(tab, nullptr, loc); }
+#ifndef SO3D_SE3QS_PREFETCH
+#define SO3D_SE3QS_PREFETCH 1  // the software pipeline of QSampleOp: t two tiles ahead, draw + schedule scalars + guide record one tile ahead
+#endif
+#if SO3D_SE3QS_PREFETCH
+  struct Pre1 {
+    int64_t t;
+  };
+  struct Pre2 {
+    int ti;
+    float eps, sc;
+    NoiseDraw d;
+    uint4 rec;
+  };
+  __device__ Pre1 prefetch1(int64_t i) const { return Pre1{t[i]}; }
+  __device__ Pre2 prefetch2(int64_t i, const Pre1& p1) const {
+    Pre2 p;
+    const int64_t ti = p1.t < 0 ? 0 : (p1.t >= T ? T - 1 : p1.t);
+    p.ti = (int)ti;
+    p.eps = __ldg(sqrt_1m_ac + ti);
+    p.sc = __ldg(sqrt_ac + ti);
+    p.d = draw_axis_u(key, row_offset + (uint64_t)i);
+    p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuide + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
+    return p;
+  }
+  __device__ void row(int64_t i, const Pre2& p, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
+    const float eps = p.eps, sc = p.sc;
+    const NoiseDraw d = p.d;
+    float ang;
+    if (guide) {
+      const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+      ang = igso3_angle_from_record(cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, d.u);
+    } else {
+      ang = igso3_angle_from_uniform(cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, d.u);
+    }
+#else
   __device__ void row(int64_t i, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
     int64_t ti = t[i];
     ti = ti < 0 ? 0 : (ti >= T ? T - 1 : ti);
     const float eps = __ldg(sqrt_1m_ac + ti), sc = __ldg(sqrt_ac + ti);
     const NoiseDraw d = draw_axis_u(key, row_offset + (uint64_t)i);
     const float ang = table_row_angle(cdf, guide, ti, tab, d.u);
+#endif
     const Quat qn = quat_axis_angle(d.axis, ang);
     const AxisAngleF ax = axis_angle_fast(a9[0]);
     o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, sc * ax.theta), qn));
@@ -1566,6 +1606,76 @@ struct SE3PStepOp {
     }
     o9[0] = quat_to_mat_unit(qm);
     o3[0] = m;
+  }
+};
+
+// The shared-t SE(3) reverse step on two rows per thread (rowwise_kernel_cta2): rotation half through the two-lane
+// arithmetic of so3d_lanes.cuh, translation half as packed FMAs; the same IEEE operations per row as SE3PStepOp<true>.
+#ifndef SO3D_SE3PS2_MINCTAS
+#define SO3D_SE3PS2_MINCTAS 5
+#endif
+struct SE3PStep2Op {
+  SO3D_OP_ARRAYS_S(1, 3, 1, 1, 1)  // in: rot_t | pred_rot, shift_t, pred_shift;  out: rot | shift
+  static constexpr int kTab = kTabCdfFloats;
+  static constexpr int kMinCtas = SO3D_SE3PS2_MINCTAS;
+  static constexpr int kInStages = 1;
+  const int64_t* t;
+  const float* recip;
+  const float* recipm1;
+  const float* coef1;
+  const float* coef2;
+  const float* sigma;
+  int64_t T;
+  const float* post_cdf;
+  const float* loc;
+  float shift_scale;
+  PhiloxKey key, key_shift;
+  uint64_t row_offset;
+  __device__ int64_t clamp_t(int64_t ti) const { return ti < 0 ? 0 : (ti >= T ? T - 1 : ti); }
+  __device__ void setup(float* tab) const {
+    if (post_cdf) stage_cdf(tab, post_cdf + clamp_t(t[0]) * kCdf, loc);
+    if (threadIdx.x == 0) {
+      const int64_t ti = clamp_t(t[0]);
+      tab[kTabScal] = __int_as_float((int)ti);
+      tab[kTabScal + 1] = recip[ti];
+      tab[kTabScal + 2] = recipm1[ti];
+      tab[kTabScal + 3] = coef1[ti];
+      tab[kTabScal + 4] = coef2[ti];
+      tab[kTabScal + 5] = sigma ? sigma[ti] : 0.f;
+    }
+  }
+  __device__ void row2(int64_t i0, const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
+    const int ti = __float_as_int(tab[kTabScal]);
+    const float k_recip = tab[kTabScal + 1], k_recipm1 = tab[kTabScal + 2], k_c1 = tab[kTabScal + 3], k_c2 = tab[kTabScal + 4],
+                k_sigma = tab[kTabScal + 5];
+    const Mat3L<L2> x = lanes_of(a9[0][0], a9[0][1]);
+    const Vec3L<L2> pred{L2{a3[0][0].x, a3[0][1].x}, L2{a3[0][0].y, a3[0][1].y}, L2{a3[0][0].z, a3[0][1].z}};
+    QuatL<L2> qh;
+    QuatL<L2> qm = p_mean_quat_l<L2, true>(x, pred, k_recip, k_recipm1, k_c1, k_c2, &qh);
+    // translation: m = c1 (recip st - recipm1 ps) + c2 st   (same association as SE3PStepOp::row)
+    const Vec3L<L2> st{L2{a3[1][0].x, a3[1][1].x}, L2{a3[1][0].y, a3[1][1].y}, L2{a3[1][0].z, a3[1][1].z}};
+    const Vec3L<L2> ps{L2{a3[2][0].x, a3[2][1].x}, L2{a3[2][0].y, a3[2][1].y}, L2{a3[2][0].z, a3[2][1].z}};
+    const L2 c1 = bc<L2>(k_c1), c2 = bc<L2>(k_c2), rc = bc<L2>(k_recip), nrm1 = bc<L2>(-k_recipm1);
+    Vec3L<L2> m{fma(c1, fma(rc, st.x, mul(nrm1, ps.x)), mul(c2, st.x)), fma(c1, fma(rc, st.y, mul(nrm1, ps.y)), mul(c2, st.y)),
+                fma(c1, fma(rc, st.z, mul(nrm1, ps.z)), mul(c2, st.z))};
+    if (post_cdf && ti != 0) {
+      const uint64_t row = row_offset + (uint64_t)i0;
+      const U4 r0 = philox4x32_10(key, row), r1 = philox4x32_10(key, row + kT2);
+      const Vec3L<L2> axis = sphere_from_uniforms_l(L2{u01(r0.x), u01(r1.x)}, L2{u01(r0.y), u01(r1.y)});
+      const L2 ang{shared_row_angle(tab, u01(r0.z)), shared_row_angle(tab, u01(r1.z))};
+      qm = qmul_l(qm, quat_axis_angle_l(axis, ang));
+      const Normal4 z0 = normal4_from_u4(philox4x32_10(key_shift, row)), z1 = normal4_from_u4(philox4x32_10(key_shift, row + kT2));
+      const L2 ns = bc<L2>(k_sigma * shift_scale);
+      m = Vec3L<L2>{fma(ns, L2{z0.a, z1.a}, m.x), fma(ns, L2{z0.b, z1.b}, m.y), fma(ns, L2{z0.c, z1.c}, m.z)};
+    }
+    const Mat3L<L2> o = quat_to_mat_unit_l(qm);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      o9[0][0].m[k] = o.m[k].x;
+      o9[0][1].m[k] = o.m[k].y;
+    }
+    o3[0][0] = Vec3{m.x.x, m.y.x, m.z.x};
+    o3[0][1] = Vec3{m.x.y, m.y.y, m.z.y};
   }
 };
 
@@ -2003,9 +2113,19 @@ int so3d_se3_p_sample_f32(const float* rot_t, const float* shift_t, const float*
   SO3D_REQUIRE(t_stride == 0 || t_stride == 1, "t_stride must be 0 or 1");
   SO3D_REQUIRE(!post_cdf || (loc && sigma), "so3d_se3_p_sample_f32: loc and sigma required with post_cdf");
   SO3D_REQUIRE(rng_offset < kShiftStream, "so3d_se3_p_sample_f32: rng_offset must be below 2^63");
-  if (t_stride == 0)
+  if (t_stride == 0) {
+    static const bool one_lane = [] { const char* e = getenv("SO3D_SE3_PSTEP_LANES"); return e && atoi(e) == 1; }();  // A/B aid
+    if (!one_lane && post_cdf) {
+      SE3PStep2Op op;
+      op.in9[0] = rot_t; op.in3[0] = pred_rot3; op.in3[1] = shift_t; op.in3[2] = pred_shift3; op.out9[0] = rot_out; op.out3[0] = shift_out;
+      op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.sigma = sigma; op.T = T;
+      op.post_cdf = post_cdf; op.loc = loc; op.shift_scale = shift_scale;
+      op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
+      return launch_rowwise2(op, n, stream, "so3d_se3_p_sample_f32");
+    }
     return launch_se3_p_step<true>(rot_t, shift_t, pred_rot3, pred_shift3, t, recip, recipm1, coef1, coef2, sigma, T, post_cdf, post_guide, loc,
                                    shift_scale, seed, rng_offset, row_offset, rot_out, shift_out, n, stream);
+  }
   return launch_se3_p_step<false>(rot_t, shift_t, pred_rot3, pred_shift3, t, recip, recipm1, coef1, coef2, sigma, T, post_cdf, post_guide, loc,
                                   shift_scale, seed, rng_offset, row_offset, rot_out, shift_out, n, stream);
 }
