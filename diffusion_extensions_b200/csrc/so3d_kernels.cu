@@ -40,6 +40,9 @@ constexpr int kTile = 256;  // rows per tile == threads per CTA
 #ifndef SO3D_QS_MINCTAS
 #define SO3D_QS_MINCTAS 4    // forward noising: resident CTAs promised to ptxas (4 -> <= 64 registers, no spills)
 #endif
+#ifndef SO3D_WROW_SHFL
+#define SO3D_WROW_SHFL 1
+#endif
 #ifndef SO3D_QSX_MINCTAS
 #define SO3D_QSX_MINCTAS 4   // forward noising with the noise / score outputs compiled in
 #endif
@@ -395,6 +398,12 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_cta(uint32_t* p, uint32_t v
   return old;
 }
 
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 template <class Op>
 __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(const Op op, const int64_t n, const int use_tma) {
   extern __shared__ float4 smem4[];
@@ -407,7 +416,14 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
   float* s_tab = s_out + Lay::kOutStages * Lay::kOutFloats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
   uint32_t* released = reinterpret_cast<uint32_t*>(bars + 2);  // per input stage: warps that have copied their rows out
-  const int tid = threadIdx.x, lane = tid & 31, wrow = tid & ~31;
+  const int tid = threadIdx.x, lane = tid & 31;
+#if SO3D_WROW_SHFL
+  // a broadcast from lane 0 tells the compiler the value is warp-uniform: the bulk-copy operands (uniform registers in
+  // SASS) then need one R2UR each instead of a predicate waterfall loop per copy (24 -> ~8 issue slots per copy, r03u)
+  const int wrow = __shfl_sync(0xffffffffu, tid & ~31, 0);
+#else
+  const int wrow = tid & ~31;
+#endif
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
       if (tma) {
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (SO3D_WROW_SHFL ? elect_one() : lane == 0) {
 #pragma unroll
           for (int a = 0; a < kO9; ++a)
             if (op.out9[a]) bulk_store(op.out9[a] + (row0 + wrow) * 9, s_o9 + a * kTile * 9 + wrow * 9, 32 * 9 * sizeof(float));
@@ -1113,21 +1129,21 @@ __global__ void __launch_bounds__(256) cdf_table_kernel(const float* __restrict_
 __device__ __forceinline__ float table_row_angle(const float* __restrict__ cdf, const uint32_t* __restrict__ guide, int64_t row,
                                                  const float* tab, float u) {
   if (guide) {
-    const uint4 w = __ldg(reinterpret_cast<const uint4*>(guide) + row * kGuide + guide_bucket(u));  // one 16-byte record
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(guide) + row * kGuideRecs + guide_bucket(u));  // one 16-byte record
     const GuideRec rec{w.x, __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w)};
     return igso3_angle_from_record(cdf + row * kCdf, tab + kTabLoc, rec, u);
   }
   return igso3_angle_from_uniform(cdf + row * kCdf, tab + kTabLoc, u);
 }
 
-// distributions.py:15-30 companion: the 1024 guide records of every CDF row (so3d_math.cuh).
+// distributions.py:15-30 companion: the kGuideRecs guide records of every CDF row (so3d_math.cuh).
 __global__ void __launch_bounds__(kTile) cdf_guide_kernel(const float* __restrict__ cdf, uint32_t* __restrict__ guide) {
   __shared__ float s_trap[kGrid];
   const int64_t row = blockIdx.x;
   for (int k = threadIdx.x; k < kCdf; k += kTile) s_trap[k] = cdf[row * kCdf + k];
   __syncthreads();
-  uint4* out = reinterpret_cast<uint4*>(guide) + row * kGuide;
-  for (int k = threadIdx.x; k < kGuide; k += kTile) {
+  uint4* out = reinterpret_cast<uint4*>(guide) + row * kGuideRecs;
+  for (int k = threadIdx.x; k < kGuideRecs; k += kTile) {
     const GuideRec r = make_guide_rec(s_trap, k);
     out[k] = make_uint4(r.lohi, __float_as_uint(r.tm1), __float_as_uint(r.t0), __float_as_uint(r.tp1));
   }
@@ -1229,10 +1245,12 @@ struct BinghamOp {
 // kExtra: the optional noise / score outputs are compiled in (more shared memory per stage).  kDevSeed: the Philox seed
 // is read from device memory when the kernel runs (so3d_q_sample_dseed_f32: a captured training step draws fresh noise
 // on every replay); a separate instantiation, the by-value kernel's code is untouched.
-template <bool kExtra, bool kDevSeed = false>
+// kNoiseOut = false with kExtra: the score output without the noise-matrix output (north_star's fused score + noising): no
+// second 9-word output stage and no live noise matrix in registers.
+template <bool kExtra, bool kDevSeed = false, bool kNoiseOut = kExtra>
 struct QSampleOp {
   // per-row table rows are dependent L2 accesses: latency-bound, so favour resident CTAs over output double-buffering
-  SO3D_OP_ARRAYS_S(1, 0, (kExtra ? 2 : 1), (kExtra ? 2 : 1), SO3D_QS_OUTSTAGES)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
+  SO3D_OP_ARRAYS_S(1, 0, (kNoiseOut ? 2 : 1), (kExtra ? 2 : 1), SO3D_QS_OUTSTAGES)  // in: x0;  out9: x_t[, noise];  out3: target[, score]
   static constexpr int kTab = kGrid;  // loc only
   static constexpr int kMinCtas = kExtra ? SO3D_QSX_MINCTAS : SO3D_QS_MINCTAS;  // 4 CTAs (<= 64 registers, no spills) beat 5 CTAs with 56 B of spills: 0.442 vs 0.476 ms (r01m)
   static constexpr bool kWarpSchedule = true;
@@ -1271,7 +1289,7 @@ struct QSampleOp {
       p.d = draw_axis_u((uint64_t)__ldg(reinterpret_cast<const unsigned long long*>(seed_dev)), row_offset + (uint64_t)i, rng_offset);
     else
       p.d = draw_axis_u(key, row_offset + (uint64_t)i);
-    p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuide + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
+    p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuideRecs + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
     return p;
   }
   __device__ void row(int64_t, const Pre2& p, const Mat3* a9, const Vec3*, Mat3* o9, Vec3* o3, const float* tab) const {
@@ -1287,7 +1305,7 @@ struct QSampleOp {
     const Quat qn = quat_axis_angle(d.axis, ang);
     const AxisAngleF ax = axis_angle_fast(a9[0]);
     o9[0] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, p.sc * ax.theta), qn));  // diffusion.py:344-346
-    if (kExtra && out9[kExtra ? 1 : 0]) o9[kExtra ? 1 : 0] = quat_to_mat_unit(qn);
+    if (kNoiseOut && out9[kNoiseOut ? 1 : 0]) o9[kNoiseOut ? 1 : 0] = quat_to_mat_unit(qn);
     const float k = ang * rcp_approx(eps);                                          // diffusion.py:355
     o3[0] = Vec3{k * d.axis.x, k * d.axis.y, k * d.axis.z};
     if (kExtra && out3[kExtra ? 1 : 0]) {
@@ -1509,7 +1527,7 @@ struct SE3QSampleOp {
     p.eps = __ldg(sqrt_1m_ac + ti);
     p.sc = __ldg(sqrt_ac + ti);
     p.d = draw_axis_u(key, row_offset + (uint64_t)i);
-    p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuide + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
+    p.rec = guide ? __ldg(reinterpret_cast<const uint4*>(guide) + ti * kGuideRecs + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
     return p;
   }
   __device__ void row(int64_t i, const Pre2& p, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
@@ -1930,14 +1948,15 @@ static int launch_sample(const float* cdf, const uint32_t* guide, const float* l
   return launch_rowwise(op, n, stream, "so3d_igso3_sample_f32");
 }
 
-template <bool kExtra, bool kDevSeed = false>
+template <bool kExtra, bool kDevSeed = false, bool kNoiseOut = kExtra>
 static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T, const float* cdf,
                            const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
                            float* target3, float* noise, float* score3, int64_t n, void* stream, const uint64_t* seed_dev = nullptr) {
-  QSampleOp<kExtra, kDevSeed> op;
+  QSampleOp<kExtra, kDevSeed, kNoiseOut> op;
   op.seed_dev = seed_dev; op.rng_offset = rng_offset;
   op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
-  if (kExtra) { op.out9[kExtra ? 1 : 0] = noise; op.out3[kExtra ? 1 : 0] = score3; }
+  if (kNoiseOut) op.out9[kNoiseOut ? 1 : 0] = noise;
+  if (kExtra) op.out3[kExtra ? 1 : 0] = score3;
   op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
   op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
   return launch_rowwise(op, n, stream, "so3d_q_sample_f32");
@@ -1992,6 +2011,9 @@ int so3d_q_sample_f32(const float* x0, const int64_t* t, const float* sqrt_ac, c
   if (n == 0) return 0;
   SO3D_REQUIRE(x0 && t && sqrt_ac && sqrt_1m_ac && cdf && loc && x_t, "so3d_q_sample_f32: null pointer");
   SO3D_REQUIRE(T > 0, "so3d_q_sample_f32: T must be positive");
+  if (score3 && !noise)
+    return launch_q_sample<true, false, false>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, nullptr, score3, n,
+                                               stream);
   if (noise || score3)
     return launch_q_sample<true>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, noise, score3, n, stream);
   return launch_q_sample<false>(x0, t, sqrt_ac, sqrt_1m_ac, T, cdf, guide, loc, seed, rng_offset, row_offset, x_t, target3, noise, score3, n, stream);

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kLT, 4) p_sample_loop_kernel(const LoopArgs a)
       if (step != 0) {  // diffusion.py:320: no noise at t == 0
         const uint64_t row = a.row_offset + (uint64_t)(pass_lo + (int64_t)k * kLT + tid);
         p.d = draw_axis_u(a.keys, row, a.rng_offset0 + (uint64_t)step);
-        p.rec = __ldg(reinterpret_cast<const uint4*>(a.post_guide) + step * kGuide + guide_bucket(p.d.u));
+        p.rec = __ldg(reinterpret_cast<const uint4*>(a.post_guide) + step * kGuideRecs + guide_bucket(p.d.u));
       }
       return p;
     };
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kLT, SO3D_LOOP2_MINCTAS) p_sample_loop_kernel2
       p.axis = sphere_from_uniforms_l(L2{u01(r0.x), u01(r1.x)}, L2{u01(r0.y), u01(r1.y)});
       p.u[0] = u01(r0.z);
       p.u[1] = u01(r1.z);
-      const uint4* g = reinterpret_cast<const uint4*>(a.post_guide) + step * kGuide;
+      const uint4* g = reinterpret_cast<const uint4*>(a.post_guide) + step * kGuideRecs;
       p.rec[0] = __ldg(g + guide_bucket(p.u[0]));
       p.rec[1] = __ldg(g + guide_bucket(p.u[1]));
       return p;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kLT, SO3D_LOOP2_MINCTAS) p_sample_loop_kernel2
           const U4 r0 = philox4x32_10(a.keys, row, a.rng_offset0 + (uint64_t)step);
           const Vec3L<L1> axis = sphere_from_uniforms_l(L1{u01(r0.x)}, L1{u01(r0.y)});
           const float u = u01(r0.z);
-          const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.post_guide) + step * kGuide + guide_bucket(u));
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.post_guide) + step * kGuideRecs + guide_bucket(u));
           const GuideRec g0{w.x, __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w)};
           qm = qmul_l(qm, quat_axis_angle_l(axis, L1{igso3_angle_from_record(trap, s_loc, g0, u)}));
         }

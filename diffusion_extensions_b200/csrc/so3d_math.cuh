@@ -1174,14 +1174,31 @@ SO3D_HD float igso3_angle_from_uniform(const float* trap, const float* loc, floa
 // Guide of a CDF row: guide[k] = #{j : trap[j] <= k / kGuide}, k = 0..kGuide.  k / 1024 and u * 1024 are exact in
 // fp32, so for u in [k/1024, (k+1)/1024) the count lies in [guide[k], guide[k+1]] and a search restricted to that
 // range returns exactly the index of the full binary search, in ~1 probe instead of 10.
-//   * shared-row kernels keep the guide as uint16 counts next to the row in shared memory;
+//   * shared-row kernels keep the guide as uint16 counts next to the row in shared memory (uniform buckets);
 //   * per-row lookups through L2 use 16-byte RECORDS, one per bucket: {lo | hi << 16, trap[lo-1], trap[lo],
 //     trap[lo+1]} (indices clamped to [0, 998]).  When the bucket holds at most one grid point (hi - lo <= 1, the
 //     common case) ONE 16-byte load resolves the lookup: the count is lo + (trap[lo] <= u) and both CDF values of
 //     the interpolation are in the record -- a single dependent memory access instead of 4-5.
+//     The record buckets are NOT uniform in u.  The grid angles are cubic in the index, so the CDF entries crowd
+//     towards 0 like a power law (F ~ j^9 for broad distributions) and towards 1 like a Gaussian tail: with 1024
+//     uniform buckets 5.1 % of the draws of the forward schedule land in a bucket that holds several grid points and
+//     fall back to a dependent binary search through L2 -- 2 lanes of every warp, so 82 % of the warps paid for it
+//     (r03u: 9 % of the issue slots and a quarter of the stall samples of the forward-noising kernel).  Records
+//     therefore follow the float format in both tails (bucket_of below): [2^-13, 2^-3) of u and of 1 - u are cut
+//     into 64 buckets per octave (the top 6 mantissa bits), the middle [1/8, 7/8] into 1/1024 steps, and one record
+//     each covers u < 2^-13 and 1 - u < 2^-13.  0.2 % of the forward draws (0.02 % of the posterior's) are left on
+//     the search path; 2051 records = 32.8 KB per row.  Every bucket edge and 1 - u (u >= 1/2) are exact in fp32, so
+//     the bracket [lo, hi] of a record is exact for every u that maps to it.
 constexpr int kGuide = 1024;
 constexpr int kGuideStride = kGuide + 2;  // uint16 entries per shared-memory guide (1025 used; even)
-constexpr int kGuideRecWords = 4;         // 32-bit words per record of the global guide (kGuide records per row)
+constexpr int kGuideRecWords = 4;         // 32-bit words per record of the global guide
+constexpr int kRecOctLo = 13, kRecOctHi = 3, kRecMant = 6;                        // log part: [2^-13, 2^-3), 2^6 buckets per octave
+constexpr int kRecLog = (kRecOctLo - kRecOctHi) << kRecMant;                      // 640 log buckets per tail
+constexpr int kRecBias = ((127 - kRecOctLo) << kRecMant);                         // float bits >> 17 of 2^-13
+constexpr int kRecMid0 = kGuide >> kRecOctHi, kRecMid1 = kGuide - kRecMid0;       // uniform buckets 128 .. 896 (inclusive)
+constexpr int kRecMidBase = 1 + kRecLog;                                          // first middle record
+constexpr int kRecUpBase = kRecMidBase + (kRecMid1 - kRecMid0 + 1);               // first record of the upper tail
+constexpr int kGuideRecs = kRecUpBase + 1 + kRecLog;                              // 2051 records per row
 
 SO3D_HD float igso3_angle_from_uniform_guided(const float* trap, const float* loc, const uint16_t* guide, float u) {
   int k = (int)(u * (float)kGuide);
@@ -1196,14 +1213,50 @@ struct GuideRec {
   float tm1, t0, tp1;
 };
 
+SO3D_HD float rec_uint_as_float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, sizeof f);
+  return f;
+#endif
+}
+SO3D_HD uint32_t rec_float_as_uint(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t b;
+  memcpy(&b, &f, sizeof b);
+  return b;
+#endif
+}
+
+// lower edge of log bucket j (j = 0 .. kRecLog; j = kRecLog is 2^-3) of a tail variable v = u or 1 - u
+SO3D_HD float rec_log_edge(int j) { return rec_uint_as_float((uint32_t)(j + kRecBias) << (23 - kRecMant)); }
+
+// [a, b]: every u that maps to record k satisfies a <= u <= b (b may be the first value of the next record)
+SO3D_HD void guide_rec_range(int k, float* a, float* b) {
+  if (k == 0) { *a = 0.f; *b = rec_log_edge(0); }
+  else if (k < kRecMidBase) { *a = rec_log_edge(k - 1); *b = rec_log_edge(k); }
+  else if (k < kRecUpBase) {
+    const int q = k - kRecMidBase + kRecMid0;
+    *a = (float)q * (1.0f / (float)kGuide);
+    *b = (float)(q + 1) * (1.0f / (float)kGuide);
+  } else if (k == kRecUpBase) { *a = 1.0f - rec_log_edge(0); *b = 1.0f; }
+  else { *a = 1.0f - rec_log_edge(k - kRecUpBase); *b = 1.0f - rec_log_edge(k - kRecUpBase - 1); }
+}
+
 SO3D_HD GuideRec make_guide_rec(const float* trap, int k) {
-  const int lo = cdf_count_le(trap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
-  const int hi = cdf_count_le(trap, (float)(k + 1) * (1.0f / (float)kGuide), 0, kCdf);
+  float a, b;
+  guide_rec_range(k, &a, &b);
+  const int lo = cdf_count_le(trap, a, 0, kCdf);
+  const int hi = cdf_count_le(trap, b, 0, kCdf);
   auto at = [&](int j) { return trap[j < 0 ? 0 : (j > kCdf - 1 ? kCdf - 1 : j)]; };
   return GuideRec{(uint32_t)lo | ((uint32_t)hi << 16), at(lo - 1), at(lo), at(lo + 1)};
 }
 
-// `rec` = the record of bucket floor(u * 1024) of this row (already loaded); trap = the row, for the rare fallback
+// `rec` = the record of bucket guide_bucket(u) of this row (already loaded); trap = the row, for the rare fallback
 SO3D_HD float igso3_angle_from_record(const float* trap, const float* loc, const GuideRec& rec, float u) {
   const int lo = (int)(rec.lohi & 0xffffu), hi = (int)(rec.lohi >> 16);
   if (hi - lo <= 1 && lo < kCdf - 1 && u >= 0.f && u < 1.0f) {
@@ -1224,9 +1277,15 @@ SO3D_HD float igso3_angle_from_record(const float* trap, const float* loc, const
   return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, in01 ? lo : 0, in01 ? hi : kCdf));
 }
 
+// record index of u (any float: values outside [0, 1) map to some valid record and take the search path)
 SO3D_HD int guide_bucket(float u) {
-  int k = (int)(u * (float)kGuide);
-  return k < 0 ? 0 : (k > kGuide - 1 ? kGuide - 1 : k);
+  const bool upper = u > 0.875f;
+  const float v = upper ? 1.0f - u : u;  // exact for u >= 1/2
+  int kl = (int)(rec_float_as_uint(v) >> (23 - kRecMant)) - (kRecBias - 1);  // 0 below 2^-13, 1 + log bucket above
+  kl = kl < 0 ? 0 : kl;
+  int k = (int)(u * (float)kGuide) + (kRecMidBase - kRecMid0);
+  k = (u < 0.125f) ? kl : (upper ? kRecUpBase + kl : k);
+  return k < 0 ? 0 : (k > kGuideRecs - 1 ? kGuideRecs - 1 : k);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -120,7 +120,7 @@ class SO3Diffusion(nn.Module):
         return (str(a.device), a.data_ptr(), a._version, b.data_ptr(), b._version, bool(self.reference_quirks))
 
     def guides(self):
-        """(fwd_guide, post_guide): the (T, 1024, 4) search records of the two CDF tables."""
+        """(fwd_guide, post_guide): the (T, 2051, 4) search records of the two CDF tables."""
         self.tables()
         return self._guides[self._schedule_key()]
 

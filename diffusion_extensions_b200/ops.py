@@ -13,7 +13,7 @@ from ._lib import call, check_f32, ptr
 
 CDF_POINTS = 999
 GRID_POINTS = 1000
-GUIDE_BUCKETS = 1024  # 16-byte records per guide row (include/so3d.h SO3D_GUIDE_BUCKETS)
+GUIDE_BUCKETS = 2051  # 16-byte records per guide row (include/so3d.h SO3D_GUIDE_BUCKETS)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -405,7 +405,7 @@ def igso3_cdf_table(eps, reference_quirks=False):
 
 
 def igso3_cdf_guide(cdf):
-    """cdf (rows, 999) -> guide (rows, 1024, 4) int32: the 16-byte search records of include/so3d.h."""
+    """cdf (rows, 999) -> guide (rows, 2051, 4) int32: the 16-byte search records of include/so3d.h."""
     cdf = check_f32(cdf, "cdf", (CDF_POINTS,))
     rows = cdf.numel() // CDF_POINTS
     out = torch.empty(rows, GUIDE_BUCKETS, 4, dtype=torch.int32, device=cdf.device)

@@ -39,7 +39,7 @@ extern "C" {
 
 #define SO3D_CDF_POINTS 999  /* entries per CDF row (distributions.py:15,30: 1000-point grid) */
 #define SO3D_GRID_POINTS 1000
-#define SO3D_GUIDE_BUCKETS 1024 /* 16-byte records per guide row */
+#define SO3D_GUIDE_BUCKETS 2051 /* 16-byte records per guide row */
 
 /* evaluator for the IGSO(3) density (mode argument) */
 #define SO3D_MODE_SERIES 0          /* truncated series, exactly L terms per row; rows whose alternating sum is
@@ -109,8 +109,10 @@ int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_l
                              float* trap_out, int quirks, void* stream);
 /* Search accelerator for the inverse-CDF lookup of distributions.py:38-43 (`(trap <= u).sum()`): for every CDF
  * row, SO3D_GUIDE_BUCKETS records of 16 bytes, record k = {lo | hi << 16, trap[lo-1], trap[lo], trap[lo+1]} with
- * lo = #{j : trap[j] <= k/1024}, hi = #{j : trap[j] <= (k+1)/1024} (trap indices clamped to [0, 998]).  For
- * u in [k/1024, (k+1)/1024) the count lies in [lo, hi]; when hi - lo <= 1 one 16-byte load resolves the lookup,
+ * lo = #{j : trap[j] <= a_k}, hi = #{j : trap[j] <= b_k} (trap indices clamped to [0, 998]) where [a_k, b_k] is the
+ * range of u served by record k: 1/1024 steps on [1/8, 7/8], 64 steps per octave of u on [2^-13, 2^-3) and of 1 - u
+ * on the mirrored range (the CDF entries crowd towards both ends), one record each for the rest of the two tails.
+ * For u in that range the count lies in [lo, hi]; when hi - lo <= 1 one 16-byte load resolves the lookup,
  * otherwise a binary search restricted to [lo, hi] does: either way the index is IDENTICAL to the full search.
  * guide_out: rows x SO3D_GUIDE_BUCKETS x 4 words, 16-byte aligned. */
 int so3d_igso3_cdf_guide(const float* cdf, int64_t rows, uint32_t* guide_out, void* stream);

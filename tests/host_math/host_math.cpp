@@ -79,6 +79,17 @@ void hm_angle_from_record(const float* trap, const float* loc, const float* u, f
     ang[i] = igso3_angle_from_record(trap, loc, rec, u[i]);
   }
 }
+// record index of every u, the [a, b] range its record serves, and whether one record resolves the lookup
+void hm_guide_bucket(const float* trap, const float* u, int* k, float* a, float* b, int* one_load, long n) {
+  for (long i = 0; i < n; ++i) {
+    k[i] = guide_bucket(u[i]);
+    guide_rec_range(k[i], a + i, b + i);
+    const GuideRec rec = make_guide_rec(trap, k[i]);
+    const int lo = (int)(rec.lohi & 0xffffu), hi = (int)(rec.lohi >> 16);
+    one_load[i] = (hi - lo <= 1 && lo < kCdf - 1) ? 1 : 0;
+  }
+}
+int hm_guide_records() { return kGuideRecs; }
 void hm_philox(unsigned long long seed, unsigned long long row0, unsigned long long offset, unsigned* out, long n) {
   for (long i = 0; i < n; ++i) { U4 r = philox4x32_10(seed, row0 + i, offset); out[4*i]=r.x; out[4*i+1]=r.y; out[4*i+2]=r.z; out[4*i+3]=r.w; }
 }

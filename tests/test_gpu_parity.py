@@ -863,20 +863,32 @@ def test_guide_table_lookup_is_exact(dx, cuda_device):
     p = dx.SO3Diffusion(None).to(cuda_device)
     fwd, post, _ = p.tables()
     fg, pg = p.guides()
-    g = fg.cpu().numpy()                                   # (T, 1024, 4) int32 records
+    g = fg.cpu().numpy()                                   # (T, 2051, 4) int32 records
     trap = fwd.cpu().numpy()
-    edges = np.arange(1025, dtype=np.float32) / np.float32(1024)
+    # the range [a_k, b_k] of u each record serves (include/so3d.h): u < 2^-13 | 64 per octave up to 1/8 | 1/1024 steps on
+    # [1/8, 7/8] | the mirror image in 1 - u, counted down from 1
+    log_edges = np.concatenate([(np.float32(2.0) ** -o) * (1 + np.arange(64, dtype=np.float32) / 64) for o in range(13, 3, -1)]
+                               + [np.float32([0.125])]).astype(np.float32)
+    lower_a = np.concatenate([np.float32([0.0]), log_edges[:-1]]); lower_b = log_edges
+    mid = np.arange(128, 898, dtype=np.float32) / np.float32(1024)
+    a_k = np.concatenate([lower_a, mid[:-1], (np.float32(1) - lower_b).astype(np.float32)])
+    b_k = np.concatenate([lower_b, mid[1:], (np.float32(1) - lower_a).astype(np.float32)])
+    assert a_k.shape[0] == g.shape[1] == 2051 and np.all(a_k < b_k)
     for row in (0, 17, 500, 999):
-        cnt = np.searchsorted(trap[row], edges, side="right")
+        lo = np.searchsorted(trap[row], a_k, side="right")
+        hi = np.searchsorted(trap[row], b_k, side="right")
         lohi = g[row, :, 0].astype(np.int64) & 0xFFFFFFFF
-        assert np.array_equal(lohi & 0xFFFF, cnt[:-1]) and np.array_equal(lohi >> 16, cnt[1:])
+        assert np.array_equal(lohi & 0xFFFF, lo) and np.array_equal(lohi >> 16, hi)
         vals = g[row, :, 1:].view(np.float32)
         for j, off in enumerate((-1, 0, 1)):
-            assert np.array_equal(vals[:, j], trap[row][np.clip(cnt[:-1] + off, 0, 998)])
+            assert np.array_equal(vals[:, j], trap[row][np.clip(lo + off, 0, 998)])
     n = 1 << 16
     rows = torch.randint(0, 1000, (n,), device=cuda_device)
     u = torch.rand(n, device=cuda_device)
     u[:4] = torch.tensor([0.0, 1.0 - 2 ** -24, 0.5, 2 ** -24])
+    u[4:8192] = u[4:8192] * 2 ** -10                      # the float-format buckets of the lower tail ...
+    u[8192:16384] = 1 - u[8192:16384] * 2 ** -10          # ... and of the upper one
+    u[16384:16390] = torch.tensor([0.125, 0.875, 2 ** -13, 1 - 2 ** -13, 0.125 - 2 ** -27, 0.875 + 2 ** -24])
     a = dx.ops.igso3_sample(post, (n,), row_idx=rows, u=u, seed=1, rng_offset=0, want_angle=True)
     b = dx.ops.igso3_sample(post, (n,), row_idx=rows, u=u, seed=1, rng_offset=0, want_angle=True, guide=pg)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

@@ -281,14 +281,36 @@ def test_inverse_cdf_guide_records(hm, golden):
     for k in range(len(g["eps_list"])):
         trap = f32(g["trap"][k])
         edges = np.arange(1024, dtype=np.float32) / np.float32(1024)
-        u = np.concatenate([rng.random(20000, dtype=np.float32), edges, np.nextafter(edges[1:], np.float32(0)), trap[:-1],
-                            np.nextafter(trap[:-1], np.float32(0)), np.nextafter(trap[:-1], np.float32(1)),
-                            f32([0.0, np.nextafter(np.float32(1), np.float32(0))])]).astype(np.float32)
+        # the float-format buckets of the two tails: 64 per octave of u (and of 1 - u) down to 2^-13, and far below
+        log_edges = (np.float32(2.0) ** -np.arange(3, 33, dtype=np.float32))[:, None] * (1 + np.arange(64, dtype=np.float32) / 64)[None, :]
+        log_edges = log_edges.reshape(-1).astype(np.float32)
+        up_edges = (np.float32(1) - log_edges[log_edges >= 2.0 ** -24]).astype(np.float32)
+        tiny = (rng.integers(0, 2 ** 20, 4000).astype(np.float64) * 2.0 ** -32).astype(np.float32)   # the generator's lattice near 0
+        near1 = (np.float32(1) - rng.integers(1, 2 ** 12, 4000).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+        special = np.concatenate([edges, log_edges, up_edges, trap[:-1], f32([0.0, 0.125, 0.875])])
+        u = np.concatenate([rng.random(20000, dtype=np.float32), tiny, near1, special, np.nextafter(special, np.float32(0)),
+                            np.nextafter(special, np.float32(1)), f32([np.nextafter(np.float32(1), np.float32(0))])]).astype(np.float32)
         u = np.ascontiguousarray(u[(u >= 0) & (u < 1)])
         a = np.empty(u.shape[0], np.float32); b = np.empty(u.shape[0], np.float32)
         hm.hm_angle_from_uniform(fp(trap), fp(loc), fp(u), fp(a), ctypes.c_long(u.shape[0]))
         hm.hm_angle_from_record(fp(trap), fp(loc), fp(u), fp(b), ctypes.c_long(u.shape[0]))
         assert np.array_equal(a, b)
+        # every u lies in the range its record was built for; records are ordered; the search path is rare
+        kk = np.empty(u.shape[0], np.int32); lo = np.empty_like(a); hi = np.empty_like(a); one = np.empty(u.shape[0], np.int32)
+        ip = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+        hm.hm_guide_bucket(fp(trap), fp(u), ip(kk), fp(lo), fp(hi), ip(one), ctypes.c_long(u.shape[0]))
+        assert kk.min() >= 0 and kk.max() < hm.hm_guide_records() == 2051
+        assert np.all(lo <= u) and np.all(u <= hi)
+        order = np.argsort(u, kind="stable")
+        us, ks = u[order], kk[order]
+        assert np.all(np.diff(ks[us <= 0.875]) >= 0) and np.all(np.diff(ks[us > 0.875]) <= 0)   # the upper tail counts down from 1
+        assert ks[us <= 0.875].max() < ks[us > 0.875].min()
+        assert one[:20000].mean() > 0.985   # (uniform 1/1024 buckets: 0.93-0.95)
+    # out-of-range and non-finite inputs land on a valid record (and take the full search)
+    bad = f32([-1.0, -0.0, 1.0, 2.0, 1e30, -1e30, np.inf, -np.inf, np.nan])
+    kk = np.empty(bad.shape[0], np.int32); lo = np.empty_like(bad); hi = np.empty_like(bad); one = np.empty(bad.shape[0], np.int32)
+    hm.hm_guide_bucket(fp(trap), fp(bad), ip(kk), fp(lo), fp(hi), ip(one), ctypes.c_long(bad.shape[0]))
+    assert kk.min() >= 0 and kk.max() < 2051
 
 
 def test_philox_known_answer_and_draws(hm):

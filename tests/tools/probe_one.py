@@ -1,4 +1,4 @@
-"""One op of probe_engine's list, a few launches (for ncu captures):  python tests/tools/probe_one.py q_sample|p_sample|p_sample_rows|auto|loop [log2_rows]"""
+"""One op of probe_engine's list, a few launches (for ncu captures):  python tests/tools/probe_one.py q_sample|q_sample_score|p_sample|p_sample_rows|auto|loop [log2_rows]"""
 import os
 import sys
 
@@ -22,6 +22,8 @@ eps = torch.exp(torch.empty(n, device=dev).uniform_(-5.05, 0.0))
 sched = (proc.sqrt_recip_alphas_cumprod, proc.sqrt_recipm1_alphas_cumprod, proc.posterior_mean_coef1, proc.posterior_mean_coef2)
 fns = {
     "q_sample": lambda: ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fwd_guide),
+    "q_sample_score": lambda: ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fwd_guide,
+                                                 want_score=True),
     "p_sample": lambda: ops.p_sample_fused(R, pred, t_range[500:501], *sched, post_cdf=post, seed=1, rng_offset=1),
     "p_sample_rows": lambda: ops.p_sample_fused(R, pred, tt, *sched, post_cdf=post, seed=1, rng_offset=1, post_guide=post_guide),
     "auto": lambda: ops.igso3_logp_score(R, eps, mode="auto"),
