@@ -53,7 +53,7 @@ constexpr int kTile = 256;  // rows per tile == threads per CTA
 #define SO3D_PSS_MINCTAS 1   // shared-t reverse step: no register cap (63 registers schedule 3 % faster than 48)
 #endif
 #ifndef SO3D_PS_MINCTAS
-#define SO3D_PS_MINCTAS 3    // per-row-t reverse step
+#define SO3D_PS_MINCTAS 3    // per-row-t reverse step (with the prefetch hooks: 3 -> 70 registers 0.418 ms, 4 -> 63 registers 0.423, 5 -> 48 + spills 0.455; r03z)
 #endif
 
 thread_local char g_err[256] = "";
@@ -984,8 +984,24 @@ struct ScaleBwdOp {
 // ------------------------------------------------------------------------------------------------
 // L1: IGSO(3)
 // ------------------------------------------------------------------------------------------------
+// The HBM-bound evaluators (closed form, auto) request eps one tile ahead through the engine's prefetch hooks: the load
+// used to be issued by the row itself and its first use held 32 % of the kernel's stall samples (r03x).  The series
+// modes spend microseconds per row and keep their code exactly as it was (ptxas's schedule of the unrolled block is
+// sensitive to everything around it).
+#ifndef SO3D_LOGP_PREFETCH
+#define SO3D_LOGP_PREFETCH 1
+#endif
+template <bool kOn>
+struct LogpPre {};
+template <>
+struct LogpPre<true> {
+  struct Pre1 {};
+  struct Pre2 {
+    float eps;
+  };
+};
 template <int kMode>
-struct LogpScoreOp {  // distributions.py:74-77 + score, fused with the axis-angle extraction
+struct LogpScoreOp : LogpPre<SO3D_LOGP_PREFETCH && (kMode == kClosed || kMode == kAuto)> {  // distributions.py:74-77 + score, fused with the axis-angle extraction
   SO3D_OP_ARRAYS(1, 0, 0, 1)
   SO3D_OP_NO_TAB
   static constexpr int kMinCtas = (kMode == kClosed || kMode == kAuto) ? 5 : 1;  // HBM-bound evaluators: >= 5 CTAs (<= 51 registers)
@@ -998,14 +1014,22 @@ struct LogpScoreOp {  // distributions.py:74-77 + score, fused with 
   float* logp;
   float* dlogf;
   int L;
-  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const {
+  __device__ void row(int64_t i, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const { row_eps(i, eps[i * eps_stride], a9, o3); }
+  __device__ void row_eps(int64_t i, float e, const Mat3* a9, Vec3* o3) const {
     const AxisAngleF a = axis_angle_fast(a9[0]);
     float lf, g;
-    igso3_logf_g_t<kMode>(a.theta, eps[i * eps_stride], L, &lf, &g);
+    igso3_logf_g_t<kMode>(a.theta, e, L, &lf, &g);
     logp[i] = lf;
     if (dlogf) dlogf[i] = g;
     o3[0] = Vec3{g * a.axis.x, g * a.axis.y, g * a.axis.z};
   }
+  // prefetch hooks (only instantiated for the modes whose base declares Pre1 / Pre2)
+  template <class P1 = typename LogpPre<true>::Pre1>
+  __device__ P1 prefetch1(int64_t) const { return P1{}; }
+  template <class P1, class P2 = typename LogpPre<true>::Pre2>
+  __device__ P2 prefetch2(int64_t i, const P1&) const { return P2{eps[i * eps_stride]}; }
+  template <class P2>
+  __device__ void row(int64_t i, const P2& p, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const { row_eps(i, p.eps, a9, o3); }
 };
 struct LogpBwdOp {
   SO3D_OP_ARRAYS(1, 0, 1, 0)
@@ -1337,11 +1361,30 @@ struct QSampleGivenOp {  // diffusion.py:339-346 with noise supplied
 // its guide live in shared memory; otherwise per-row t with table rows (and the optional guide) read through L2.
 // kDevSeed: the Philox seed is read from device memory (CUDA-graph replays with fresh noise, so3d_p_sample_dseed_f32);
 // a separate instantiation, so the by-value kernels' code is untouched.
+// Per-row t: the row's chain t -> four schedule scalars + guide record used to start inside the row; like forward noising
+// it now runs through the engine's prefetch hooks (t two tiles ahead; scalars, draw and record one tile ahead).
+#ifndef SO3D_PS_PREFETCH
+#define SO3D_PS_PREFETCH 1
+#endif
+template <bool kOn>
+struct PStepPre {};
+template <>
+struct PStepPre<true> {
+  struct Pre1 {
+    int64_t t;
+  };
+  struct Pre2 {
+    int ti;
+    float k_recip, k_recipm1, k_c1, k_c2;
+    NoiseDraw d;
+    uint4 rec;
+  };
+};
 template <bool kSharedT, bool kX0, bool kDevSeed = false>
-struct PStepOp {
+struct PStepOp : PStepPre<SO3D_PS_PREFETCH && !kSharedT> {
   SO3D_OP_ARRAYS_S(1, 1, (kX0 ? 2 : 1), 0, (kSharedT ? SO3D_PSS_OUTSTAGES : 1))  // in: x_t, pred;  out9: x_{t-1}[, x0_hat]
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
-  // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
+  // per-row t: cap SO3D_PS_MINCTAS (measured there).  Shared t: issue-bound, shared memory
   // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
   static constexpr int kMinCtas = kSharedT ? SO3D_PSS_MINCTAS : SO3D_PS_MINCTAS;
   static constexpr bool kWarpSchedule = !kSharedT;
@@ -1396,6 +1439,36 @@ struct PStepOp {
       const NoiseDraw d = draw_axis_u(sd, row_offset + (uint64_t)i, rng_offset);
       const float ang = kSharedT ? shared_row_angle(tab, d.u) : table_row_angle(post_cdf, post_guide, ti, tab, d.u);
       qm = qmul(qm, quat_axis_angle(d.axis, ang));
+    }
+    o9[0] = quat_to_mat_unit(qm);
+    if (kX0) o9[kX0 ? 1 : 0] = quat_to_mat_unit(qh);
+  }
+  // prefetch hooks of the per-row-t instantiations (the same functions of the same inputs as row() above: same bits)
+  template <class P1 = typename PStepPre<true>::Pre1>
+  __device__ P1 prefetch1(int64_t i) const { return P1{t[i]}; }
+  template <class P1, class P2 = typename PStepPre<true>::Pre2>
+  __device__ P2 prefetch2(int64_t i, const P1& p1) const {
+    P2 p;
+    const int64_t ti = clamp_t(p1.t);
+    p.ti = (int)ti;
+    p.k_recip = __ldg(recip + ti), p.k_recipm1 = __ldg(recipm1 + ti), p.k_c1 = __ldg(coef1 + ti), p.k_c2 = __ldg(coef2 + ti);
+    p.d = draw_axis_u(seed, row_offset + (uint64_t)i, rng_offset);
+    p.rec = (post_cdf && post_guide) ? __ldg(reinterpret_cast<const uint4*>(post_guide) + ti * kGuideRecs + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
+    return p;
+  }
+  template <class P2>
+  __device__ void row(int64_t, const P2& p, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3*, const float* tab) const {
+    Quat qh;
+    Quat qm = p_mean_quat(a9[0], a3[0], p.k_recip, p.k_recipm1, p.k_c1, p.k_c2, &qh);
+    if (post_cdf && p.ti != 0) {  // diffusion.py:320-326
+      float ang;
+      if (post_guide) {
+        const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+        ang = igso3_angle_from_record(post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, p.d.u);
+      } else {
+        ang = igso3_angle_from_uniform(post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
+      }
+      qm = qmul(qm, quat_axis_angle(p.d.axis, ang));
     }
     o9[0] = quat_to_mat_unit(qm);
     if (kX0) o9[kX0 ? 1 : 0] = quat_to_mat_unit(qh);
@@ -1567,7 +1640,7 @@ template <bool kSharedT>
 struct SE3PStepOp {
   SO3D_OP_ARRAYS_S(1, 3, 1, 1, 1)  // in: rot_t | pred_rot, shift_t, pred_shift;  out: rot | shift
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
-  // per-row t: latency-bound, 5 CTAs (<= 51 registers; ptxas needs 48).  Shared t: issue-bound, shared memory
+  // per-row t: cap SO3D_PS_MINCTAS (measured there).  Shared t: issue-bound, shared memory
   // limits it to 4 CTAs and the uncapped 63-register allocation is 3 % faster than a 48-register one (r01l).
   static constexpr int kMinCtas = kSharedT ? SO3D_PSS_MINCTAS : SO3D_PS_MINCTAS;
   static constexpr bool kWarpSchedule = !kSharedT;
