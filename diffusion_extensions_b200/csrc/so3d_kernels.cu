@@ -521,8 +521,10 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
       if (tid < rows) op.row(row0 + tid, a9, a3, o9, o3, s_tab);
     }
     if (kO9 + kO3 > 0) {
-      // this warp's earlier bulk stores must have finished reading the slice that is about to be overwritten
-      if (lane == 0) {
+      // this warp's earlier bulk stores must have finished reading the slice that is about to be overwritten.  Bulk
+      // groups belong to the thread that committed them; every lane waits (lanes without groups fall through), so
+      // the wait does not depend on which lane elect.sync picked for the store issue
+      if (SO3D_WROW_SHFL || lane == 0) {
         if (Lay::kOutStages == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
       }
       __syncwarp();
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(kTile, OpMinCtas<Op>::value) rowwise_kernel(co
       }
     }
   }
-  if (lane == 0) bulk_wait_read<0>();
+  if (SO3D_WROW_SHFL || lane == 0) bulk_wait_read<0>();
 }
 
 template <class Op>
@@ -790,6 +792,225 @@ int launch_rowwise2(const Op& op, int64_t n, void* stream, const char* name) {
   static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
   static int resident_dev[kMaxDevices] = {};
   auto kern = rowwise_kernel_cta2<Op>;
+  const int dev = current_device();
+  if (resident_dev[dev] == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kT2, smem) != cudaSuccess || occ < 1) occ = 1;
+    resident_dev[dev] = occ;
+  }
+  int ctas_per_sm = resident_dev[dev];
+  if (const char* e = getenv("SO3D_CTAS_PER_SM")) {
+    const int v = atoi(e);
+    if (v > 0 && v < ctas_per_sm) ctas_per_sm = v;
+  }
+  const int64_t tiles = (n + kRows2 - 1) / kRows2;
+  const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  kern<<<(int)(tiles < cap ? tiles : cap), kT2, smem, (cudaStream_t)stream>>>(op, n, use_tma);
+  return check_launch(name);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two rows per thread on the WARP-AUTONOMOUS schedule (rowwise_kernel_w2): for the latency-spread ops that also define
+// prefetch hooks.  A CTA of kT2 threads moves tiles of kRows2 = 2 kT2 rows; warp w owns the 64 consecutive rows
+// [64 w, 64 w + 64) of a tile, thread `lane` of it the rows 64 w + lane (lane 0 of the packed arithmetic) and
+// 64 w + 32 + lane (lane 1).  Input side as in rowwise_kernel (CTA-wide bulk loads into a two-stage ring, the last warp
+// that has copied its rows out refills the stage); output side per warp (64-row slices: 2304 B / 768 B per array), issued
+// under elect.sync.  Everything that is paid once per warp and tile -- ring wait, stage release, fence, store issue, tile
+// bookkeeping -- is paid per 64 rows instead of per 32, and the op's FP32 arithmetic runs as FFMA2 / FMUL2 / FADD2.
+//   Op2 provides Pre1 / Pre2 / prefetch1 / prefetch2 like a one-row op (called once per row) and
+//     __device__ void row2(const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const
+// ------------------------------------------------------------------------------------------------
+// An op may set Op::kBranchless: no branches around the prefetch of the next tiles and the rows' arithmetic, so that ptxas
+// schedules the integer-heavy prefetch (Philox, address arithmetic) and the FP32 arithmetic of the current rows as ONE block.
+// Row indices are clamped to n - 1, so a prefetch beyond the CTA's last tile re-reads valid entries; rows beyond the end of
+// a ragged tile compute on stale shared memory and are not stored.  Measured per op (r04c): forward noising with the score
+// 0.393 -> 0.385 ms, plain forward noising 0.323 -> 0.365 ms (a 96-register schedule that overlaps less) -- hence a trait.
+template <class Op, class = void>
+struct OpBranchless {
+  static constexpr bool value = false;
+};
+template <class Op>
+struct OpBranchless<Op, std::void_t<decltype(Op::kBranchless)>> {
+  static constexpr bool value = Op::kBranchless;
+};
+template <class Op>
+__global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(const Op op, const int64_t n, const int use_tma) {
+  extern __shared__ float4 smem4[];
+  constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
+  constexpr int kWarps = kT2 / 32;
+  using Lay = OpLayout2<Op>;
+  static_assert(Lay::kInStages == 2 && Lay::kOutStages == 1, "rowwise_kernel_w2: two input stages, one output stage");
+  float* smem = reinterpret_cast<float*>(smem4);
+  float* s_out = smem + 2 * Lay::kInFloats;
+  float* s_tab = s_out + Lay::kOutFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
+  uint32_t* released = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wrow = __shfl_sync(0xffffffffu, 2 * (tid & ~31), 0);  // first row of the warp's slice (warp-uniform: see rowwise_kernel)
+  const int r0 = wrow + lane, r1 = r0 + 32;                       // this thread's two rows of a tile
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    released[0] = 0;
+    released[1] = 0;
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t tiles = (n + kRows2 - 1) / kRows2;
+  const int my_tiles = (tiles > (int64_t)blockIdx.x) ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int my_full = my_tiles - (((n % kRows2) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
+  const int64_t first_row = (int64_t)blockIdx.x * kRows2, stride_rows = (int64_t)gridDim.x * kRows2;
+  auto issue_load = [&](int k, int64_t row0) {  // one thread
+    if (kI9 + kI3 == 0) return;
+    const int st = k & 1;
+    float* base = smem + st * Lay::kInFloats;
+    mbar_expect_tx(&bars[st], (uint32_t)(kRows2 * Lay::kInWords * sizeof(float)));
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) bulk_load(base + a * kRows2 * 9, op.in9[a] + row0 * 9, kRows2 * 9 * sizeof(float), &bars[st]);
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kRows2 * 9 + a * kRows2 * 3, op.in3[a] + row0 * 3, kRows2 * 3 * sizeof(float), &bars[st]);
+  };
+  if (tid == 0 && use_tma) {
+    if (my_full > 0) issue_load(0, first_row);
+    if (my_full > 1) issue_load(1, first_row + stride_rows);
+  }
+  op.setup(s_tab);
+  __syncthreads();
+
+  typename Op::Pre1 p1_next[2]{};  // Pre1 of tile k+1, both rows
+  typename Op::Pre2 p2_cur[2]{};   // Pre2 of tile k
+  auto pre_row = [&](int64_t row0, int r) -> int64_t {  // clamped into range (the result of a row beyond the end is dropped)
+    const int64_t i = row0 + r;
+    return i < n ? i : n - 1;
+  };
+  if (my_tiles > 0) {
+    p2_cur[0] = op.prefetch2(pre_row(first_row, r0), op.prefetch1(pre_row(first_row, r0)));
+    p2_cur[1] = op.prefetch2(pre_row(first_row, r1), op.prefetch1(pre_row(first_row, r1)));
+  }
+  if (my_tiles > 1) {
+    p1_next[0] = op.prefetch1(pre_row(first_row + stride_rows, r0));
+    p1_next[1] = op.prefetch1(pre_row(first_row + stride_rows, r1));
+  }
+
+  int64_t row0 = first_row;
+  for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
+    const int st = k & 1;
+    const int rows = k < my_full ? kRows2 : (int)(n - row0);
+    const bool tma = use_tma && rows == kRows2;
+    int wrows = rows - wrow;  // rows of this warp's slice that exist
+    wrows = wrows < 0 ? 0 : (wrows > 64 ? 64 : wrows);
+    float* s_i9 = smem + st * Lay::kInFloats;
+    float* s_i3 = s_i9 + kI9 * kRows2 * 9;
+    float* s_o9 = s_out;
+    float* s_o3 = s_o9 + kO9 * kRows2 * 9;
+    if (kI9 + kI3 > 0) {
+      if (tma) {
+        mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+      } else {
+#pragma unroll
+        for (int a = 0; a < kI9; ++a) warp_load<9>(s_i9 + a * kRows2 * 9 + wrow * 9, op.in9[a] + (row0 + wrow) * 9, wrows, lane);
+#pragma unroll
+        for (int a = 0; a < kI3; ++a) warp_load<3>(s_i3 + a * kRows2 * 3 + wrow * 3, op.in3[a] + (row0 + wrow) * 3, wrows, lane);
+        __syncwarp();
+      }
+    }
+    Mat3 a9[kI9 > 0 ? kI9 : 1][2];
+    Vec3 a3[kI3 > 0 ? kI3 : 1][2];
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) {
+      a9[a][0] = sm_mat(s_i9 + a * kRows2 * 9, r0);
+      a9[a][1] = sm_mat(s_i9 + a * kRows2 * 9, r1);
+    }
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) {
+      a3[a][0] = sm_vec(s_i3 + a * kRows2 * 3, r0);
+      a3[a][1] = sm_vec(s_i3 + a * kRows2 * 3, r1);
+    }
+    if (kI9 + kI3 > 0) {
+      __syncwarp();  // every lane's copy of its rows is complete
+      if (tma && lane == 0 && k + 2 < my_full) {
+        const uint32_t old = atom_add_acq_rel_cta(&released[st], 1u);
+        if ((old & (kWarps - 1)) == kWarps - 1) issue_load(k + 2, row0 + 2 * stride_rows);  // last warp out refills the stage
+      }
+    }
+
+    Mat3 o9[kO9 > 0 ? kO9 : 1][2];
+    Vec3 o3[kO3 > 0 ? kO3 : 1][2];
+    {
+      typename Op::Pre2 p2_next[2]{};
+      typename Op::Pre1 p1_next2[2]{};
+      constexpr bool kBl = OpBranchless<Op>::value;
+      if (kBl || k + 1 < my_tiles) {  // loads land during this tile's arithmetic
+        p2_next[0] = op.prefetch2(pre_row(row0 + stride_rows, r0), p1_next[0]);
+        p2_next[1] = op.prefetch2(pre_row(row0 + stride_rows, r1), p1_next[1]);
+      }
+      if (kBl || k + 2 < my_tiles) {
+        p1_next2[0] = op.prefetch1(pre_row(row0 + 2 * stride_rows, r0));
+        p1_next2[1] = op.prefetch1(pre_row(row0 + 2 * stride_rows, r1));
+      }
+      if (kBl || r0 < rows) op.row2(p2_cur, a9, a3, o9, o3, s_tab);
+      p2_cur[0] = p2_next[0], p2_cur[1] = p2_next[1];
+      p1_next[0] = p1_next2[0], p1_next[1] = p1_next2[1];
+    }
+    if (kO9 + kO3 > 0) {
+      bulk_wait_read<0>();  // every lane (see rowwise_kernel): the warp's earlier stores have finished reading the slice
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (r0 + 32 * j < rows) {
+#pragma unroll
+          for (int a = 0; a < kO9; ++a) sm_put_mat(s_o9 + a * kRows2 * 9, r0 + 32 * j, o9[a][j]);
+#pragma unroll
+          for (int a = 0; a < kO3; ++a) sm_put_vec(s_o3 + a * kRows2 * 3, r0 + 32 * j, o3[a][j]);
+        }
+      }
+      if (tma) {
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < kO9; ++a)
+            if (op.out9[a]) bulk_store(op.out9[a] + (row0 + wrow) * 9, s_o9 + a * kRows2 * 9 + wrow * 9, 64 * 9 * sizeof(float));
+#pragma unroll
+          for (int a = 0; a < kO3; ++a)
+            if (op.out3[a]) bulk_store(op.out3[a] + (row0 + wrow) * 3, s_o3 + a * kRows2 * 3 + wrow * 3, 64 * 3 * sizeof(float));
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < kO9; ++a)
+          if (op.out9[a]) warp_store<9>(op.out9[a] + (row0 + wrow) * 9, s_o9 + a * kRows2 * 9 + wrow * 9, wrows, lane);
+#pragma unroll
+        for (int a = 0; a < kO3; ++a)
+          if (op.out3[a]) warp_store<3>(op.out3[a] + (row0 + wrow) * 3, s_o3 + a * kRows2 * 3 + wrow * 3, wrows, lane);
+        __syncwarp();
+      }
+    }
+  }
+  bulk_wait_read<0>();
+}
+
+template <class Op>
+int launch_rowwise_w2(const Op& op, int64_t n, void* stream, const char* name) {
+  if (n < 0) return fail(SO3D_EINVAL, "negative n");
+  if (n == 0) return 0;
+  int use_tma = 1;
+  for (int a = 0; a < Op::kIn9; ++a) {
+    if (!op.in9[a]) return fail(SO3D_EINVAL, "null input pointer");
+    use_tma &= aligned16(op.in9[a]);
+  }
+  for (int a = 0; a < Op::kIn3; ++a) {
+    if (!op.in3[a]) return fail(SO3D_EINVAL, "null input pointer");
+    use_tma &= aligned16(op.in3[a]);
+  }
+  for (int a = 0; a < Op::kOut9; ++a) use_tma &= aligned16(op.out9[a]);
+  for (int a = 0; a < Op::kOut3; ++a) use_tma &= aligned16(op.out3[a]);
+  constexpr size_t smem = OpLayout2<Op>::kSmemBytes;
+  static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
+  static int resident_dev[kMaxDevices] = {};
+  auto kern = rowwise_kernel_w2<Op>;
   const int dev = current_device();
   if (resident_dev[dev] == 0) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1340,6 +1561,66 @@ struct QSampleOp {
   }
 };
 
+// Forward noising on two rows per thread, WARP-AUTONOMOUS (rowwise_kernel_w2): the members, table staging and prefetch
+// hooks of QSampleOp (called once per row) and its row arithmetic through the two-lane instantiation of so3d_lanes.cuh
+// (q_sample_quat_l: the same IEEE operations per row, hence the same bits as the one-row kernel;
+// test_lanes_header_restates_the_scalar_arithmetic_bit_for_bit on the host, test_two_row_noising_equals_one_row on the GPU).
+#ifndef SO3D_QS_LANES_DEFAULT2
+#define SO3D_QS_LANES_DEFAULT2 1  // forward noising: two rows per thread by default
+#endif
+#ifndef SO3D_QS2_MINCTAS
+#define SO3D_QS2_MINCTAS 4   // 4 CTAs of 128 threads: <= 128 registers
+#endif
+#ifndef SO3D_QSX2_MINCTAS
+#define SO3D_QSX2_MINCTAS 4
+#endif
+template <bool kExtra, bool kDevSeed = false, bool kNoiseOut = kExtra>
+struct QSample2Op : QSampleOp<kExtra, kDevSeed, kNoiseOut> {
+  using Base = QSampleOp<kExtra, kDevSeed, kNoiseOut>;
+  using Pre2 = typename Base::Pre2;
+  static constexpr int kMinCtas = kExtra ? SO3D_QSX2_MINCTAS : SO3D_QS2_MINCTAS;
+  static constexpr bool kBranchless = kExtra;  // see OpBranchless
+  __device__ float angle_of(const Pre2& p, const float* tab) const {
+    if (this->guide) {
+      const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+      return igso3_angle_from_record(this->cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, p.d.u);
+    }
+    return igso3_angle_from_uniform(this->cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
+  }
+  __device__ void row2(const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
+    const L2 ang{angle_of(p[0], tab), angle_of(p[1], tab)};
+    const Vec3L<L2> axis{L2{p[0].d.axis.x, p[1].d.axis.x}, L2{p[0].d.axis.y, p[1].d.axis.y}, L2{p[0].d.axis.z, p[1].d.axis.z}};
+    QuatL<L2> qn;
+    const QuatL<L2> q = q_sample_quat_l<L2>(lanes_of(a9[0][0], a9[0][1]), L2{p[0].sc, p[1].sc}, axis, ang, &qn);  // diffusion.py:344-346
+    const Mat3L<L2> o = quat_to_mat_unit_l(q);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      o9[0][0].m[k] = o.m[k].x;
+      o9[0][1].m[k] = o.m[k].y;
+    }
+    if (kNoiseOut && this->out9[kNoiseOut ? 1 : 0]) {
+      const Mat3L<L2> nm = quat_to_mat_unit_l(qn);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        o9[kNoiseOut ? 1 : 0][0].m[k] = nm.m[k].x;
+        o9[kNoiseOut ? 1 : 0][1].m[k] = nm.m[k].y;
+      }
+    }
+    const L2 kk{ang.x * rcp_approx(p[0].eps), ang.y * rcp_approx(p[1].eps)};  // diffusion.py:355
+    const L2 tx = mul(kk, axis.x), ty = mul(kk, axis.y), tz = mul(kk, axis.z);
+    o3[0][0] = Vec3{tx.x, ty.x, tz.x};
+    o3[0][1] = Vec3{tx.y, ty.y, tz.y};
+    if (kExtra && this->out3[kExtra ? 1 : 0]) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float lf, g;
+        igso3_logf_g_t<kAuto>(j ? ang.y : ang.x, p[j].eps, 2000, &lf, &g);
+        o3[kExtra ? 1 : 0][j] = Vec3{g * p[j].d.axis.x, g * p[j].d.axis.y, g * p[j].d.axis.z};
+      }
+    }
+  }
+};
+
 // (Forward noising was also tried on two rows per thread with the CTA-synchronous two-row kernel, the step indices
 // travelling with the tile: bit-identical, but SLOWER than the warp-autonomous one-row kernel above -- 0.432 vs 0.395 ms per
 // 2^24 rows, and 0.688 vs 0.486 ms with the score output (profiles/r03l_qsample_lanes_negative.jsonl): this kernel lives
@@ -1472,6 +1753,50 @@ struct PStepOp : PStepPre<SO3D_PS_PREFETCH && !kSharedT> {
     }
     o9[0] = quat_to_mat_unit(qm);
     if (kX0) o9[kX0 ? 1 : 0] = quat_to_mat_unit(qh);
+  }
+};
+
+// The per-row-t reverse step on two rows per thread, warp-autonomous (rowwise_kernel_w2): members and prefetch hooks of
+// PStepOp<false, false>, row arithmetic through p_mean_quat_l<L2> (same bits; test_two_row_reverse_step_rows_equals_one_row).
+#ifndef SO3D_PS2R_MINCTAS
+#define SO3D_PS2R_MINCTAS 4
+#endif
+template <bool kDevSeed>
+struct PStepRows2Op : PStepOp<false, false, kDevSeed> {
+  using Base = PStepOp<false, false, kDevSeed>;
+  using Pre2 = typename Base::Pre2;
+  static constexpr int kMinCtas = SO3D_PS2R_MINCTAS;
+  __device__ float angle_of(const Pre2& p, const float* tab) const {
+    if (this->post_guide) {
+      const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+      return igso3_angle_from_record(this->post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, p.d.u);
+    }
+    return igso3_angle_from_uniform(this->post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
+  }
+  __device__ void row2(const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*)[2], const float* tab) const {
+    const Mat3L<L2> x = lanes_of(a9[0][0], a9[0][1]);
+    const Vec3L<L2> pred{L2{a3[0][0].x, a3[0][1].x}, L2{a3[0][0].y, a3[0][1].y}, L2{a3[0][0].z, a3[0][1].z}};
+    QuatL<L2> qh;
+    QuatL<L2> qm = p_mean_quat_rows_l(x, pred, L2{p[0].k_recip, p[1].k_recip}, L2{p[0].k_recipm1, p[1].k_recipm1}, L2{p[0].k_c1, p[1].k_c1},
+                                      L2{p[0].k_c2, p[1].k_c2}, &qh);
+    if (this->post_cdf) {  // diffusion.py:320-326; rows at t == 0 take the mean
+      const bool n0 = p[0].ti != 0, n1 = p[1].ti != 0;
+      if (n0 || n1) {
+        const L2 ang{n0 ? angle_of(p[0], tab) : 0.f, n1 ? angle_of(p[1], tab) : 0.f};
+        const Vec3L<L2> axis{L2{p[0].d.axis.x, p[1].d.axis.x}, L2{p[0].d.axis.y, p[1].d.axis.y}, L2{p[0].d.axis.z, p[1].d.axis.z}};
+        const QuatL<L2> qz = qmul_l(qm, quat_axis_angle_l(axis, ang));
+        qm.w = L2{n0 ? qz.w.x : qm.w.x, n1 ? qz.w.y : qm.w.y};
+        qm.x = L2{n0 ? qz.x.x : qm.x.x, n1 ? qz.x.y : qm.x.y};
+        qm.y = L2{n0 ? qz.y.x : qm.y.x, n1 ? qz.y.y : qm.y.y};
+        qm.z = L2{n0 ? qz.z.x : qm.z.x, n1 ? qz.z.y : qm.z.y};
+      }
+    }
+    const Mat3L<L2> o = quat_to_mat_unit_l(qm);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      o9[0][0].m[k] = o.m[k].x;
+      o9[0][1].m[k] = o.m[k].y;
+    }
   }
 };
 
@@ -2025,13 +2350,28 @@ template <bool kExtra, bool kDevSeed = false, bool kNoiseOut = kExtra>
 static int launch_q_sample(const float* x0, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac, int64_t T, const float* cdf,
                            const uint32_t* guide, const float* loc, uint64_t seed, uint64_t rng_offset, uint64_t row_offset, float* x_t,
                            float* target3, float* noise, float* score3, int64_t n, void* stream, const uint64_t* seed_dev = nullptr) {
+  // two rows per thread with packed FP32 on the warp-autonomous schedule (SO3D_QS_LANES=1 selects the one-row kernel for A/B runs)
+  // (read per call: the cross-kernel parity test switches it; the variant that also writes the noise matrix would spill
+  // at 128 registers and stays on the one-row kernel)
+  const char* lanes_env = getenv("SO3D_QS_LANES");
+  const bool one_lane = kNoiseOut || (lanes_env ? atoi(lanes_env) == 1 : !SO3D_QS_LANES_DEFAULT2);
+  auto fill = [&](auto& op) {
+    op.seed_dev = seed_dev; op.rng_offset = rng_offset;
+    op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
+    if (kNoiseOut) op.out9[kNoiseOut ? 1 : 0] = noise;
+    if (kExtra) op.out3[kExtra ? 1 : 0] = score3;
+    op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
+    op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
+  };
+  if constexpr (!kNoiseOut) {
+    if (!one_lane) {
+      QSample2Op<kExtra, kDevSeed, kNoiseOut> op2;
+      fill(op2);
+      return launch_rowwise_w2(op2, n, stream, "so3d_q_sample_f32");
+    }
+  }
   QSampleOp<kExtra, kDevSeed, kNoiseOut> op;
-  op.seed_dev = seed_dev; op.rng_offset = rng_offset;
-  op.in9[0] = x0; op.out9[0] = x_t; op.out3[0] = target3;
-  if (kNoiseOut) op.out9[kNoiseOut ? 1 : 0] = noise;
-  if (kExtra) op.out3[kExtra ? 1 : 0] = score3;
-  op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
-  op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
+  fill(op);
   return launch_rowwise(op, n, stream, "so3d_q_sample_f32");
 }
 
@@ -2050,6 +2390,19 @@ static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t,
       op2.t = t; op2.recip = recip; op2.recipm1 = recipm1; op2.coef1 = coef1; op2.coef2 = coef2; op2.T = T;
       op2.post_cdf = post_cdf; op2.loc = loc; op2.seed = seed; op2.rng_offset = rng_offset; op2.row_offset = row_offset;
       return launch_rowwise2(op2, n, stream, "so3d_p_sample_f32");
+    }
+  }
+  if constexpr (!kSharedT && !kX0 && SO3D_PS_PREFETCH) {
+    // per-row t: two rows per thread on the warp-autonomous two-row schedule (SO3D_PS_LANES=1: the one-row kernel; read per call
+    // for the cross-kernel parity test)
+    const char* lanes_env = getenv("SO3D_PS_LANES");
+    if (!(lanes_env && atoi(lanes_env) == 1)) {
+      PStepRows2Op<kDevSeed> op2;
+      op2.seed_dev = seed_dev;
+      op2.in9[0] = x_t; op2.in3[0] = pred3; op2.out9[0] = out;
+      op2.t = t; op2.recip = recip; op2.recipm1 = recipm1; op2.coef1 = coef1; op2.coef2 = coef2; op2.T = T;
+      op2.post_cdf = post_cdf; op2.post_guide = post_guide; op2.loc = loc; op2.seed = seed; op2.rng_offset = rng_offset; op2.row_offset = row_offset;
+      return launch_rowwise_w2(op2, n, stream, "so3d_p_sample_f32");
     }
   }
   PStepOp<kSharedT, kX0, kDevSeed> op;

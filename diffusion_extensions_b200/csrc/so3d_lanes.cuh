@@ -327,6 +327,23 @@ SO3D_HD QuatL<L> p_mean_quat_l(const Mat3L<L>& x_t, const Vec3L<L>& pred, float 
   return qmul_l(q3, q4);
 }
 
+// the same with per-lane schedule scalars (rows with their own step index)
+template <class L>
+SO3D_HD QuatL<L> p_mean_quat_rows_l(const Mat3L<L>& x_t, const Vec3L<L>& pred, L a, L b, L c1, L c2, QuatL<L>* x0h) {
+  const AxisAngleL<L> ax = axis_angle_fast_l(x_t);
+  const L nb = neg(b);
+  const QuatL<L> q1 = quat_axis_angle_l(ax.axis, mul(a, ax.theta));
+  const QuatL<L> q2 = quat_exp_vec_l(Vec3L<L>{mul(nb, pred.x), mul(nb, pred.y), mul(nb, pred.z)});
+  const QuatL<L> qh = qmul_l(q1, q2);
+  Vec3L<L> n0;
+  L h0;
+  quat_axis_halfangle_l(qh, &n0, &h0);
+  const QuatL<L> q3 = quat_axis_angle_l(n0, mul(mulc(2.0f, c1), h0));
+  const QuatL<L> q4 = quat_axis_angle_l(ax.axis, mul(c2, ax.theta));
+  *x0h = qh;
+  return qmul_l(q3, q4);
+}
+
 // ---- drawn direction (sphere_from_uniforms): the azimuth's sin / cos are per-lane MUFU (or the polynomial on the host) ------
 SO3D_HD void sincos_draw_l(L1 x, L1* s, L1* c) { sincos_draw(x.x, &s->x, &c->x); }
 SO3D_HD void sincos_draw_l(L2 x, L2* s, L2* c) {
@@ -344,6 +361,16 @@ SO3D_HD Vec3L<L> sphere_from_uniforms_l(L ua, L ub) {
 }
 
 // ---- lane <-> scalar glue ------------------------------------------------------------------------------------------------
+// diffusion.py:344-346 over lanes: the quaternion of x_t = so3_scale(x0, sc) . noise with noise = rot(axis, ang) (its
+// quaternion goes to *qn_out) -- the operations of the one-row forward-noising kernel (QSampleOp::row) in the same order
+template <class L>
+SO3D_HD QuatL<L> q_sample_quat_l(const Mat3L<L>& x0, L sc, const Vec3L<L>& axis, L ang, QuatL<L>* qn_out) {
+  const QuatL<L> qn = quat_axis_angle_l(axis, ang);
+  const AxisAngleL<L> ax = axis_angle_fast_l(x0);
+  *qn_out = qn;
+  return qmul_l(quat_axis_angle_l(ax.axis, mul(sc, ax.theta)), qn);
+}
+
 SO3D_HD Mat3L<L1> lanes_of(const Mat3& a) {
   Mat3L<L1> r;
   for (int k = 0; k < 9; ++k) r.m[k] = L1{a.m[k]};

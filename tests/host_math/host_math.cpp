@@ -174,6 +174,58 @@ extern "C" long hm_lanes_p_mean(const float* x, const float* pred, const float* 
   }
   return bad;
 }
+// per-row schedule scalars (p_mean_quat_rows_l) against the scalar p_mean_quat: mismatching words
+extern "C" long hm_lanes_p_mean_rows(const float* x, const float* pred, const float* a, const float* b, const float* c1, const float* c2, long n) {
+  long bad = 0;
+  for (long i = 0; i + 1 < n; i += 2) {
+    const Mat3 r0 = ld(x + 9 * i), r1 = ld(x + 9 * (i + 1));
+    Quat qh0, qh1;
+    const Quat q0 = p_mean_quat(r0, Vec3{pred[3*i], pred[3*i+1], pred[3*i+2]}, a[i], b[i], c1[i], c2[i], &qh0);
+    const Quat q1 = p_mean_quat(r1, Vec3{pred[3*i+3], pred[3*i+4], pred[3*i+5]}, a[i+1], b[i+1], c1[i+1], c2[i+1], &qh1);
+    const Mat3 m0 = quat_to_mat_unit(q0), m1 = quat_to_mat_unit(q1);
+    QuatL<L2> qh2;
+    const Vec3L<L2> p2{L2{pred[3*i], pred[3*i+3]}, L2{pred[3*i+1], pred[3*i+4]}, L2{pred[3*i+2], pred[3*i+5]}};
+    const QuatL<L2> q2 = p_mean_quat_rows_l<L2>(lanes_of(r0, r1), p2, L2{a[i], a[i+1]}, L2{b[i], b[i+1]}, L2{c1[i], c1[i+1]}, L2{c2[i], c2[i+1]}, &qh2);
+    const Mat3L<L2> m2 = quat_to_mat_unit_l(q2);
+    for (int k = 0; k < 9; ++k) {
+      bad += fbits(m2.m[k].x) != fbits(m0.m[k]);
+      bad += fbits(m2.m[k].y) != fbits(m1.m[k]);
+    }
+  }
+  return bad;
+}
+// forward noising over lanes (q_sample_quat_l) against the one-row kernel's scalar sequence: mismatching words
+extern "C" long hm_lanes_q_sample(const float* x, const float* sc, const float* axis, const float* ang, float* xt, long n) {
+  long bad = 0;
+  for (long i = 0; i + 1 < n; i += 2) {
+    const Mat3 r0 = ld(x + 9 * i), r1 = ld(x + 9 * (i + 1));
+    Mat3 m[2], nm[2];
+    for (int j = 0; j < 2; ++j) {
+      const long r = i + j;
+      const Vec3 a{axis[3*r], axis[3*r+1], axis[3*r+2]};
+      const Quat qn = quat_axis_angle(a, ang[r]);
+      const AxisAngleF ax = axis_angle_fast(j ? r1 : r0);
+      m[j] = quat_to_mat_unit(qmul(quat_axis_angle(ax.axis, sc[r] * ax.theta), qn));
+      nm[j] = quat_to_mat_unit(qn);
+    }
+    const Vec3L<L2> a2{L2{axis[3*i], axis[3*i+3]}, L2{axis[3*i+1], axis[3*i+4]}, L2{axis[3*i+2], axis[3*i+5]}};
+    QuatL<L2> qn2;
+    const QuatL<L2> q2 = q_sample_quat_l<L2>(lanes_of(r0, r1), L2{sc[i], sc[i+1]}, a2, L2{ang[i], ang[i+1]}, &qn2);
+    const Mat3L<L2> m2 = quat_to_mat_unit_l(q2), n2 = quat_to_mat_unit_l(qn2);
+    const Vec3L<L1> a1{L1{axis[3*i]}, L1{axis[3*i+1]}, L1{axis[3*i+2]}};
+    QuatL<L1> qn1;
+    const Mat3L<L1> m1 = quat_to_mat_unit_l(q_sample_quat_l<L1>(lanes_of(r0), L1{sc[i]}, a1, L1{ang[i]}, &qn1));
+    for (int k = 0; k < 9; ++k) {
+      bad += fbits(m2.m[k].x) != fbits(m[0].m[k]);
+      bad += fbits(m2.m[k].y) != fbits(m[1].m[k]);
+      bad += fbits(n2.m[k].x) != fbits(nm[0].m[k]);
+      bad += fbits(n2.m[k].y) != fbits(nm[1].m[k]);
+      bad += fbits(m1.m[k].x) != fbits(m[0].m[k]);
+      xt[9 * i + k] = m2.m[k].x; xt[9 * (i + 1) + k] = m2.m[k].y;
+    }
+  }
+  return bad;
+}
 extern "C" long hm_lanes_sphere(const float* ua, const float* ub, float* axis, long n) {
   long bad = 0;
   for (long i = 0; i + 1 < n; i += 2) {

@@ -532,6 +532,87 @@ def test_fused_q_sample_consistency(dx, cuda_device):
     assert ks < 2.5 / math.sqrt(ang.size)
 
 
+def test_two_row_noising_equals_one_row(dx, cuda_device, monkeypatch):
+    """Forward noising runs two rows per thread (packed FP32, warp-autonomous two-row engine) by default; the one-row
+    kernel (SO3D_QS_LANES=1) must give the same bits: full and ragged tiles, a single row, the score output, a shard
+    offset, unaligned (non-TMA) arrays and out-of-range step indices."""
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    fwd, _, _ = p.tables()
+    fg, _ = p.guides()
+    ops = dx.ops
+    g = torch.Generator(device=cuda_device); g.manual_seed(77)
+    for n in (1, 31, 64, 255, 256, 257, 1000, 256 * 148 * 4 + 77, 300_001):
+        x0 = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+        t = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+        if n > 40:
+            t[:4] = torch.tensor([0, 999, -5, 1234], device=cuda_device)   # clamped like the one-row kernel
+            x0[5] = torch.eye(3, device=cuda_device)
+        for kw in ({}, {"want_score": True}, {"want_target": False}, {"row_offset": 12345}):
+            res = {}
+            for lanes in ("1", "2"):
+                monkeypatch.setenv("SO3D_QS_LANES", lanes)
+                res[lanes] = ops.q_sample_fused(x0, t, p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd, seed=9, rng_offset=3, guide=fg, **kw)
+            for k in res["1"]:
+                if res["1"][k] is not None:
+                    assert torch.equal(res["1"][k], res["2"][k]), (n, kw, k)
+    # unaligned views (4-byte aligned only): both kernels fall back to plain loads / stores
+    n = 1000
+    buf = torch.empty(n * 9 + 1, device=cuda_device)
+    x0u = buf[1:].view(n, 3, 3)
+    x0u.copy_(ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g)))
+    t = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+    res = {}
+    for lanes in ("1", "2"):
+        monkeypatch.setenv("SO3D_QS_LANES", lanes)
+        res[lanes] = ops.q_sample_fused(x0u, t, p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd, seed=9, rng_offset=3, guide=fg, want_score=True)
+    for k in res["1"]:
+        if res["1"][k] is not None:
+            assert torch.equal(res["1"][k], res["2"][k]), k
+    # without the guide table (full binary search per row)
+    for lanes in ("1", "2"):
+        monkeypatch.setenv("SO3D_QS_LANES", lanes)
+        res[lanes] = ops.q_sample_fused(x0u, t, p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd, seed=9, rng_offset=3)
+    assert torch.equal(res["1"]["x_t"], res["2"]["x_t"]) and torch.equal(res["1"]["target"], res["2"]["target"])
+
+
+def test_two_row_reverse_step_rows_equals_one_row(dx, cuda_device, monkeypatch):
+    """The per-row-t reverse step runs two rows per thread by default; the one-row kernel (SO3D_PS_LANES=1) gives the same
+    bits: ragged sizes, rows at t = 0 next to noisy rows, without the guide, without noise, unaligned arrays, a shard offset."""
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    _, post, _ = p.tables()
+    _, pg = p.guides()
+    ops = dx.ops
+    sched = (p.sqrt_recip_alphas_cumprod, p.sqrt_recipm1_alphas_cumprod, p.posterior_mean_coef1, p.posterior_mean_coef2)
+    g = torch.Generator(device=cuda_device); g.manual_seed(78)
+
+    def both(x, pred, t, **kw):
+        res = {}
+        for lanes in ("1", "2"):
+            monkeypatch.setenv("SO3D_PS_LANES", lanes)
+            res[lanes] = ops.p_sample_fused(x, pred, t, *sched, seed=5, rng_offset=7, **kw)
+        return res["1"], res["2"]
+
+    for n in (1, 33, 64, 255, 256, 257, 4097, 256 * 148 * 4 + 99, 200_003):
+        x = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+        pred = torch.randn(n, 3, device=cuda_device, generator=g) * 0.4
+        t = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+        t[::3] = 0                                         # mean-only rows interleaved with noisy ones (both lanes of a thread differ)
+        if n > 40:
+            t[1:5] = torch.tensor([999, -3, 5000, 1], device=cuda_device)
+            x[7] = torch.eye(3, device=cuda_device)
+        for kw in ({"post_cdf": post, "post_guide": pg}, {"post_cdf": post}, {}, {"post_cdf": post, "post_guide": pg, "row_offset": 999}):
+            a, b = both(x, pred, t, **kw)
+            assert torch.equal(a, b), (n, list(kw))
+    n = 3000
+    buf = torch.empty(n * 9 + 1, device=cuda_device)
+    xu = buf[1:].view(n, 3, 3)
+    xu.copy_(ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g)))
+    pred = torch.randn(n, 3, device=cuda_device, generator=g) * 0.4
+    t = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+    a, b = both(xu, pred, t, post_cdf=post, post_guide=pg)
+    assert torch.equal(a, b)
+
+
 def test_fused_p_sample_against_oracle(dx, cuda_device):
     """Fused reverse step with per-row t vs the oracle mean; the noise factor is recovered as
     mean^T out and must be a rotation whose angle follows the posterior table."""

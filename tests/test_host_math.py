@@ -492,6 +492,16 @@ def test_lanes_header_restates_the_scalar_arithmetic_bit_for_bit(hm):
         bad = hm.hm_lanes_p_mean(fp(R), fp(pred), fp(a), fp(b), fp(c1), fp(c2), fp(mean), fp(x0h), ctypes.c_long(n), has_pred)
         assert bad == 0, (has_pred, bad)
         assert np.isfinite(mean).all()
+    hm.hm_lanes_p_mean_rows.restype = ctypes.c_long   # per-row step indices (the two lanes carry different schedule scalars)
+    assert hm.hm_lanes_p_mean_rows(fp(R), fp(pred), fp(a), fp(b), fp(c1), fp(c2), ctypes.c_long(n)) == 0
+    # forward noising (q_sample_quat_l): x0 incl. identity / near-pi rows, schedule scales, drawn axis and angle
+    sc = f32(s["sqrt_alphas_cumprod"][t])
+    nax = rng.standard_normal((n, 3)); nax = f32(nax / np.linalg.norm(nax, axis=-1, keepdims=True))
+    nang = f32(rng.uniform(0, np.pi, n)); nang[:3] = [0.0, np.pi, 1e-4]
+    xt = np.empty((n, 9), np.float32)
+    hm.hm_lanes_q_sample.restype = ctypes.c_long
+    assert hm.hm_lanes_q_sample(fp(R), fp(sc), fp(nax), fp(nang), fp(xt), ctypes.c_long(n)) == 0
+    assert np.isfinite(xt).all()
     ua, ub = f32(rng.uniform(0, 1, n)), f32(rng.uniform(0, 1, n))
     ua[:4] = [0.0, 1.0 - 2 ** -24, 0.5, 2 ** -24]
     axis = np.empty((n, 3), np.float32)
