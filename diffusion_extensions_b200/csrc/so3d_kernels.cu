@@ -819,7 +819,8 @@ int launch_rowwise2(const Op& op, int64_t n, void* stream, const char* name) {
 // under elect.sync.  Everything that is paid once per warp and tile -- ring wait, stage release, fence, store issue, tile
 // bookkeeping -- is paid per 64 rows instead of per 32, and the op's FP32 arithmetic runs as FFMA2 / FMUL2 / FADD2.
 //   Op2 provides Pre1 / Pre2 / prefetch1 / prefetch2 like a one-row op (called once per row) and
-//     __device__ void row2(const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const
+//     __device__ void row2(int64_t i0, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const
+//   for the rows i0 (lane 0) and i0 + 32 (lane 1).
 // ------------------------------------------------------------------------------------------------
 // An op may set Op::kBranchless: no branches around the prefetch of the next tiles and the rows' arithmetic, so that ptxas
 // schedules the integer-heavy prefetch (Philox, address arithmetic) and the FP32 arithmetic of the current rows as ONE block.
@@ -949,7 +950,7 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
         p1_next2[0] = op.prefetch1(pre_row(row0 + 2 * stride_rows, r0));
         p1_next2[1] = op.prefetch1(pre_row(row0 + 2 * stride_rows, r1));
       }
-      if (kBl || r0 < rows) op.row2(p2_cur, a9, a3, o9, o3, s_tab);
+      if (kBl || r0 < rows) op.row2(row0 + r0, p2_cur, a9, a3, o9, o3, s_tab);
       p2_cur[0] = p2_next[0], p2_cur[1] = p2_next[1];
       p1_next[0] = p1_next2[0], p1_next[1] = p1_next2[1];
     }
@@ -1587,7 +1588,7 @@ struct QSample2Op : QSampleOp<kExtra, kDevSeed, kNoiseOut> {
     }
     return igso3_angle_from_uniform(this->cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
   }
-  __device__ void row2(const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
+  __device__ void row2(int64_t, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
     const L2 ang{angle_of(p[0], tab), angle_of(p[1], tab)};
     const Vec3L<L2> axis{L2{p[0].d.axis.x, p[1].d.axis.x}, L2{p[0].d.axis.y, p[1].d.axis.y}, L2{p[0].d.axis.z, p[1].d.axis.z}};
     QuatL<L2> qn;
@@ -1773,7 +1774,7 @@ struct PStepRows2Op : PStepOp<false, false, kDevSeed> {
     }
     return igso3_angle_from_uniform(this->post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
   }
-  __device__ void row2(const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*)[2], const float* tab) const {
+  __device__ void row2(int64_t, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*)[2], const float* tab) const {
     const Mat3L<L2> x = lanes_of(a9[0][0], a9[0][1]);
     const Vec3L<L2> pred{L2{a3[0][0].x, a3[0][1].x}, L2{a3[0][0].y, a3[0][1].y}, L2{a3[0][0].z, a3[0][1].z}};
     QuatL<L2> qh;
@@ -1957,6 +1958,54 @@ struct SE3QSampleOp {
     o3[2] = Vec3{z.a, z.b, z.c};
   }
 };
+
+#if SO3D_SE3QS_PREFETCH
+// SE(3) noising on two rows per thread, warp-autonomous (rowwise_kernel_w2): same bits as SE3QSampleOp
+// (test_two_row_se3_noising_equals_one_row).
+#ifndef SO3D_SE3QS2_MINCTAS
+#define SO3D_SE3QS2_MINCTAS 4
+#endif
+#ifndef SO3D_SE3QS2_BRANCHLESS
+#define SO3D_SE3QS2_BRANCHLESS 0
+#endif
+struct SE3QSample2Op : SE3QSampleOp {
+  static constexpr int kMinCtas = SO3D_SE3QS2_MINCTAS;
+  static constexpr bool kBranchless = SO3D_SE3QS2_BRANCHLESS;
+  __device__ float angle_of(const Pre2& p, const float* tab) const {
+    if (guide) {
+      const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+      return igso3_angle_from_record(cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, p.d.u);
+    }
+    return igso3_angle_from_uniform(cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
+  }
+  __device__ void row2(int64_t i0, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
+    const L2 ang{angle_of(p[0], tab), angle_of(p[1], tab)};
+    const Vec3L<L2> axis{L2{p[0].d.axis.x, p[1].d.axis.x}, L2{p[0].d.axis.y, p[1].d.axis.y}, L2{p[0].d.axis.z, p[1].d.axis.z}};
+    const L2 eps{p[0].eps, p[1].eps}, sc{p[0].sc, p[1].sc};
+    QuatL<L2> qn;
+    const Mat3L<L2> o = quat_to_mat_unit_l(q_sample_quat_l<L2>(lanes_of(a9[0][0], a9[0][1]), sc, axis, ang, &qn));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      o9[0][0].m[k] = o.m[k].x;
+      o9[0][1].m[k] = o.m[k].y;
+    }
+    const L2 kk{ang.x * rcp_approx(eps.x), ang.y * rcp_approx(eps.y)};
+    const L2 tx = mul(kk, axis.x), ty = mul(kk, axis.y), tz = mul(kk, axis.z);
+    o3[0][0] = Vec3{tx.x, ty.x, tz.x};
+    o3[0][1] = Vec3{tx.y, ty.y, tz.y};
+    const Normal4 z0 = normal4_from_u4(philox4x32_10(key_shift, row_offset + (uint64_t)i0));
+    const Normal4 z1 = normal4_from_u4(philox4x32_10(key_shift, row_offset + (uint64_t)i0 + 32u));
+    const L2 ns = mul(eps, bc<L2>(shift_scale));
+    const L2 sx = fma(sc, L2{a3[0][0].x, a3[0][1].x}, mul(ns, L2{z0.a, z1.a}));
+    const L2 sy = fma(sc, L2{a3[0][0].y, a3[0][1].y}, mul(ns, L2{z0.b, z1.b}));
+    const L2 sz = fma(sc, L2{a3[0][0].z, a3[0][1].z}, mul(ns, L2{z0.c, z1.c}));
+    o3[1][0] = Vec3{sx.x, sy.x, sz.x};
+    o3[1][1] = Vec3{sx.y, sy.y, sz.y};
+    o3[2][0] = Vec3{z0.a, z0.b, z0.c};
+    o3[2][1] = Vec3{z1.a, z1.b, z1.c};
+  }
+};
+#endif
 
 // reverse step: diffusion.py:446-485
 //   rot as PStepOp;  shift0_hat = recip_t shift_t - recipm1_t pred_shift;  mean = c1 shift0_hat + c2 shift_t;
@@ -2541,10 +2590,25 @@ int so3d_se3_q_sample_f32(const float* rot0, const float* shift0, const int64_t*
   SO3D_REQUIRE(rot0 && shift0 && t && sqrt_ac && sqrt_1m_ac && cdf && loc && rot_t && shift_t, "so3d_se3_q_sample_f32: null pointer");
   SO3D_REQUIRE(T > 0, "so3d_se3_q_sample_f32: T must be positive");
   SO3D_REQUIRE(rng_offset < kShiftStream, "so3d_se3_q_sample_f32: rng_offset must be below 2^63");
+  auto fill = [&](auto& op) {
+    op.in9[0] = rot0; op.in3[0] = shift0; op.out9[0] = rot_t; op.out3[0] = target_rot3; op.out3[1] = shift_t; op.out3[2] = target_shift3;
+    op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
+    op.shift_scale = shift_scale; op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
+  };
+#if SO3D_SE3QS_PREFETCH
+  // The two-row kernel is bit-identical but NOT faster here (r04f/r04g: 0.467 ms at 4 CTAs / 119 registers, 0.425 at 3 CTAs /
+  // 135 registers, 0.465 branch-free, against 0.424 for the one-row kernel: with four output arrays this kernel sits at 0.77 of
+  // the HBM peak already and gains nothing from fewer issue slots).  It stays selectable (SO3D_SE3_QS_LANES=2) for the
+  // cross-kernel parity test.
+  const char* lanes_env = getenv("SO3D_SE3_QS_LANES");
+  if (lanes_env && atoi(lanes_env) == 2) {
+    SE3QSample2Op op2;
+    fill(op2);
+    return launch_rowwise_w2(op2, n, stream, "so3d_se3_q_sample_f32");
+  }
+#endif
   SE3QSampleOp op;
-  op.in9[0] = rot0; op.in3[0] = shift0; op.out9[0] = rot_t; op.out3[0] = target_rot3; op.out3[1] = shift_t; op.out3[2] = target_shift3;
-  op.t = t; op.sqrt_ac = sqrt_ac; op.sqrt_1m_ac = sqrt_1m_ac; op.T = T; op.cdf = cdf; op.guide = guide; op.loc = loc;
-  op.shift_scale = shift_scale; op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
+  fill(op);
   return launch_rowwise(op, n, stream, "so3d_se3_q_sample_f32");
 }
 

@@ -613,6 +613,32 @@ def test_two_row_reverse_step_rows_equals_one_row(dx, cuda_device, monkeypatch):
     assert torch.equal(a, b)
 
 
+def test_two_row_se3_noising_equals_one_row(dx, cuda_device, monkeypatch):
+    """SE(3) noising: the two-row kernel (SO3D_SE3_QS_LANES=2; measured no faster, so not the default) and the one-row kernel
+    give the same bits."""
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    fwd, _, _ = p.tables()
+    fg, _ = p.guides()
+    ops = dx.ops
+    g = torch.Generator(device=cuda_device); g.manual_seed(79)
+    for n in (1, 40, 256, 300, 256 * 148 * 4 + 5, 150_001):
+        rot = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+        shift = torch.randn(n, 3, device=cuda_device, generator=g) * 10
+        t = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+        for kw in ({"guide": fg}, {}, {"guide": fg, "row_offset": 4242}):
+            res = {}
+            for lanes in ("1", "2"):
+                monkeypatch.setenv("SO3D_SE3_QS_LANES", lanes)
+                res[lanes] = ops.se3_q_sample_fused(rot, shift, t, p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd, 75.0, seed=4, rng_offset=2, **kw)
+            a, b = res["1"], res["2"]
+            a = list(a.values()) if isinstance(a, dict) else list(a)
+            b = list(b.values()) if isinstance(b, dict) else list(b)
+            assert len(a) == len(b) >= 2
+            for u, v in zip(a, b):
+                if u is not None:
+                    assert torch.equal(u, v), (n, list(kw))
+
+
 def test_fused_p_sample_against_oracle(dx, cuda_device):
     """Fused reverse step with per-row t vs the oracle mean; the noise factor is recovered as
     mean^T out and must be a rotation whose angle follows the posterior table."""
