@@ -841,23 +841,32 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
   constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
   constexpr int kWarps = kT2 / 32;
   using Lay = OpLayout2<Op>;
-  static_assert(Lay::kInStages == 2 && Lay::kOutStages == 1, "rowwise_kernel_w2: two input stages, one output stage");
+  // kWarpIn (Op::kInStages == 1): ONE input stage, every warp loads its own 64-row slice (its own mbarrier) and refills it as
+  // soon as its rows are in registers -- no ring, no release counter, no coupling between the warps of a CTA, and 12 KB
+  // less shared memory.  Otherwise (two stages): CTA-wide loads into a ring, the last warp out refills the stage.
+  constexpr bool kWarpIn = Lay::kInStages == 1;
+  static_assert(Lay::kOutStages == 1, "rowwise_kernel_w2: one output stage");
   float* smem = reinterpret_cast<float*>(smem4);
-  float* s_out = smem + 2 * Lay::kInFloats;
+  float* s_out = smem + Lay::kInStages * Lay::kInFloats;
   float* s_tab = s_out + Lay::kOutFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);  // kWarpIn: one per warp;  else two + the release counters
   uint32_t* released = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, lane = tid & 31;
   const int wrow = __shfl_sync(0xffffffffu, 2 * (tid & ~31), 0);  // first row of the warp's slice (warp-uniform: see rowwise_kernel)
   const int r0 = wrow + lane, r1 = r0 + 32;                       // this thread's two rows of a tile
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    released[0] = 0;
-    released[1] = 0;
+    if (kWarpIn) {
+      for (int w = 0; w < kWarps; ++w) mbar_init(&bars[w], 1);
+    } else {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      released[0] = 0;
+      released[1] = 0;
+    }
     fence_barrier_init();
   }
   __syncthreads();
+  uint64_t* wbar = &bars[kWarpIn ? (wrow >> 6) : 0];  // this warp's barrier (kWarpIn)
   const int64_t tiles = (n + kRows2 - 1) / kRows2;
   const int my_tiles = (tiles > (int64_t)blockIdx.x) ? (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int my_full = my_tiles - (((n % kRows2) != 0 && (tiles - 1) % gridDim.x == blockIdx.x) ? 1 : 0);
@@ -872,7 +881,17 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
 #pragma unroll
     for (int a = 0; a < kI3; ++a) bulk_load(base + kI9 * kRows2 * 9 + a * kRows2 * 3, op.in3[a] + row0 * 3, kRows2 * 3 * sizeof(float), &bars[st]);
   };
-  if (tid == 0 && use_tma) {
+  auto issue_warp_load = [&](int64_t row0) {  // one lane: this warp's 64-row slice of the tile at row0 (kWarpIn)
+    if (kI9 + kI3 == 0) return;
+    mbar_expect_tx(wbar, (uint32_t)(64 * Lay::kInWords * sizeof(float)));
+#pragma unroll
+    for (int a = 0; a < kI9; ++a) bulk_load(smem + a * kRows2 * 9 + wrow * 9, op.in9[a] + (row0 + wrow) * 9, 64 * 9 * sizeof(float), wbar);
+#pragma unroll
+    for (int a = 0; a < kI3; ++a) bulk_load(smem + kI9 * kRows2 * 9 + a * kRows2 * 3 + wrow * 3, op.in3[a] + (row0 + wrow) * 3, 64 * 3 * sizeof(float), wbar);
+  };
+  if (kWarpIn) {
+    if (use_tma && my_full > 0 && elect_one()) issue_warp_load(first_row);
+  } else if (tid == 0 && use_tma) {
     if (my_full > 0) issue_load(0, first_row);
     if (my_full > 1) issue_load(1, first_row + stride_rows);
   }
@@ -896,7 +915,7 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
 
   int64_t row0 = first_row;
   for (int k = 0; k < my_tiles; ++k, row0 += stride_rows) {
-    const int st = k & 1;
+    const int st = kWarpIn ? 0 : (k & 1);
     const int rows = k < my_full ? kRows2 : (int)(n - row0);
     const bool tma = use_tma && rows == kRows2;
     int wrows = rows - wrow;  // rows of this warp's slice that exist
@@ -907,7 +926,7 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
     float* s_o3 = s_o9 + kO9 * kRows2 * 9;
     if (kI9 + kI3 > 0) {
       if (tma) {
-        mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
+        if (kWarpIn) mbar_wait(wbar, (uint32_t)(k & 1)); else mbar_wait(&bars[st], (uint32_t)((k >> 1) & 1));
       } else {
 #pragma unroll
         for (int a = 0; a < kI9; ++a) warp_load<9>(s_i9 + a * kRows2 * 9 + wrow * 9, op.in9[a] + (row0 + wrow) * 9, wrows, lane);
@@ -930,7 +949,9 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
     }
     if (kI9 + kI3 > 0) {
       __syncwarp();  // every lane's copy of its rows is complete
-      if (tma && lane == 0 && k + 2 < my_full) {
+      if (kWarpIn) {
+        if (tma && k + 1 < my_full && elect_one()) issue_warp_load(row0 + stride_rows);  // the next tile's slice loads behind the arithmetic
+      } else if (tma && lane == 0 && k + 2 < my_full) {
         const uint32_t old = atom_add_acq_rel_cta(&released[st], 1u);
         if ((old & (kWarps - 1)) == kWarps - 1) issue_load(k + 2, row0 + 2 * stride_rows);  // last warp out refills the stage
       }
@@ -1008,7 +1029,7 @@ int launch_rowwise_w2(const Op& op, int64_t n, void* stream, const char* name) {
   }
   for (int a = 0; a < Op::kOut9; ++a) use_tma &= aligned16(op.out9[a]);
   for (int a = 0; a < Op::kOut3; ++a) use_tma &= aligned16(op.out3[a]);
-  constexpr size_t smem = OpLayout2<Op>::kSmemBytes;
+  constexpr size_t smem = OpLayout2<Op>::kSmemBytes + (kT2 / 32) * sizeof(uint64_t);  // (+ per-warp barriers of the one-stage mode)
   static_assert(smem <= 227 * 1024, "tile stages exceed shared memory");
   static int resident_dev[kMaxDevices] = {};
   auto kern = rowwise_kernel_w2<Op>;
@@ -1575,12 +1596,16 @@ struct QSampleOp {
 #ifndef SO3D_QSX2_MINCTAS
 #define SO3D_QSX2_MINCTAS 4
 #endif
+#ifndef SO3D_QS2_INSTAGES
+#define SO3D_QS2_INSTAGES 1  // 1: every warp loads its own slice (rowwise_kernel_w2, kWarpIn): 0.3215 -> 0.3042 ms, with the score 0.386 -> 0.365 (r04j)
+#endif
 template <bool kExtra, bool kDevSeed = false, bool kNoiseOut = kExtra>
 struct QSample2Op : QSampleOp<kExtra, kDevSeed, kNoiseOut> {
   using Base = QSampleOp<kExtra, kDevSeed, kNoiseOut>;
   using Pre2 = typename Base::Pre2;
   static constexpr int kMinCtas = kExtra ? SO3D_QSX2_MINCTAS : SO3D_QS2_MINCTAS;
   static constexpr bool kBranchless = kExtra;  // see OpBranchless
+  static constexpr int kInStages = SO3D_QS2_INSTAGES;
   __device__ float angle_of(const Pre2& p, const float* tab) const {
     if (this->guide) {
       const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
@@ -1762,11 +1787,15 @@ struct PStepOp : PStepPre<SO3D_PS_PREFETCH && !kSharedT> {
 #ifndef SO3D_PS2R_MINCTAS
 #define SO3D_PS2R_MINCTAS 4
 #endif
+#ifndef SO3D_PS2R_INSTAGES
+#define SO3D_PS2R_INSTAGES 1  // per-warp input slices: 0.382 -> 0.372 ms (r04j)
+#endif
 template <bool kDevSeed>
 struct PStepRows2Op : PStepOp<false, false, kDevSeed> {
   using Base = PStepOp<false, false, kDevSeed>;
   using Pre2 = typename Base::Pre2;
   static constexpr int kMinCtas = SO3D_PS2R_MINCTAS;
+  static constexpr int kInStages = SO3D_PS2R_INSTAGES;
   __device__ float angle_of(const Pre2& p, const float* tab) const {
     if (this->post_guide) {
       const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
@@ -1851,6 +1880,10 @@ struct PStep2Op {
     }
   }
   __device__ void row2(int64_t i0, const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*)[2], const float* tab) const {
+    row2_at<kT2>(i0, a9, a3, o9, tab);
+  }
+  template <int kLane1>  // lane 1 is the row i0 + kLane1
+  __device__ void row2_at(int64_t i0, const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], const float* tab) const {
     const int ti = __float_as_int(tab[kTabScal]);
     const float k_recip = tab[kTabScal + 1], k_recipm1 = tab[kTabScal + 2], k_c1 = tab[kTabScal + 3], k_c2 = tab[kTabScal + 4];
     const Mat3L<L2> x = lanes_of(a9[0][0], a9[0][1]);
@@ -1860,7 +1893,7 @@ struct PStep2Op {
     if (post_cdf && ti != 0) {  // diffusion.py:320-326
       const uint64_t sd = kDevSeed ? ((uint64_t)__float_as_uint(tab[kTabScal + 5]) | ((uint64_t)__float_as_uint(tab[kTabScal + 6]) << 32)) : seed;
       const uint64_t row = row_offset + (uint64_t)i0;
-      const U4 r0 = philox4x32_10(sd, row, rng_offset), r1 = philox4x32_10(sd, row + kT2, rng_offset);
+      const U4 r0 = philox4x32_10(sd, row, rng_offset), r1 = philox4x32_10(sd, row + kLane1, rng_offset);
       const Vec3L<L2> axis = sphere_from_uniforms_l(L2{u01(r0.x), u01(r1.x)}, L2{u01(r0.y), u01(r1.y)});
       const L2 ang{shared_row_angle(tab, u01(r0.z)), shared_row_angle(tab, u01(r1.z))};
       qm = qmul_l(qm, quat_axis_angle_l(axis, ang));
@@ -1871,6 +1904,24 @@ struct PStep2Op {
       o9[0][0].m[k] = o.m[k].x;
       o9[0][1].m[k] = o.m[k].y;
     }
+  }
+};
+
+// Experiment (SO3D_PSTEP_ENGINE=w2): the same step on the warp-autonomous two-row engine -- no CTA barriers, but two input
+// stages (44 KB -> 5 CTAs of 4 warps instead of 7).
+#ifndef SO3D_PSS2W_INSTAGES
+#define SO3D_PSS2W_INSTAGES 1
+#endif
+template <bool kDevSeed>
+struct PStep2wOp : PStep2Op<kDevSeed> {
+  struct Pre1 {};
+  struct Pre2 {};
+  static constexpr int kInStages = SO3D_PSS2W_INSTAGES;
+  static constexpr int kMinCtas = SO3D_PSS2W_INSTAGES == 1 ? 7 : 5;
+  __device__ Pre1 prefetch1(int64_t) const { return Pre1{}; }
+  __device__ Pre2 prefetch2(int64_t, const Pre1&) const { return Pre2{}; }
+  __device__ void row2(int64_t i0, const Pre2 (&)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*)[2], const float* tab) const {
+    this->template row2_at<32>(i0, a9, a3, o9, tab);
   }
 };
 
@@ -1963,13 +2014,17 @@ struct SE3QSampleOp {
 // SE(3) noising on two rows per thread, warp-autonomous (rowwise_kernel_w2): same bits as SE3QSampleOp
 // (test_two_row_se3_noising_equals_one_row).
 #ifndef SO3D_SE3QS2_MINCTAS
-#define SO3D_SE3QS2_MINCTAS 4
+#define SO3D_SE3QS2_MINCTAS 3  // 135 registers; the 119-register schedule of a 4-CTA cap is 10 % slower (r04g, r04k)
 #endif
 #ifndef SO3D_SE3QS2_BRANCHLESS
 #define SO3D_SE3QS2_BRANCHLESS 0
 #endif
+#ifndef SO3D_SE3QS2_INSTAGES
+#define SO3D_SE3QS2_INSTAGES 1
+#endif
 struct SE3QSample2Op : SE3QSampleOp {
   static constexpr int kMinCtas = SO3D_SE3QS2_MINCTAS;
+  static constexpr int kInStages = SO3D_SE3QS2_INSTAGES;
   static constexpr bool kBranchless = SO3D_SE3QS2_BRANCHLESS;
   __device__ float angle_of(const Pre2& p, const float* tab) const {
     if (guide) {
@@ -2432,6 +2487,15 @@ static int launch_p_step(const float* x_t, const float* pred3, const int64_t* t,
   if constexpr (kSharedT && !kX0) {
     // the hot shared-t step: two rows per thread with packed FP32 (SO3D_PSTEP_LANES=1 selects the one-row kernel for A/B runs)
     static const bool one_lane = [] { const char* e = getenv("SO3D_PSTEP_LANES"); return e && atoi(e) == 1; }();
+    static const bool w2_engine = [] { const char* e = getenv("SO3D_PSTEP_ENGINE"); return e && strcmp(e, "w2") == 0; }();
+    if (!one_lane && post_cdf && w2_engine) {
+      PStep2wOp<kDevSeed> op2;
+      op2.seed_dev = seed_dev;
+      op2.in9[0] = x_t; op2.in3[0] = pred3; op2.out9[0] = out;
+      op2.t = t; op2.recip = recip; op2.recipm1 = recipm1; op2.coef1 = coef1; op2.coef2 = coef2; op2.T = T;
+      op2.post_cdf = post_cdf; op2.loc = loc; op2.seed = seed; op2.rng_offset = rng_offset; op2.row_offset = row_offset;
+      return launch_rowwise_w2(op2, n, stream, "so3d_p_sample_f32");
+    }
     if (!one_lane && post_cdf) {
       PStep2Op<kDevSeed> op2;
       op2.seed_dev = seed_dev;
@@ -2596,12 +2660,10 @@ int so3d_se3_q_sample_f32(const float* rot0, const float* shift0, const int64_t*
     op.shift_scale = shift_scale; op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
   };
 #if SO3D_SE3QS_PREFETCH
-  // The two-row kernel is bit-identical but NOT faster here (r04f/r04g: 0.467 ms at 4 CTAs / 119 registers, 0.425 at 3 CTAs /
-  // 135 registers, 0.465 branch-free, against 0.424 for the one-row kernel: with four output arrays this kernel sits at 0.77 of
-  // the HBM peak already and gains nothing from fewer issue slots).  It stays selectable (SO3D_SE3_QS_LANES=2) for the
-  // cross-kernel parity test.
+  // Two rows per thread with per-warp input slices: 0.424 -> 0.412 ms (r04k; with the CTA-wide input ring it was no faster,
+  // r04f/r04g).  SO3D_SE3_QS_LANES=1 selects the one-row kernel (cross-kernel parity test).
   const char* lanes_env = getenv("SO3D_SE3_QS_LANES");
-  if (lanes_env && atoi(lanes_env) == 2) {
+  if (!(lanes_env && atoi(lanes_env) == 1)) {
     SE3QSample2Op op2;
     fill(op2);
     return launch_rowwise_w2(op2, n, stream, "so3d_se3_q_sample_f32");

@@ -614,8 +614,7 @@ def test_two_row_reverse_step_rows_equals_one_row(dx, cuda_device, monkeypatch):
 
 
 def test_two_row_se3_noising_equals_one_row(dx, cuda_device, monkeypatch):
-    """SE(3) noising: the two-row kernel (SO3D_SE3_QS_LANES=2; measured no faster, so not the default) and the one-row kernel
-    give the same bits."""
+    """SE(3) noising: the two-row kernel (default) and the one-row kernel (SO3D_SE3_QS_LANES=1) give the same bits."""
     p = dx.SO3Diffusion(None).to(cuda_device)
     fwd, _, _ = p.tables()
     fg, _ = p.guides()
