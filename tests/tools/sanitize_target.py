@@ -2,7 +2,8 @@
 initcheck):  compute-sanitizer --tool racecheck python tests/tools/sanitize_target.py
 
 Ragged and unaligned sizes (both engine schedules, TMA path and the cooperative fallback), the warp-autonomous
-schedule's mbarrier / acq_rel stage recycling (q_sample, per-row-t reverse step, per-row sampler, SE(3) noising), the
+schedule's mbarrier / acq_rel stage recycling (per-row sampler, the one-row fallbacks) and the two-row kernels' per-warp
+input slices (q_sample, per-row-t reverse step, SE(3) noising), the
 shared-t kernels with the CDF row staged in shared memory, the tcgen05 / TMEM denoiser step and its multi-step loop,
 the all-pairs MMD kernel, the table builders.  Sizes are tiny: the tools slow kernels down 10-100x."""
 import os
@@ -42,6 +43,8 @@ for n in (sizes if want("rows") else []):
         ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fg, want_noise=True, want_score=True)
         ops.p_sample_fused(R, v, t1, *sched, post_cdf=post, seed=1, rng_offset=2)
         ops.p_sample_fused(R, v, tt, *sched, post_cdf=post, seed=1, rng_offset=2, post_guide=pg, want_x0_hat=True)
+        ops.p_sample_fused(R, v, tt, *sched, post_cdf=post, seed=1, rng_offset=2, post_guide=pg)   # two rows per thread, per-warp input slices
+        ops.q_sample_fused(R, tt, proc.sqrt_alphas_cumprod, proc.sqrt_one_minus_alphas_cumprod, fwd, seed=1, rng_offset=1, guide=fg, want_score=True)
         ops.igso3_sample(fwd, (n,), row=3, seed=1, rng_offset=3)
         ops.igso3_sample(fwd, (n,), row_idx=tt, seed=1, rng_offset=3, guide=fg)
         sig = (0.5 * proc.posterior_log_variance_clipped).exp().contiguous()
