@@ -1,6 +1,7 @@
 // so3d_cdf_smem.cuh -- the CDF row of one timestep staged in shared memory (shared-t fast paths of the sampler and
 // of the reverse step, distributions.py:33-51 with a scalar eps): grid locations, the row's trapezoid CDF and a
-// 1024-bucket guide built by the CTA, so that an inverse-CDF lookup costs ~1 probe instead of a 10-step search.
+// float-format guide (so3d_math.cuh: sg_bucket) built by the CTA, so that an inverse-CDF lookup costs ~1 probe instead of a
+// 10-step search.
 #pragma once
 
 #include "so3d_math.cuh"
@@ -20,8 +21,8 @@ __device__ __forceinline__ void stage_cdf(float* tab, const float* __restrict__ 
   __syncthreads();
   if (cdf_row) {
     uint16_t* guide = reinterpret_cast<uint16_t*>(tab + kTabGuide);
-    for (int k = threadIdx.x; k <= kGuide; k += blockDim.x)
-      guide[k] = (uint16_t)cdf_count_le(tab + kTabTrap, (float)k * (1.0f / (float)kGuide), 0, kCdf);
+    for (int k = threadIdx.x; k <= kSgBuckets; k += blockDim.x)
+      guide[k] = (uint16_t)cdf_count_le(tab + kTabTrap, sg_edge(k), 0, kCdf);
   }
 }
 __device__ __forceinline__ float shared_row_angle(const float* tab, float u) {

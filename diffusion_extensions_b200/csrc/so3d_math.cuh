@@ -1174,7 +1174,7 @@ SO3D_HD float igso3_angle_from_uniform(const float* trap, const float* loc, floa
 // Guide of a CDF row: guide[k] = #{j : trap[j] <= k / kGuide}, k = 0..kGuide.  k / 1024 and u * 1024 are exact in
 // fp32, so for u in [k/1024, (k+1)/1024) the count lies in [guide[k], guide[k+1]] and a search restricted to that
 // range returns exactly the index of the full binary search, in ~1 probe instead of 10.
-//   * shared-row kernels keep the guide as uint16 counts next to the row in shared memory (uniform buckets);
+//   * shared-row kernels keep the guide as uint16 counts next to the row in shared memory (sg_bucket / sg_edge below);
 //   * per-row lookups through L2 use 16-byte RECORDS, one per bucket: {lo | hi << 16, trap[lo-1], trap[lo],
 //     trap[lo+1]} (indices clamped to [0, 998]).  When the bucket holds at most one grid point (hi - lo <= 1, the
 //     common case) ONE 16-byte load resolves the lookup: the count is lo + (trap[lo] <= u) and both CDF values of
@@ -1190,7 +1190,18 @@ SO3D_HD float igso3_angle_from_uniform(const float* trap, const float* loc, floa
 //     the search path; 2051 records = 32.8 KB per row.  Every bucket edge and 1 - u (u >= 1/2) are exact in fp32, so
 //     the bracket [lo, hi] of a record is exact for every u that maps to it.
 constexpr int kGuide = 1024;
-constexpr int kGuideStride = kGuide + 2;  // uint16 entries per shared-memory guide (1025 used; even)
+// Shared-memory guide (shared-row kernels): uint16 counts at kSgBuckets + 1 increasing edges of u, bucket b = [edge b,
+// edge b + 1].  The same float-format idea within the shared-memory budget of the two-row reverse step (7 resident CTAs):
+// 64 buckets per octave of u and of 1 - u on [2^-10, 2^-2), 1/512 steps on [1/4, 3/4) -- 1282 buckets instead of 1024
+// uniform ones (+516 B), and the rows that need a search drop from 2.7 % to 0.2 % (posterior tables; forward 5.1 % -> 0.9 %).
+constexpr int kSgOctLo = 10, kSgOctHi = 2, kSgMant = 6, kSgMid = 512;
+constexpr int kSgLog = (kSgOctLo - kSgOctHi) << kSgMant;                // 512 log buckets per tail
+constexpr int kSgBias = (127 - kSgOctLo) << kSgMant;                    // float bits >> 17 of 2^-10
+constexpr int kSgMid0 = kSgMid >> kSgOctHi, kSgMid1 = kSgMid - kSgMid0;  // 128 .. 384
+constexpr int kSgMidBase = 1 + kSgLog;                                  // 513: first middle bucket
+constexpr int kSgUpBase = kSgMidBase + (kSgMid1 - kSgMid0);             // 769: first bucket of the upper tail
+constexpr int kSgBuckets = kSgUpBase + 1 + kSgLog;                      // 1282
+constexpr int kGuideStride = kSgBuckets + 2;  // uint16 entries per shared-memory guide (kSgBuckets + 1 used; even)
 constexpr int kGuideRecWords = 4;         // 32-bit words per record of the global guide
 constexpr int kRecOctLo = 13, kRecOctHi = 3, kRecMant = 6;                        // log part: [2^-13, 2^-3), 2^6 buckets per octave
 constexpr int kRecLog = (kRecOctLo - kRecOctHi) << kRecMant;                      // 640 log buckets per tail
@@ -1200,9 +1211,46 @@ constexpr int kRecMidBase = 1 + kRecLog;                                        
 constexpr int kRecUpBase = kRecMidBase + (kRecMid1 - kRecMid0 + 1);               // first record of the upper tail
 constexpr int kGuideRecs = kRecUpBase + 1 + kRecLog;                              // 2051 records per row
 
+SO3D_HD float sg_uint_as_float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, sizeof f);
+  return f;
+#endif
+}
+SO3D_HD uint32_t sg_float_as_uint(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t b;
+  memcpy(&b, &f, sizeof b);
+  return b;
+#endif
+}
+SO3D_HD float sg_log_edge(int j) { return sg_uint_as_float((uint32_t)(j + kSgBias) << (23 - kSgMant)); }  // j = 0 .. kSgLog (2^-2)
+// edge idx = 0 .. kSgBuckets of the shared-memory guide (non-decreasing in idx; all exact in fp32)
+SO3D_HD float sg_edge(int idx) {
+  if (idx <= 0) return 0.f;
+  if (idx <= kSgMidBase) return sg_log_edge(idx - 1);
+  if (idx <= kSgUpBase) return (float)(kSgMid0 + idx - kSgMidBase) * (1.0f / (float)kSgMid);
+  if (idx < kSgBuckets) return 1.0f - sg_log_edge(kSgBuckets - idx - 1);
+  return 1.0f;
+}
+// bucket of u: sg_edge(b) <= u <= sg_edge(b + 1) for every u in [0, 1) (any other float maps to some valid bucket)
+SO3D_HD int sg_bucket(float u) {
+  const bool upper = u >= 0.75f;
+  const float v = upper ? 1.0f - u : u;  // exact for u >= 1/2
+  int kl = (int)(sg_float_as_uint(v) >> (23 - kSgMant)) - (kSgBias - 1);
+  kl = kl < 0 ? 0 : (kl > kSgLog ? kSgLog : kl);
+  int b = (int)(u * (float)kSgMid) + (kSgMidBase - kSgMid0);
+  b = (u < 0.25f) ? kl : (upper ? (kSgBuckets - 1) - kl : b);
+  return b < 0 ? 0 : (b > kSgBuckets - 1 ? kSgBuckets - 1 : b);
+}
+
 SO3D_HD float igso3_angle_from_uniform_guided(const float* trap, const float* loc, const uint16_t* guide, float u) {
-  int k = (int)(u * (float)kGuide);
-  k = k < 0 ? 0 : (k > kGuide - 1 ? kGuide - 1 : k);
+  const int k = sg_bucket(u);
   const int lo = (u >= 0.f) ? (int)guide[k] : 0;
   const int hi = (u < 1.0f) ? (int)guide[k + 1] : kCdf;
   return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, lo, hi));

@@ -79,6 +79,19 @@ void hm_angle_from_record(const float* trap, const float* loc, const float* u, f
     ang[i] = igso3_angle_from_record(trap, loc, rec, u[i]);
   }
 }
+// inverse CDF through the shared-memory guide (uint16 counts at sg_edge(0 .. kSgBuckets), built here like stage_cdf does);
+// one_probe[i] = 1 when the bucket of u[i] holds at most one grid point
+void hm_angle_from_smem_guide(const float* trap, const float* loc, const float* u, float* ang, int* bucket, int* one_probe, long n) {
+  static unsigned short guide[kGuideStride];
+  for (int k = 0; k <= kSgBuckets; ++k) guide[k] = (unsigned short)cdf_count_le(trap, sg_edge(k), 0, kCdf);
+  for (long i = 0; i < n; ++i) {
+    ang[i] = igso3_angle_from_uniform_guided(trap, loc, guide, u[i]);
+    bucket[i] = sg_bucket(u[i]);
+    one_probe[i] = (guide[bucket[i] + 1] - guide[bucket[i]] <= 1) ? 1 : 0;
+  }
+}
+void hm_sg_edges(float* e) { for (int k = 0; k <= kSgBuckets; ++k) e[k] = sg_edge(k); }
+int hm_sg_buckets() { return kSgBuckets; }
 // record index of every u, the [a, b] range its record serves, and whether one record resolves the lookup
 void hm_guide_bucket(const float* trap, const float* u, int* k, float* a, float* b, int* one_load, long n) {
   for (long i = 0; i < n; ++i) {

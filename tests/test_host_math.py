@@ -306,6 +306,23 @@ def test_inverse_cdf_guide_records(hm, golden):
         assert np.all(np.diff(ks[us <= 0.875]) >= 0) and np.all(np.diff(ks[us > 0.875]) <= 0)   # the upper tail counts down from 1
         assert ks[us <= 0.875].max() < ks[us > 0.875].min()
         assert one[:20000].mean() > 0.985   # (uniform 1/1024 buckets: 0.93-0.95)
+        # the shared-memory guide of the shared-row kernels (uint16 counts at sg_edge): same index as the full search, every u
+        # inside its bucket's edges, edges non-decreasing
+        nb = hm.hm_sg_buckets()
+        assert nb == 1282
+        edges_sg = np.empty(nb + 1, np.float32)
+        hm.hm_sg_edges(fp(edges_sg))
+        assert edges_sg[0] == 0 and edges_sg[-1] == 1 and np.all(np.diff(edges_sg) >= 0)
+        us = np.ascontiguousarray(np.concatenate([u, edges_sg[:-1], np.nextafter(edges_sg[1:], np.float32(0))]).astype(np.float32))
+        us = np.ascontiguousarray(us[(us >= 0) & (us < 1)])
+        a2 = np.empty(us.shape[0], np.float32); c2 = np.empty(us.shape[0], np.float32)
+        bk = np.empty(us.shape[0], np.int32); op1 = np.empty(us.shape[0], np.int32)
+        hm.hm_angle_from_uniform(fp(trap), fp(loc), fp(us), fp(a2), ctypes.c_long(us.shape[0]))
+        hm.hm_angle_from_smem_guide(fp(trap), fp(loc), fp(us), fp(c2), ip(bk), ip(op1), ctypes.c_long(us.shape[0]))
+        assert np.array_equal(a2, c2)
+        assert bk.min() >= 0 and bk.max() < nb
+        assert np.all(edges_sg[bk] <= us) and np.all(us <= edges_sg[bk + 1])
+        assert op1[:20000].mean() > 0.97   # (1024 uniform buckets: 0.93-0.95)
     # out-of-range and non-finite inputs land on a valid record (and take the full search)
     bad = f32([-1.0, -0.0, 1.0, 2.0, 1e30, -1e30, np.inf, -np.inf, np.nan])
     kk = np.empty(bad.shape[0], np.int32); lo = np.empty_like(bad); hi = np.empty_like(bad); one = np.empty(bad.shape[0], np.int32)
