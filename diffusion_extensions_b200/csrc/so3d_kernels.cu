@@ -845,10 +845,9 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
   // soon as its rows are in registers -- no ring, no release counter, no coupling between the warps of a CTA, and 12 KB
   // less shared memory.  Otherwise (two stages): CTA-wide loads into a ring, the last warp out refills the stage.
   constexpr bool kWarpIn = Lay::kInStages == 1;
-  static_assert(Lay::kOutStages == 1, "rowwise_kernel_w2: one output stage");
   float* smem = reinterpret_cast<float*>(smem4);
   float* s_out = smem + Lay::kInStages * Lay::kInFloats;
-  float* s_tab = s_out + Lay::kOutFloats;
+  float* s_tab = s_out + Lay::kOutStages * Lay::kOutFloats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + Lay::kTabFloats);  // kWarpIn: one per warp;  else two + the release counters
   uint32_t* released = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -922,7 +921,7 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
     wrows = wrows < 0 ? 0 : (wrows > 64 ? 64 : wrows);
     float* s_i9 = smem + st * Lay::kInFloats;
     float* s_i3 = s_i9 + kI9 * kRows2 * 9;
-    float* s_o9 = s_out;
+    float* s_o9 = s_out + (Lay::kOutStages == 2 ? (k & 1) : 0) * Lay::kOutFloats;
     float* s_o3 = s_o9 + kO9 * kRows2 * 9;
     if (kI9 + kI3 > 0) {
       if (tma) {
@@ -976,7 +975,8 @@ __global__ void __launch_bounds__(kT2, OpMinCtas<Op>::value) rowwise_kernel_w2(c
       p1_next[0] = p1_next2[0], p1_next[1] = p1_next2[1];
     }
     if (kO9 + kO3 > 0) {
-      bulk_wait_read<0>();  // every lane (see rowwise_kernel): the warp's earlier stores have finished reading the slice
+      // every lane (see rowwise_kernel): the warp's earlier stores have finished reading the slice that is written next
+      if (Lay::kOutStages == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -1049,6 +1049,62 @@ int launch_rowwise_w2(const Op& op, int64_t n, void* stream, const char* name) {
   const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
   kern<<<(int)(tiles < cap ? tiles : cap), kT2, smem, (cudaStream_t)stream>>>(op, n, use_tma);
   return check_launch(name);
+}
+
+// Any one-row op without prefetch hooks on the two-row warp-autonomous engine: the op's row() runs once per row (no packing),
+// but the engine work is paid per 64 rows, every warp streams its own slices and there is no CTA barrier in the tile loop.
+// Measured at 2^24 rows (profiles/r04r_probe.jsonl, r04s_probe.jsonl; fraction of the HBM peak, one-row -> two-row): ops with
+// SMALL outputs gain -- closed-form score 0.85 -> 0.95 (LogpScore2Op, the same construction), log_vec 0.93 -> 0.99, rmat_dist
+// 0.97 -> 0.99 -- while ops that write a matrix per row lose, with one or two output stages alike: log_rmat 0.92 -> 0.89,
+// exp_vec 0.83 -> 0.79, so3_scale 0.87 -> 0.85, compose 0.98 -> 0.96, shared-row sampler 0.65 -> 0.60 (a warp's 2304-byte
+// bulk stores against the CTA-synchronous kernel's 9216-byte ones).  So the choice is per call site (`prefer_two`);
+// SO3D_ROW_LANES=1 / 2 forces one kernel for every op (cross-kernel parity test, A/B runs).
+#ifndef SO3D_TWOROW_MINCTAS
+#define SO3D_TWOROW_MINCTAS 6
+#endif
+#ifndef SO3D_TWOROW_OUTSTAGES
+#define SO3D_TWOROW_OUTSTAGES 2
+#endif
+template <class Op>
+struct TwoRow : Op {
+  struct Pre1 {};
+  struct Pre2 {};
+  static constexpr int kOutStages = SO3D_TWOROW_OUTSTAGES;
+  static constexpr int kInStages = 1;
+  static constexpr int kMinCtas = SO3D_TWOROW_MINCTAS;
+  int64_t n_rows;  // a row beyond the end must not run (ops read / write per-row scalars by index)
+  __device__ Pre1 prefetch1(int64_t) const { return Pre1{}; }
+  __device__ Pre2 prefetch2(int64_t, const Pre1&) const { return Pre2{}; }
+  __device__ void row2(int64_t i0, const Pre2 (&)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
+    constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int64_t i = i0 + 32 * j;
+      if (i < n_rows) {
+        Mat3 A9[kI9 > 0 ? kI9 : 1], O9[kO9 > 0 ? kO9 : 1];
+        Vec3 A3[kI3 > 0 ? kI3 : 1], O3[kO3 > 0 ? kO3 : 1];
+#pragma unroll
+        for (int a = 0; a < kI9; ++a) A9[a] = a9[a][j];
+#pragma unroll
+        for (int a = 0; a < kI3; ++a) A3[a] = a3[a][j];
+        Op::row(i, A9, A3, O9, O3, tab);
+#pragma unroll
+        for (int a = 0; a < kO9; ++a) o9[a][j] = O9[a];
+#pragma unroll
+        for (int a = 0; a < kO3; ++a) o3[a][j] = O3[a];
+      }
+    }
+  }
+};
+template <class Op>
+int launch_rowwise_pick(const Op& op, int64_t n, void* stream, const char* name, bool prefer_two = false) {
+  const char* lanes_env = getenv("SO3D_ROW_LANES");  // 1 / 2 force the one-row / two-row kernel for every op
+  const int forced = lanes_env ? atoi(lanes_env) : 0;
+  if (forced == 1 || (forced != 2 && !prefer_two)) return launch_rowwise(op, n, stream, name);
+  TwoRow<Op> op2;
+  static_cast<Op&>(op2) = op;
+  op2.n_rows = n;
+  return launch_rowwise_w2(op2, n, stream, name);
 }
 
 // dummy arrays for ops without a given kind of operand (zero-length arrays are not allowed)
@@ -1273,6 +1329,38 @@ struct LogpScoreOp : LogpPre<SO3D_LOGP_PREFETCH && (kMode == kClosed || kMode ==
   __device__ P2 prefetch2(int64_t i, const P1&) const { return P2{eps[i * eps_stride]}; }
   template <class P2>
   __device__ void row(int64_t i, const P2& p, const Mat3* a9, const Vec3*, Mat3*, Vec3* o3, const float*) const { row_eps(i, p.eps, a9, o3); }
+};
+// The closed-form / auto evaluators on two rows per thread with per-warp input slices (rowwise_kernel_w2): the engine's
+// per-tile work is a third of this light kernel's issue slots and is paid per 64 rows; the axis-angle extraction runs packed
+// (axis_angle_fast_l, the same bits), the evaluator itself once per row.  SO3D_LOGP_LANES=1 selects the one-row kernel.
+#ifndef SO3D_LOGP2_MINCTAS
+#define SO3D_LOGP2_MINCTAS 8
+#endif
+#ifndef SO3D_LOGP2_OUTSTAGES
+#define SO3D_LOGP2_OUTSTAGES 1
+#endif
+template <int kMode>
+struct LogpScore2Op : LogpScoreOp<kMode> {
+  static_assert(kMode == kClosed || kMode == kAuto, "two-row form: HBM-bound evaluators only");
+  using Pre2 = typename LogpPre<true>::Pre2;
+  static constexpr int kOutStages = SO3D_LOGP2_OUTSTAGES;
+  static constexpr int kInStages = 1;
+  static constexpr int kMinCtas = SO3D_LOGP2_MINCTAS;
+  int64_t n;  // rows beyond the end of a ragged tile must not touch logp / dlogf
+  __device__ void row2(int64_t i0, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*)[2], Mat3 (*)[2], Vec3 (*o3)[2], const float*) const {
+    const AxisAngleL<L2> a = axis_angle_fast_l(lanes_of(a9[0][0], a9[0][1]));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int64_t i = i0 + 32 * j;
+      float lf, g;
+      igso3_logf_g_t<kMode>(j ? a.theta.y : a.theta.x, p[j].eps, this->L, &lf, &g);
+      if (i < n) {
+        this->logp[i] = lf;
+        if (this->dlogf) this->dlogf[i] = g;
+      }
+      o3[0][j] = j ? Vec3{g * a.axis.x.y, g * a.axis.y.y, g * a.axis.z.y} : Vec3{g * a.axis.x.x, g * a.axis.y.x, g * a.axis.z.x};
+    }
+  }
 };
 struct LogpBwdOp {
   SO3D_OP_ARRAYS(1, 0, 1, 0)
@@ -2224,35 +2312,35 @@ int so3d_log_f32(const float* R, float* out9, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (R && out9), "so3d_log_f32: null pointer");
   LogOp op;
   op.in9[0] = R; op.out9[0] = out9;
-  return launch_rowwise(op, n, stream, "so3d_log_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_log_f32");
 }
 
 int so3d_logvec_f32(const float* R, float* out3, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (R && out3), "so3d_logvec_f32: null pointer");
   LogVecOp op;
   op.in9[0] = R; op.out3[0] = out3;
-  return launch_rowwise(op, n, stream, "so3d_logvec_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_logvec_f32", true);
 }
 
 int so3d_rmat_to_aa_f32(const float* R, float* axis3, float* angle, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (R && axis3 && angle), "so3d_rmat_to_aa_f32: null pointer");
   RmatToAaOp op;
   op.in9[0] = R; op.out3[0] = axis3; op.angle = angle;
-  return launch_rowwise(op, n, stream, "so3d_rmat_to_aa_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_rmat_to_aa_f32");
 }
 
 int so3d_aa_to_rmat_f32(const float* axis3, const float* angle, float* R, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (axis3 && angle && R), "so3d_aa_to_rmat_f32: null pointer");
   AaToRmatOp op;
   op.in3[0] = axis3; op.angle = angle; op.out9[0] = R;
-  return launch_rowwise(op, n, stream, "so3d_aa_to_rmat_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_aa_to_rmat_f32");
 }
 
 int so3d_expvec_f32(const float* v3, float* R, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (v3 && R), "so3d_expvec_f32: null pointer");
   ExpVecOp op;
   op.in3[0] = v3; op.out9[0] = R;
-  return launch_rowwise(op, n, stream, "so3d_expvec_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_expvec_f32");
 }
 
 int so3d_scale_f32(const float* R, const float* s, int s_stride, float* out, int64_t n, void* stream) {
@@ -2260,14 +2348,14 @@ int so3d_scale_f32(const float* R, const float* s, int s_stride, float* out, int
   SO3D_REQUIRE(s_stride == 0 || s_stride == 1, "so3d_scale_f32: s_stride must be 0 or 1");
   ScaleOp op;
   op.in9[0] = R; op.s = s; op.s_stride = s_stride; op.out9[0] = out;
-  return launch_rowwise(op, n, stream, "so3d_scale_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_scale_f32");
 }
 
 int so3d_quat_to_rmat_f32(const float* q4, float* R, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (q4 && R), "so3d_quat_to_rmat_f32: null pointer");
   QuatToRmatOp op;
   op.q = q4; op.q_vec = aligned16(q4); op.out9[0] = R;
-  return launch_rowwise(op, n, stream, "so3d_quat_to_rmat_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_quat_to_rmat_f32");
 }
 
 int so3d_rmat_to_quat_f32(const float* R, float* q4, int64_t n, void* stream) {
@@ -2275,7 +2363,7 @@ int so3d_rmat_to_quat_f32(const float* R, float* q4, int64_t n, void* stream) {
   SO3D_REQUIRE(aligned16(q4), "so3d_rmat_to_quat_f32: q4 must be 16-byte aligned");
   RmatToQuatOp op;
   op.in9[0] = R; op.q = q4;
-  return launch_rowwise(op, n, stream, "so3d_rmat_to_quat_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_rmat_to_quat_f32");
 }
 
 }  // extern "C"
@@ -2285,15 +2373,15 @@ static int compose_dispatch(const float* A, int a_stride, const float* B, int b_
   if (a_stride && b_stride) {
     ComposeOp<TA, TB> op;
     op.in9[0] = A; op.in9[1] = B; op.out9[0] = C;
-    return launch_rowwise(op, n, stream, "so3d_compose_f32");
+    return launch_rowwise_pick(op, n, stream, "so3d_compose_f32");
   } else if (!a_stride && b_stride) {
     ComposeSharedOp<TA, TB, true> op;
     op.in9[0] = B; op.shared = A; op.out9[0] = C;
-    return launch_rowwise(op, n, stream, "so3d_compose_f32");
+    return launch_rowwise_pick(op, n, stream, "so3d_compose_f32");
   } else if (a_stride && !b_stride) {
     ComposeSharedOp<TA, TB, false> op;
     op.in9[0] = A; op.shared = B; op.out9[0] = C;
-    return launch_rowwise(op, n, stream, "so3d_compose_f32");
+    return launch_rowwise_pick(op, n, stream, "so3d_compose_f32");
   }
   return fail(SO3D_EINVAL, "so3d_compose_f32: at most one operand may be shared");
 }
@@ -2313,7 +2401,7 @@ int so3d_rmat_dist_f32(const float* A, const float* B, float* out, int64_t n, vo
   SO3D_REQUIRE(n == 0 || (A && B && out), "so3d_rmat_dist_f32: null pointer");
   RmatDistOp op;
   op.in9[0] = A; op.in9[1] = B; op.out = out;
-  return launch_rowwise(op, n, stream, "so3d_rmat_dist_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_rmat_dist_f32", true);
 }
 
 int so3d_lerp_f32(const float* A, const float* B, const float* w, int w_stride, float* out, int64_t n, void* stream) {
@@ -2321,14 +2409,14 @@ int so3d_lerp_f32(const float* A, const float* B, const float* w, int w_stride, 
   SO3D_REQUIRE(w_stride == 0 || w_stride == 1, "so3d_lerp_f32: w_stride must be 0 or 1");
   LerpOp op;
   op.in9[0] = A; op.in9[1] = B; op.w = w; op.w_stride = w_stride; op.out9[0] = out;
-  return launch_rowwise(op, n, stream, "so3d_lerp_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_lerp_f32");
 }
 
 int so3d_log_bwd_f32(const float* R, const float* G9, float* gR, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (R && G9 && gR), "so3d_log_bwd_f32: null pointer");
   LogBwdOp op;
   op.in9[0] = R; op.in9[1] = G9; op.out9[0] = gR;
-  return launch_rowwise(op, n, stream, "so3d_log_bwd_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_log_bwd_f32");
 }
 
 int so3d_aa_to_rmat_bwd_f32(const float* axis3, const float* angle, const float* G9, float* g_axis3, float* g_angle,
@@ -2336,14 +2424,14 @@ int so3d_aa_to_rmat_bwd_f32(const float* axis3, const float* angle, const float*
   SO3D_REQUIRE(n == 0 || (axis3 && angle && G9 && g_axis3 && g_angle), "so3d_aa_to_rmat_bwd_f32: null pointer");
   AaToRmatBwdOp op;
   op.in9[0] = G9; op.in3[0] = axis3; op.angle = angle; op.out3[0] = g_axis3; op.g_angle = g_angle;
-  return launch_rowwise(op, n, stream, "so3d_aa_to_rmat_bwd_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_aa_to_rmat_bwd_f32");
 }
 
 int so3d_expvec_bwd_f32(const float* v3, const float* G9, float* g_v3, int64_t n, void* stream) {
   SO3D_REQUIRE(n == 0 || (v3 && G9 && g_v3), "so3d_expvec_bwd_f32: null pointer");
   ExpVecBwdOp op;
   op.in9[0] = G9; op.in3[0] = v3; op.out3[0] = g_v3;
-  return launch_rowwise(op, n, stream, "so3d_expvec_bwd_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_expvec_bwd_f32");
 }
 
 int so3d_scale_bwd_f32(const float* R, const float* s, int s_stride, const float* G9, float* gR, float* g_s, int64_t n,
@@ -2352,7 +2440,7 @@ int so3d_scale_bwd_f32(const float* R, const float* s, int s_stride, const float
   SO3D_REQUIRE(s_stride == 0 || s_stride == 1, "so3d_scale_bwd_f32: s_stride must be 0 or 1");
   ScaleBwdOp op;
   op.in9[0] = R; op.in9[1] = G9; op.s = s; op.s_stride = s_stride; op.g_s = g_s; op.out9[0] = gR;
-  return launch_rowwise(op, n, stream, "so3d_scale_bwd_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_scale_bwd_f32");
 }
 
 }  // extern "C"
@@ -2360,6 +2448,17 @@ int so3d_scale_bwd_f32(const float* R, const float* s, int s_stride, const float
 template <int kMode>
 static int launch_logp_score(const float* R, const float* eps, int eps_stride, float* logp, float* score3, float* dlogf, int64_t n, int L,
                              void* stream) {
+#if SO3D_LOGP_PREFETCH
+  if constexpr (kMode == kClosed || kMode == kAuto) {
+    const char* lanes_env = getenv("SO3D_LOGP_LANES");
+    if (!(lanes_env && atoi(lanes_env) == 1)) {
+      LogpScore2Op<kMode> op2;
+      op2.in9[0] = R; op2.eps = eps; op2.eps_stride = eps_stride; op2.logp = logp; op2.dlogf = dlogf; op2.out3[0] = score3;
+      op2.L = L; op2.n = n;
+      return launch_rowwise_w2(op2, n, stream, "so3d_igso3_logp_score_f32");
+    }
+  }
+#endif
   LogpScoreOp<kMode> op;
   op.in9[0] = R; op.eps = eps; op.eps_stride = eps_stride; op.logp = logp; op.dlogf = dlogf; op.out3[0] = score3;
   op.L = L;
@@ -2424,7 +2523,7 @@ int so3d_igso3_logp_bwd_f32(const float* R, const float* dlogf, const float* gou
   SO3D_REQUIRE(n == 0 || (R && dlogf && gout && gR), "so3d_igso3_logp_bwd_f32: null pointer");
   LogpBwdOp op;
   op.in9[0] = R; op.dlogf = dlogf; op.gout = gout; op.out9[0] = gR;
-  return launch_rowwise(op, n, stream, "so3d_igso3_logp_bwd_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_igso3_logp_bwd_f32");
 }
 
 int so3d_igso3_cdf_table_f32(const float* eps, int64_t rows, const float* grid_loc, const float* haar_w, float* trap_out,
@@ -2447,7 +2546,7 @@ static int launch_sample(const float* cdf, const uint32_t* guide, const float* l
   op.out9[0] = R; op.out3[0] = axis3;
   op.cdf = cdf; op.guide = guide; op.loc = loc; op.row_idx = row_idx; op.shared_row = row; op.rows = rows; op.u_in = u; op.axes_in = axes3;
   op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset; op.mean = mean; op.mean_stride = mean_stride; op.angle_out = angle;
-  return launch_rowwise(op, n, stream, "so3d_igso3_sample_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_igso3_sample_f32");
 }
 
 template <bool kExtra, bool kDevSeed = false, bool kNoiseOut = kExtra>
@@ -2575,7 +2674,7 @@ int so3d_q_sample_given_f32(const float* x0, const int64_t* t, const float* sqrt
   SO3D_REQUIRE(T > 0, "so3d_q_sample_given_f32: T must be positive");
   QSampleGivenOp op;
   op.in9[0] = x0; op.in9[1] = noise; op.out9[0] = x_t; op.t = t; op.sqrt_ac = sqrt_ac; op.T = T;
-  return launch_rowwise(op, n, stream, "so3d_q_sample_given_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_q_sample_given_f32");
 }
 
 int so3d_bingham_sample_f32(const float* scale_tril16, const float* z4, uint64_t seed, uint64_t rng_offset, uint64_t row_offset,
@@ -2587,7 +2686,7 @@ int so3d_bingham_sample_f32(const float* scale_tril16, const float* z4, uint64_t
   BinghamOp op;
   op.out9[0] = R; op.tril = scale_tril16; op.z_in = z4; op.z_vec = aligned16(z4); op.q_out = q4;
   op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
-  return launch_rowwise(op, n, stream, "so3d_bingham_sample_f32");
+  return launch_rowwise_pick(op, n, stream, "so3d_bingham_sample_f32");
 }
 
 int so3d_igso3_cdf_guide(const float* cdf, int64_t rows, uint32_t* guide_out, void* stream) {

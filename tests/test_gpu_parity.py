@@ -532,6 +532,99 @@ def test_fused_q_sample_consistency(dx, cuda_device):
     assert ks < 2.5 / math.sqrt(ang.size)
 
 
+def test_two_row_engine_equals_one_row_for_the_maps(dx, cuda_device, monkeypatch):
+    """Every map / backward / sampler op can run on the two-row warp-autonomous engine (one row() call per row, the engine's
+    work per 64 rows; the default where it measured faster: log_vec, rmat_dist, closed-form score).  SO3D_ROW_LANES=1 / 2 force
+    the one-row / two-row kernel for every op, and both must give the same bits: ragged and single-row sizes, aligned and
+    unaligned inputs, per-row and broadcast scalars."""
+    ops = dx.ops
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    fwd, _, _ = p.tables()
+    fg, _ = p.guides()
+    g = torch.Generator(device=cuda_device); g.manual_seed(81)
+
+    def flat(o):
+        if isinstance(o, dict):
+            return [v for v in o.values() if v is not None]
+        if isinstance(o, (tuple, list)):
+            return [v for v in o if v is not None]
+        return [o]
+
+    for n in (1, 31, 64, 255, 257, 4099, 256 * 148 * 6 + 13):
+        buf = torch.empty(n * 9 + 1, device=cuda_device)
+        R = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+        R2 = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+        Ru = buf[1:].view(n, 3, 3); Ru.copy_(R)
+        v = torch.randn(n, 3, device=cuda_device, generator=g) * 0.7
+        G = torch.randn(n, 3, 3, device=cuda_device, generator=g)
+        sc = torch.rand(n, device=cuda_device, generator=g) + 0.5
+        q = torch.randn(n, 4, device=cuda_device, generator=g)
+        tt = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+        ang = torch.rand(n, device=cuda_device, generator=g) * 3
+        cases = {
+            "log_rmat": lambda: ops.log_rmat(R), "log_rmat_unaligned": lambda: ops.log_rmat(Ru), "log_vec": lambda: ops.log_vec(R),
+            "rmat_to_aa": lambda: ops.rmat_to_aa(R), "aa_to_rmat": lambda: ops.aa_to_rmat(v, ang), "exp_vec": lambda: ops.exp_vec(v),
+            "so3_scale": lambda: ops.so3_scale(R, sc), "so3_scale_bcast": lambda: ops.so3_scale(R, sc[:1]), "quat_to_rmat": lambda: ops.quat_to_rmat(q),
+            "rmat_to_quat": lambda: ops.rmat_to_quat(R), "compose": lambda: ops.compose(R, R2), "compose_tn": lambda: ops.compose(R, R2, trans_a=True),
+            "compose_shared": lambda: ops.compose(R[:1], R2) if n > 1 else ops.compose(R, R2), "rmat_dist": lambda: ops.rmat_dist(R, R2),
+            "so3_lerp": lambda: ops.so3_lerp(R, R2, sc - 0.5), "sample_shared": lambda: ops.igso3_sample(fwd, (n,), row=300, seed=3, rng_offset=1),
+            "sample_rows": lambda: ops.igso3_sample(fwd, (n,), row_idx=tt, seed=3, rng_offset=1, guide=fg, want_angle=True),
+            "q_sample_given": lambda: ops.q_sample_given(R, tt, p.sqrt_alphas_cumprod, R2),
+            "bingham": lambda: ops.bingham_sample(torch.eye(4, device=cuda_device), (n,), seed=2, rng_offset=0, want_rmat=True),
+        }
+        for name, fn in cases.items():
+            res = {}
+            for lanes in ("1", "2"):
+                monkeypatch.setenv("SO3D_ROW_LANES", lanes)
+                res[lanes] = flat(fn())
+            assert len(res["1"]) == len(res["2"]) >= 1
+            for x, y in zip(res["1"], res["2"]):
+                assert torch.equal(x, y), (n, name)
+    # backward passes (autograd functions of util): same gradients
+    n = 3001
+    R = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+    v0 = torch.randn(n, 3, device=cuda_device, generator=g) * 0.7
+    sc0 = torch.rand(n, device=cuda_device, generator=g) + 0.5
+    w = torch.randn(n, 3, 3, device=cuda_device, generator=g)
+    grads = {}
+    for lanes in ("1", "2"):
+        monkeypatch.setenv("SO3D_ROW_LANES", lanes)
+        Rr = R.clone().requires_grad_(True); vv = v0.clone().requires_grad_(True); ss = sc0.clone().requires_grad_(True)
+        loss = (dx.util.log_rmat(Rr) * w).sum() + (dx.util.so3_scale(Rr, ss) * w).sum() + (dx.util.aa_to_rmat(vv, ss[:, None]) * w).sum()
+        loss.backward()
+        grads[lanes] = (Rr.grad.clone(), vv.grad.clone(), ss.grad.clone())
+    for x, y in zip(grads["1"], grads["2"]):
+        assert torch.equal(x, y)
+
+
+def test_two_row_closed_form_score_equals_one_row(dx, cuda_device, monkeypatch):
+    """Closed-form / auto log-density + score: the two-row kernel (default) and the one-row kernel (SO3D_LOGP_LANES=1) give
+    the same bits -- ragged sizes, scalar and per-row eps, with and without the dlogf output, unaligned input (writes beyond n:
+    compute-sanitizer memcheck over tests/tools/sanitize_target.py)."""
+    ops = dx.ops
+    g = torch.Generator(device=cuda_device); g.manual_seed(80)
+    for n in (1, 33, 64, 255, 256, 257, 5000, 256 * 148 * 8 + 45, 400_003):
+        buf = torch.empty(n * 9 + 1, device=cuda_device)
+        R = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+        Ru = buf[1:].view(n, 3, 3); Ru.copy_(R)
+        eps = torch.exp(torch.empty(n, device=cuda_device).uniform_(-5.0, 0.3, generator=g))
+        if n > 40:
+            R[3] = torch.eye(3, device=cuda_device)
+        for mode in ("closed", "auto"):
+            for RR, ee in ((R, eps), (Ru, eps), (R, eps[:1])):
+                res = {}
+                for lanes in ("1", "2"):
+                    monkeypatch.setenv("SO3D_LOGP_LANES", lanes)
+                    out = ops.igso3_logp_score(RR, ee, mode=mode, want_dlogf=(mode == "closed"))
+                    res[lanes] = out
+                a, b = res["1"], res["2"]
+                a = a if isinstance(a, (tuple, list)) else (a,)
+                b = b if isinstance(b, (tuple, list)) else (b,)
+                for x, y in zip(a, b):
+                    if x is not None:
+                        assert torch.equal(x, y), (n, mode)
+
+
 def test_two_row_noising_equals_one_row(dx, cuda_device, monkeypatch):
     """Forward noising runs two rows per thread (packed FP32, warp-autonomous two-row engine) by default; the one-row
     kernel (SO3D_QS_LANES=1) must give the same bits: full and ragged tiles, a single row, the score output, a shard
