@@ -1089,11 +1089,35 @@ static __host__ __device__ __noinline__ void igso3_closed_f32_outofline(float w,
 inline void igso3_closed_f32_outofline(float w, float eps, float* logf_out, float* g_out) { igso3_closed_f32(w, eps, logf_out, g_out); }
 #endif
 
+// auto's series branch (eps > 1: at most 12 live terms) can be compiled out of line (SO3D_AUTO_SERIES_OUTOFLINE=1) so that the
+// HBM-bound kernels that evaluate `auto` do not carry the unrolled series block inline.  Measured (profiles/r04u_probe.jsonl):
+// 20 % fewer instructions in those kernels and SLOWER -- auto score 0.1675 -> 0.175 ms, forward noising with the score
+// 0.3637 -> 0.378 ms (the call's register conventions cost more on the hot path than the inline block's size) -- so it is off.
+#ifndef SO3D_AUTO_SERIES_OUTOFLINE
+#define SO3D_AUTO_SERIES_OUTOFLINE 0
+#endif
+template <int kMode>
+SO3D_HD void igso3_series_branch(float w, float eps, int L, float* logf_out, float* g_out);
+#if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
+static __host__ __device__ __noinline__ void igso3_auto_series_outofline(float w, float eps, int L, float* logf_out, float* g_out);
+#else
+inline void igso3_auto_series_outofline(float w, float eps, int L, float* logf_out, float* g_out);
+#endif
+
 template <int kMode>
 SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g_out) {
   if (kMode == kClosed || (kMode == kAuto && eps <= kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
+  } else if (kMode == kAuto && SO3D_AUTO_SERIES_OUTOFLINE) {
+    igso3_auto_series_outofline(w, eps, L, logf_out, g_out);
   } else {
+    igso3_series_branch<kMode>(w, eps, L, logf_out, g_out);
+  }
+}
+
+template <int kMode>
+SO3D_HD void igso3_series_branch(float w, float eps, int L, float* logf_out, float* g_out) {
+  {
     int terms = L;
     if (kMode == kAuto || kMode == kSeriesAdaptive) {
       terms = igso3_series_live_terms(eps, L);
@@ -1125,6 +1149,13 @@ SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g
     }
   }
 }
+#if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
+static __host__ __device__ __noinline__ void igso3_auto_series_outofline(float w, float eps, int L, float* logf_out, float* g_out) {
+  igso3_series_branch<kAuto>(w, eps, L, logf_out, g_out);
+}
+#else
+inline void igso3_auto_series_outofline(float w, float eps, int L, float* logf_out, float* g_out) { igso3_series_branch<kAuto>(w, eps, L, logf_out, g_out); }
+#endif
 
 // runtime-mode dispatch (host harness, non-critical call sites)
 SO3D_HD void igso3_logf_g(float w, float eps, int mode, int L, float* logf_out, float* g_out) {
