@@ -933,6 +933,21 @@ SO3D_HD SeriesAcc igso3_series_terms(float w, float eps, int L) {
   return SeriesAcc{st.b + st.b2, st.bp + st.bp2};
 }
 
+// terms l = 0 .. L-1 in one rolled loop (igso3_series_run<1>): bit-identical to igso3_series_terms, tiny code
+#ifndef SO3D_AUTO_SERIES_ROLLED
+#define SO3D_AUTO_SERIES_ROLLED 1
+#endif
+SO3D_HD SeriesAcc igso3_series_terms_rolled(float w, float eps, int L) {
+  const float cexp = -(eps * eps) * 1.4426950408889634f;
+  float sh, ch;
+  sincos_f(0.5f * w, &sh, &ch);
+  const float kap = 4.0f * sh * sh, kapp = 4.0f * sh * ch;
+  SeriesState st;
+  st.b = st.d = st.bp = st.dp = st.b2 = st.bp2 = 0.f;
+  igso3_series_run<1>(st, kap, kapp, cexp, L - 1, L);
+  return SeriesAcc{st.b + st.b2, st.bp + st.bp2};
+}
+
 // ------------------------------------------------------------------------------------------------
 // The same series with ONE WARP per rotation (small batches: a one-thread-per-rotation launch of 4096 rows is a single
 // 2000-term dependent chain per thread, ~40 us, with most of the GPU idle).  The backward recurrence is linear in its
@@ -1096,6 +1111,9 @@ inline void igso3_closed_f32_outofline(float w, float eps, float* logf_out, floa
 #ifndef SO3D_AUTO_SERIES_OUTOFLINE
 #define SO3D_AUTO_SERIES_OUTOFLINE 0
 #endif
+#ifndef SO3D_AUTO_CLOSED_FIRST
+#define SO3D_AUTO_CLOSED_FIRST 1
+#endif
 template <int kMode>
 SO3D_HD void igso3_series_branch(float w, float eps, int L, float* logf_out, float* g_out);
 #if defined(__CUDACC__) && !defined(SO3D_HOST_ONLY)
@@ -1106,7 +1124,12 @@ inline void igso3_auto_series_outofline(float w, float eps, int L, float* logf_o
 
 template <int kMode>
 SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g_out) {
-  if (kMode == kClosed || (kMode == kAuto && eps <= kAutoSeriesEps)) {
+  if (kMode == kAuto && SO3D_AUTO_CLOSED_FIRST) {
+    // the closed form unconditionally and straight-line (so that ptxas can interleave it with the neighbouring row's / the
+    // surrounding arithmetic), then the rare rows above eps = 1 are re-evaluated by the series: the same bits as branching first
+    igso3_closed_f32(w, eps, logf_out, g_out);
+    if (!(eps <= kAutoSeriesEps)) igso3_series_branch<kAuto>(w, eps, L, logf_out, g_out);
+  } else if (kMode == kClosed || (kMode == kAuto && eps <= kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
   } else if (kMode == kAuto && SO3D_AUTO_SERIES_OUTOFLINE) {
     igso3_auto_series_outofline(w, eps, L, logf_out, g_out);
@@ -1128,8 +1151,10 @@ SO3D_HD void igso3_series_branch(float w, float eps, int L, float* logf_out, flo
 #endif
 #if SO3D_SERIES_ROUNDUP
       // whole blocks only: the extra terms have weight exactly 0 as well, and the partial-block loop is the slow one
-      const int up = (terms + kSeriesBlock - 1) / kSeriesBlock * kSeriesBlock;
-      terms = up <= L ? up : L;
+      if (!(kMode == kAuto && SO3D_AUTO_SERIES_ROLLED)) {
+        const int up = (terms + kSeriesBlock - 1) / kSeriesBlock * kSeriesBlock;
+        terms = up <= L ? up : L;
+      }
 #endif
     }
     constexpr bool kGuarded = (kMode == kSeries || kMode == kSeriesAdaptive);
@@ -1139,7 +1164,10 @@ SO3D_HD void igso3_series_branch(float w, float eps, int L, float* logf_out, flo
       if (SO3D_SERIES_GUARD_FORM == 3) igso3_closed_f32_outofline(w, eps, &lf_c, &g_c);
       else igso3_closed_f32(w, eps, &lf_c, &g_c);
     }
-    const SeriesAcc a = igso3_series_terms(w, eps, terms);
+    // auto reaches this branch only above eps = 1, where at most 12 terms are live: a rolled loop over exactly those (the same
+    // operations per term as the unrolled blocks, whose extra terms weigh exactly 0: the same bits) keeps the unrolled block out
+    // of the HBM-bound kernels that evaluate `auto`
+    const SeriesAcc a = (kMode == kAuto && SO3D_AUTO_SERIES_ROLLED) ? igso3_series_terms_rolled(w, eps, terms) : igso3_series_terms(w, eps, terms);
     *logf_out = logf(2.0f * a.F);
     *g_out = a.dF / a.F;
     if (kGuarded && guard) {
