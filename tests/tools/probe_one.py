@@ -1,4 +1,4 @@
-"""One op of probe_engine's list, a few launches (for ncu captures):  python tests/tools/probe_one.py q_sample|q_sample_score|p_sample|p_sample_rows|auto|loop [log2_rows]"""
+"""One op of probe_engine's list, a few launches (for ncu captures):  python tests/tools/probe_one.py q_sample|q_sample_score|p_sample|p_sample_rows|auto|closed|loop [log2_rows]"""
 import os
 import sys
 
@@ -27,6 +27,7 @@ fns = {
     "p_sample": lambda: ops.p_sample_fused(R, pred, t_range[500:501], *sched, post_cdf=post, seed=1, rng_offset=1),
     "p_sample_rows": lambda: ops.p_sample_fused(R, pred, tt, *sched, post_cdf=post, seed=1, rng_offset=1, post_guide=post_guide),
     "auto": lambda: ops.igso3_logp_score(R, eps, mode="auto"),
+    "closed": lambda: ops.igso3_logp_score(R, eps, mode="closed"),
     "series_small": lambda: ops.igso3_logp_score(R, eps, mode="series", L=2000),      # n = 2^12: one warp per rotation
     # the one-launch reverse process, 40 steps (an ncu replay of all 1000 would take minutes)
     "loop": lambda: ops.p_sample_loop_fused(R, None, 539, 500, *sched, post, post_guide, seed=1, rng_offset=0),
