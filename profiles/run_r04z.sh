@@ -1,0 +1,18 @@
+#!/bin/bash
+# r04z: final bench line at HEAD (driver's flags) + reference arm + GPU tests + smoke
+mkdir -p gpurun_out
+T=r04z
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log; tail -3 gpurun_out/${T}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -2 gpurun_out/${T}_smoke.log
+timeout 1200 python bench.py --steps 20 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench exit $?"
+timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r04z_bench.json"))
+print("value", d["value"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], "launches", d.get("gpu_launches"))
+for k in ("score_evals_per_sec_auto", "reverse_particle_steps_per_sec", "noised_rotations_per_sec", "noised_rotations_with_score_per_sec"):
+    v = d["extra"][k]; print(k, v.get("value"), v["roofline"]["frac"])
+v = d["extra"]["se3_frames_cfg5"]; print("se3", v["noising_frames_per_sec"]["value"], v["noising_frames_per_sec"]["roofline"]["frac"], v["reverse_frame_steps_per_sec"]["value"], v["reverse_frame_steps_per_sec"]["roofline"]["frac"])
+v = d["extra"]["reverse_loop_1000_steps"]; print("loop", v["seconds"], v["one_launch"]["seconds"])
+r = json.load(open("gpurun_out/r04z_bench_reference.json")); print("reference", r["value"], "e2e ratio", d["e2e"]["value"] / r["value"])
+PY
