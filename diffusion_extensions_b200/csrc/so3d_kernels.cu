@@ -1059,6 +1059,9 @@ int launch_rowwise_w2(const Op& op, int64_t n, void* stream, const char* name) {
 // exp_vec 0.83 -> 0.79, so3_scale 0.87 -> 0.85, compose 0.98 -> 0.96, shared-row sampler 0.65 -> 0.60 (a warp's 2304-byte
 // bulk stores against the CTA-synchronous kernel's 9216-byte ones).  So the choice is per call site (`prefer_two`);
 // SO3D_ROW_LANES=1 / 2 forces one kernel for every op (cross-kernel parity test, A/B runs).
+#ifndef SO3D_SE3PS_ROWS_TWO
+#define SO3D_SE3PS_ROWS_TWO 1  // SE(3) per-row-t reverse step through TwoRow<Op>: 0.731 -> 0.640 ms (r05d); the per-row sampler: 0.232 -> 0.357, stays one-row
+#endif
 #ifndef SO3D_TWOROW_MINCTAS
 #define SO3D_TWOROW_MINCTAS 6
 #endif
@@ -2739,6 +2742,7 @@ static int launch_se3_p_step(const float* rot_t, const float* shift_t, const flo
   op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.sigma = sigma; op.T = T;
   op.post_cdf = post_cdf; op.post_guide = post_guide; op.loc = loc; op.shift_scale = shift_scale;
   op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
+  if constexpr (!kSharedT) return launch_rowwise_pick(op, n, stream, "so3d_se3_p_sample_f32", SO3D_SE3PS_ROWS_TWO != 0);  // per-row t (r05d)
   return launch_rowwise(op, n, stream, "so3d_se3_p_sample_f32");
 }
 

@@ -571,6 +571,10 @@ def test_two_row_engine_equals_one_row_for_the_maps(dx, cuda_device, monkeypatch
             "sample_rows": lambda: ops.igso3_sample(fwd, (n,), row_idx=tt, seed=3, rng_offset=1, guide=fg, want_angle=True),
             "q_sample_given": lambda: ops.q_sample_given(R, tt, p.sqrt_alphas_cumprod, R2),
             "bingham": lambda: ops.bingham_sample(torch.eye(4, device=cuda_device), (n,), seed=2, rng_offset=0, want_rmat=True),
+            "se3_p_sample_rows": lambda: ops.se3_p_sample_fused(R, v, v * 0.3, v * 0.1, tt, p.sqrt_recip_alphas_cumprod, p.sqrt_recipm1_alphas_cumprod,
+                                                                p.posterior_mean_coef1, p.posterior_mean_coef2,
+                                                                (0.5 * p.posterior_log_variance_clipped).exp().contiguous(), 75.0,
+                                                                post_cdf=p.tables()[1], seed=6, rng_offset=2, post_guide=p.guides()[1]) if n > 1 else R,
         }
         for name, fn in cases.items():
             res = {}
