@@ -1110,6 +1110,50 @@ int launch_rowwise_pick(const Op& op, int64_t n, void* stream, const char* name,
   return launch_rowwise_w2(op2, n, stream, name);
 }
 
+#ifndef SO3D_TWOROWPRE_MINCTAS
+#define SO3D_TWOROWPRE_MINCTAS 4
+#endif
+// The same adaptor for one-row ops that DO define prefetch hooks (per-row table rows): the hooks run once per row, row() gets
+// the row's Pre2.
+template <class Op>
+struct TwoRowPre : Op {
+  static constexpr int kOutStages = 1;
+  static constexpr int kInStages = 1;
+  static constexpr int kMinCtas = SO3D_TWOROWPRE_MINCTAS;  // two rows' prefetch state live across the tile: 4 CTAs of 128 threads = 128 registers
+  int64_t n_rows;
+  __device__ void row2(int64_t i0, const typename Op::Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*a3)[2], Mat3 (*o9)[2], Vec3 (*o3)[2],
+                       const float* tab) const {
+    constexpr int kI9 = Op::kIn9, kI3 = Op::kIn3, kO9 = Op::kOut9, kO3 = Op::kOut3;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int64_t i = i0 + 32 * j;
+      if (i < n_rows) {
+        Mat3 A9[kI9 > 0 ? kI9 : 1], O9[kO9 > 0 ? kO9 : 1];
+        Vec3 A3[kI3 > 0 ? kI3 : 1], O3[kO3 > 0 ? kO3 : 1];
+#pragma unroll
+        for (int a = 0; a < kI9; ++a) A9[a] = a9[a][j];
+#pragma unroll
+        for (int a = 0; a < kI3; ++a) A3[a] = a3[a][j];
+        Op::row(i, p[j], A9, A3, O9, O3, tab);
+#pragma unroll
+        for (int a = 0; a < kO9; ++a) o9[a][j] = O9[a];
+#pragma unroll
+        for (int a = 0; a < kO3; ++a) o3[a][j] = O3[a];
+      }
+    }
+  }
+};
+template <class Op>
+int launch_rowwise_pick_pre(const Op& op, int64_t n, void* stream, const char* name, bool prefer_two) {
+  const char* lanes_env = getenv("SO3D_ROW_LANES");
+  const int forced = lanes_env ? atoi(lanes_env) : 0;
+  if (forced == 1 || (forced != 2 && !prefer_two)) return launch_rowwise(op, n, stream, name);
+  TwoRowPre<Op> op2;
+  static_cast<Op&>(op2) = op;
+  op2.n_rows = n;
+  return launch_rowwise_w2(op2, n, stream, name);
+}
+
 // dummy arrays for ops without a given kind of operand (zero-length arrays are not allowed)
 #define SO3D_OP_ARRAYS(I9, I3, O9, O3) SO3D_OP_ARRAYS_S(I9, I3, O9, O3, 2)
 // S = output stages: 2 (double-buffered) or 1 (less shared memory -> more resident CTAs, for latency-bound ops)
@@ -2156,8 +2200,25 @@ struct SE3QSample2Op : SE3QSampleOp {
 // reverse step: diffusion.py:446-485
 //   rot as PStepOp;  shift0_hat = recip_t shift_t - recipm1_t pred_shift;  mean = c1 shift0_hat + c2 shift_t;
 //   out = t == 0 ? mean : mean + sigma_t shift_scale z
+#ifndef SO3D_SE3PS_PREFETCH
+#define SO3D_SE3PS_PREFETCH 1  // per-row t: step index two tiles ahead, schedule scalars + draw + guide record one tile ahead
+#endif
+template <bool kOn>
+struct SE3PStepPre {};
+template <>
+struct SE3PStepPre<true> {
+  struct Pre1 {
+    int64_t t;
+  };
+  struct Pre2 {
+    int ti;
+    float k_recip, k_recipm1, k_c1, k_c2, k_sigma;
+    NoiseDraw d;
+    uint4 rec;
+  };
+};
 template <bool kSharedT>
-struct SE3PStepOp {
+struct SE3PStepOp : SE3PStepPre<SO3D_SE3PS_PREFETCH && !kSharedT> {
   SO3D_OP_ARRAYS_S(1, 3, 1, 1, 1)  // in: rot_t | pred_rot, shift_t, pred_shift;  out: rot | shift
   static constexpr int kTab = kSharedT ? kTabCdfFloats : kGrid;
   // per-row t: cap SO3D_PS_MINCTAS (measured there).  Shared t: issue-bound, shared memory
@@ -2213,6 +2274,44 @@ struct SE3PStepOp {
       qm = qmul(qm, quat_axis_angle(d.axis, ang));
       const Normal4 z = normal4_from_u4(philox4x32_10(key_shift, row_offset + (uint64_t)i));
       const float ns = k_sigma * shift_scale;
+      m = Vec3{fmaf(ns, z.a, m.x), fmaf(ns, z.b, m.y), fmaf(ns, z.c, m.z)};
+    }
+    o9[0] = quat_to_mat_unit(qm);
+    o3[0] = m;
+  }
+  // prefetch hooks of the per-row-t instantiation (same functions of the same inputs as row(): same bits)
+  template <class P1 = typename SE3PStepPre<true>::Pre1>
+  __device__ P1 prefetch1(int64_t i) const { return P1{t[i]}; }
+  template <class P1, class P2 = typename SE3PStepPre<true>::Pre2>
+  __device__ P2 prefetch2(int64_t i, const P1& p1) const {
+    P2 p;
+    const int64_t ti = clamp_t(p1.t);
+    p.ti = (int)ti;
+    p.k_recip = __ldg(recip + ti), p.k_recipm1 = __ldg(recipm1 + ti), p.k_c1 = __ldg(coef1 + ti), p.k_c2 = __ldg(coef2 + ti), p.k_sigma = __ldg(sigma + ti);
+    p.d = draw_axis_u(key, row_offset + (uint64_t)i);
+    p.rec = (post_cdf && post_guide) ? __ldg(reinterpret_cast<const uint4*>(post_guide) + ti * kGuideRecs + guide_bucket(p.d.u)) : make_uint4(0, 0, 0, 0);
+    return p;
+  }
+  template <class P2>
+  __device__ void row(int64_t i, const P2& p, const Mat3* a9, const Vec3* a3, Mat3* o9, Vec3* o3, const float* tab) const {
+    Quat qh;
+    Quat qm = p_mean_quat(a9[0], a3[0], p.k_recip, p.k_recipm1, p.k_c1, p.k_c2, &qh);
+    const Vec3 st = a3[1], ps = a3[2];
+    Vec3 m;
+    m.x = fmaf(p.k_c1, fmaf(p.k_recip, st.x, -p.k_recipm1 * ps.x), p.k_c2 * st.x);
+    m.y = fmaf(p.k_c1, fmaf(p.k_recip, st.y, -p.k_recipm1 * ps.y), p.k_c2 * st.y);
+    m.z = fmaf(p.k_c1, fmaf(p.k_recip, st.z, -p.k_recipm1 * ps.z), p.k_c2 * st.z);
+    if (post_cdf && p.ti != 0) {
+      float ang;
+      if (post_guide) {
+        const GuideRec rec{p.rec.x, __uint_as_float(p.rec.y), __uint_as_float(p.rec.z), __uint_as_float(p.rec.w)};
+        ang = igso3_angle_from_record(post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, rec, p.d.u);
+      } else {
+        ang = igso3_angle_from_uniform(post_cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
+      }
+      qm = qmul(qm, quat_axis_angle(p.d.axis, ang));
+      const Normal4 z = normal4_from_u4(philox4x32_10(key_shift, row_offset + (uint64_t)i));
+      const float ns = p.k_sigma * shift_scale;
       m = Vec3{fmaf(ns, z.a, m.x), fmaf(ns, z.b, m.y), fmaf(ns, z.c, m.z)};
     }
     o9[0] = quat_to_mat_unit(qm);
@@ -2549,6 +2648,7 @@ static int launch_sample(const float* cdf, const uint32_t* guide, const float* l
   op.out9[0] = R; op.out3[0] = axis3;
   op.cdf = cdf; op.guide = guide; op.loc = loc; op.row_idx = row_idx; op.shared_row = row; op.rows = rows; op.u_in = u; op.axes_in = axes3;
   op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset; op.mean = mean; op.mean_stride = mean_stride; op.angle_out = angle;
+  // (prefetch hooks for the per-row table rows measured no gain here, 0.2329 ms either way, r05g: the kernel is bound by its 48 B/row of writes)
   return launch_rowwise_pick(op, n, stream, "so3d_igso3_sample_f32");
 }
 
@@ -2742,7 +2842,10 @@ static int launch_se3_p_step(const float* rot_t, const float* shift_t, const flo
   op.t = t; op.recip = recip; op.recipm1 = recipm1; op.coef1 = coef1; op.coef2 = coef2; op.sigma = sigma; op.T = T;
   op.post_cdf = post_cdf; op.post_guide = post_guide; op.loc = loc; op.shift_scale = shift_scale;
   op.key = make_philox_key(seed, rng_offset); op.key_shift = make_philox_key(seed, rng_offset | kShiftStream); op.row_offset = row_offset;
-  if constexpr (!kSharedT) return launch_rowwise_pick(op, n, stream, "so3d_se3_p_sample_f32", SO3D_SE3PS_ROWS_TWO != 0);  // per-row t (r05d)
+  if constexpr (!kSharedT) {  // per-row t (r05d, r05f)
+    if constexpr (SO3D_SE3PS_PREFETCH) return launch_rowwise_pick_pre(op, n, stream, "so3d_se3_p_sample_f32", SO3D_SE3PS_ROWS_TWO != 0);
+    else return launch_rowwise_pick(op, n, stream, "so3d_se3_p_sample_f32", SO3D_SE3PS_ROWS_TWO != 0);
+  }
   return launch_rowwise(op, n, stream, "so3d_se3_p_sample_f32");
 }
 
