@@ -672,6 +672,37 @@ def test_two_row_noising_equals_one_row(dx, cuda_device, monkeypatch):
     assert torch.equal(res["1"]["x_t"], res["2"]["x_t"]) and torch.equal(res["1"]["target"], res["2"]["target"])
 
 
+def test_two_row_kernels_equal_one_row_at_bench_size(dx, cuda_device, monkeypatch):
+    """BASELINE-size check of the cross-kernel identities: 2^24 + 7 rows (ragged last tile, every CTA of the persistent grids
+    many tiles deep) through forward noising with the score, the per-row-t reverse step and the closed-form score, one-row
+    vs two-row kernels, compared bit for bit."""
+    n = (1 << 24) + 7
+    p = dx.SO3Diffusion(None).to(cuda_device)
+    fwd, post, _ = p.tables()
+    fg, pg = p.guides()
+    ops = dx.ops
+    g = torch.Generator(device=cuda_device); g.manual_seed(82)
+    x = ops.quat_to_rmat(torch.randn(n, 4, device=cuda_device, generator=g))
+    t = torch.randint(0, 1000, (n,), device=cuda_device, generator=g)
+    pred = torch.randn(n, 3, device=cuda_device, generator=g) * 0.3
+    eps = torch.exp(torch.empty(n, device=cuda_device).uniform_(-5.0, 0.2, generator=g))
+    sched = (p.sqrt_recip_alphas_cumprod, p.sqrt_recipm1_alphas_cumprod, p.posterior_mean_coef1, p.posterior_mean_coef2)
+
+    def run(lanes):
+        for k in ("SO3D_QS_LANES", "SO3D_PS_LANES", "SO3D_LOGP_LANES"):
+            monkeypatch.setenv(k, lanes)
+        q = ops.q_sample_fused(x, t, p.sqrt_alphas_cumprod, p.sqrt_one_minus_alphas_cumprod, fwd, seed=11, rng_offset=5, guide=fg, want_score=True)
+        r = ops.p_sample_fused(x, pred, t, *sched, post_cdf=post, seed=11, rng_offset=6, post_guide=pg)
+        l, s_, _ = ops.igso3_logp_score(x, eps, mode="auto")
+        return [q["x_t"], q["target"], q["score"], r, l, s_]
+
+    a = run("1")
+    b = run("2")
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    del a, b
+
+
 def test_two_row_reverse_step_rows_equals_one_row(dx, cuda_device, monkeypatch):
     """The per-row-t reverse step runs two rows per thread by default; the one-row kernel (SO3D_PS_LANES=1) gives the same
     bits: ragged sizes, rows at t = 0 next to noisy rows, without the guide, without noise, unaligned arrays, a shard offset."""
