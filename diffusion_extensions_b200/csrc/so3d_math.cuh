@@ -1108,6 +1108,7 @@ inline void igso3_closed_f32_outofline(float w, float eps, float* logf_out, floa
 // HBM-bound kernels that evaluate `auto` do not carry the unrolled series block inline.  Measured (profiles/r04u_probe.jsonl):
 // 20 % fewer instructions in those kernels and SLOWER -- auto score 0.1675 -> 0.175 ms, forward noising with the score
 // 0.3637 -> 0.378 ms (the call's register conventions cost more on the hot path than the inline block's size) -- so it is off.
+// (Again with the closed form evaluated first and the call only on the rare override, r05i: 0.1655 -> 0.1735 ms, 0.3595 -> 0.376.)
 #ifndef SO3D_AUTO_SERIES_OUTOFLINE
 #define SO3D_AUTO_SERIES_OUTOFLINE 0
 #endif
@@ -1128,7 +1129,10 @@ SO3D_HD void igso3_logf_g_t(float w, float eps, int L, float* logf_out, float* g
     // the closed form unconditionally and straight-line (so that ptxas can interleave it with the neighbouring row's / the
     // surrounding arithmetic), then the rare rows above eps = 1 are re-evaluated by the series: the same bits as branching first
     igso3_closed_f32(w, eps, logf_out, g_out);
-    if (!(eps <= kAutoSeriesEps)) igso3_series_branch<kAuto>(w, eps, L, logf_out, g_out);
+    if (!(eps <= kAutoSeriesEps)) {
+      if (SO3D_AUTO_SERIES_OUTOFLINE) igso3_auto_series_outofline(w, eps, L, logf_out, g_out);
+      else igso3_series_branch<kAuto>(w, eps, L, logf_out, g_out);
+    }
   } else if (kMode == kClosed || (kMode == kAuto && eps <= kAutoSeriesEps)) {
     igso3_closed_f32(w, eps, logf_out, g_out);
   } else if (kMode == kAuto && SO3D_AUTO_SERIES_OUTOFLINE) {
