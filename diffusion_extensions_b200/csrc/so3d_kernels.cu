@@ -1383,6 +1383,9 @@ struct LogpScoreOp : LogpPre<SO3D_LOGP_PREFETCH && (kMode == kClosed || kMode ==
 #ifndef SO3D_LOGP2_MINCTAS
 #define SO3D_LOGP2_MINCTAS 8
 #endif
+#ifndef SO3D_LOGP2_AUTO_VOTE
+#define SO3D_LOGP2_AUTO_VOTE 1
+#endif
 #ifndef SO3D_LOGP2_OUTSTAGES
 #define SO3D_LOGP2_OUTSTAGES 1
 #endif
@@ -1396,11 +1399,26 @@ struct LogpScore2Op : LogpScoreOp<kMode> {
   int64_t n;  // rows beyond the end of a ragged tile must not touch logp / dlogf
   __device__ void row2(int64_t i0, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*)[2], Mat3 (*)[2], Vec3 (*o3)[2], const float*) const {
     const AxisAngleL<L2> a = axis_angle_fast_l(lanes_of(a9[0][0], a9[0][1]));
+    float lf2[2], g2[2];
+    if (kMode == kAuto && SO3D_LOGP2_AUTO_VOTE) {
+      // auto: the closed form for both rows, straight-line; the rows above eps = 1 (none in a DDPM schedule) are re-evaluated by
+      // the series behind ONE warp vote instead of a divergent region per row (r05j: the per-row branch scaffolding was 10 % of
+      // this kernel's issue slots).  Same bits as igso3_logf_g_t<kAuto>.
+      igso3_closed_f32(a.theta.x, p[0].eps, &lf2[0], &g2[0]);
+      igso3_closed_f32(a.theta.y, p[1].eps, &lf2[1], &g2[1]);
+      const bool s0 = !(p[0].eps <= kAutoSeriesEps), s1 = !(p[1].eps <= kAutoSeriesEps);
+      if (__any_sync(__activemask(), s0 || s1)) {
+        if (s0) igso3_series_branch<kAuto>(a.theta.x, p[0].eps, this->L, &lf2[0], &g2[0]);
+        if (s1) igso3_series_branch<kAuto>(a.theta.y, p[1].eps, this->L, &lf2[1], &g2[1]);
+      }
+    } else {
+      igso3_logf_g_t<kMode>(a.theta.x, p[0].eps, this->L, &lf2[0], &g2[0]);
+      igso3_logf_g_t<kMode>(a.theta.y, p[1].eps, this->L, &lf2[1], &g2[1]);
+    }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int64_t i = i0 + 32 * j;
-      float lf, g;
-      igso3_logf_g_t<kMode>(j ? a.theta.y : a.theta.x, p[j].eps, this->L, &lf, &g);
+      const float lf = lf2[j], g = g2[j];
       if (i < n) {
         this->logp[i] = lf;
         if (this->dlogf) this->dlogf[i] = g;
