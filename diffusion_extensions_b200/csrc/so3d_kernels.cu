@@ -1749,6 +1749,9 @@ struct QSampleOp {
 #ifndef SO3D_QSX2_MINCTAS
 #define SO3D_QSX2_MINCTAS 4
 #endif
+#ifndef SO3D_QSX2_AUTO_VOTE
+#define SO3D_QSX2_AUTO_VOTE 1
+#endif
 #ifndef SO3D_QS2_INSTAGES
 #define SO3D_QS2_INSTAGES 1  // 1: every warp loads its own slice (rowwise_kernel_w2, kWarpIn): 0.3215 -> 0.3042 ms, with the score 0.386 -> 0.365 (r04j)
 #endif
@@ -1790,12 +1793,23 @@ struct QSample2Op : QSampleOp<kExtra, kDevSeed, kNoiseOut> {
     o3[0][0] = Vec3{tx.x, ty.x, tz.x};
     o3[0][1] = Vec3{tx.y, ty.y, tz.y};
     if (kExtra && this->out3[kExtra ? 1 : 0]) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float lf, g;
-        igso3_logf_g_t<kAuto>(j ? ang.y : ang.x, p[j].eps, 2000, &lf, &g);
-        o3[kExtra ? 1 : 0][j] = Vec3{g * p[j].d.axis.x, g * p[j].d.axis.y, g * p[j].d.axis.z};
+      // auto evaluator as in LogpScore2Op: closed form for both rows, ONE warp vote for the series override (eps > 1 does not
+      // occur in a DDPM schedule: eps_t = sqrt(1 - abar_t)); same bits as igso3_logf_g_t<kAuto> per row
+      float lf[2], g[2];
+#if SO3D_QSX2_AUTO_VOTE
+      igso3_closed_f32(ang.x, p[0].eps, &lf[0], &g[0]);
+      igso3_closed_f32(ang.y, p[1].eps, &lf[1], &g[1]);
+      const bool s0 = !(p[0].eps <= kAutoSeriesEps), s1 = !(p[1].eps <= kAutoSeriesEps);
+      if (__any_sync(__activemask(), s0 || s1)) {
+        if (s0) igso3_series_branch<kAuto>(ang.x, p[0].eps, 2000, &lf[0], &g[0]);
+        if (s1) igso3_series_branch<kAuto>(ang.y, p[1].eps, 2000, &lf[1], &g[1]);
       }
+#else
+      igso3_logf_g_t<kAuto>(ang.x, p[0].eps, 2000, &lf[0], &g[0]);
+      igso3_logf_g_t<kAuto>(ang.y, p[1].eps, 2000, &lf[1], &g[1]);
+#endif
+#pragma unroll
+      for (int j = 0; j < 2; ++j) o3[kExtra ? 1 : 0][j] = Vec3{g[j] * p[j].d.axis.x, g[j] * p[j].d.axis.y, g[j] * p[j].d.axis.z};
     }
   }
 };
