@@ -1749,6 +1749,9 @@ struct QSampleOp {
 #ifndef SO3D_QSX2_MINCTAS
 #define SO3D_QSX2_MINCTAS 4
 #endif
+#ifndef SO3D_QS2_ANGLE_VOTE
+#define SO3D_QS2_ANGLE_VOTE 1
+#endif
 #ifndef SO3D_QSX2_AUTO_VOTE
 #define SO3D_QSX2_AUTO_VOTE 1
 #endif
@@ -1769,8 +1772,26 @@ struct QSample2Op : QSampleOp<kExtra, kDevSeed, kNoiseOut> {
     }
     return igso3_angle_from_uniform(this->cdf + (int64_t)p.ti * kCdf, tab + kTabLoc, p.d.u);
   }
+  // both rows' lookups: the one-record resolution straight-line, the rare search (0.2 % of the rows) behind ONE warp vote
+  __device__ L2 angles_of(const Pre2 (&p)[2], const float* tab) const {
+    // (per variant, r05m: with the score 0.3588 -> 0.3555 ms; plain noising picks a 127-register schedule, 0.304 -> 0.317 ms)
+#if SO3D_QS2_ANGLE_VOTE
+    if (kExtra && this->guide) {
+      const GuideRec r0{p[0].rec.x, __uint_as_float(p[0].rec.y), __uint_as_float(p[0].rec.z), __uint_as_float(p[0].rec.w)};
+      const GuideRec r1{p[1].rec.x, __uint_as_float(p[1].rec.y), __uint_as_float(p[1].rec.z), __uint_as_float(p[1].rec.w)};
+      bool f0, f1;
+      L2 ang{igso3_angle_record_fast(tab + kTabLoc, r0, p[0].d.u, &f0), igso3_angle_record_fast(tab + kTabLoc, r1, p[1].d.u, &f1)};
+      if (__any_sync(__activemask(), !f0 || !f1)) {
+        if (!f0) ang.x = angle_of(p[0], tab);
+        if (!f1) ang.y = angle_of(p[1], tab);
+      }
+      return ang;
+    }
+#endif
+    return L2{angle_of(p[0], tab), angle_of(p[1], tab)};
+  }
   __device__ void row2(int64_t, const Pre2 (&p)[2], const Mat3 (*a9)[2], const Vec3 (*)[2], Mat3 (*o9)[2], Vec3 (*o3)[2], const float* tab) const {
-    const L2 ang{angle_of(p[0], tab), angle_of(p[1], tab)};
+    const L2 ang = angles_of(p, tab);
     const Vec3L<L2> axis{L2{p[0].d.axis.x, p[1].d.axis.x}, L2{p[0].d.axis.y, p[1].d.axis.y}, L2{p[0].d.axis.z, p[1].d.axis.z}};
     QuatL<L2> qn;
     const QuatL<L2> q = q_sample_quat_l<L2>(lanes_of(a9[0][0], a9[0][1]), L2{p[0].sc, p[1].sc}, axis, ang, &qn);  // diffusion.py:344-346

@@ -1388,6 +1388,24 @@ SO3D_HD float igso3_angle_from_record(const float* trap, const float* loc, const
   return igso3_angle_lerp(trap, loc, u, cdf_count_le(trap, u, in01 ? lo : 0, in01 ? hi : kCdf));
 }
 
+// The one-record resolution alone, straight-line: *fast tells whether it applies (otherwise the caller runs
+// igso3_angle_from_record, which searches).  For kernels that resolve two rows per thread and guard the rare search with one
+// warp vote instead of a divergent region per row.  Same operations as the fast branch of igso3_angle_from_record.
+SO3D_HD float igso3_angle_record_fast(const float* loc, const GuideRec& rec, float u, bool* fast) {
+  const int lo = (int)(rec.lohi & 0xffffu), hi = (int)(rec.lohi >> 16);
+  *fast = hi - lo <= 1 && lo < kCdf - 1 && u >= 0.f && u < 1.0f;
+  const bool up = (hi > lo) && (rec.t0 <= u);
+  int i1 = lo + (up ? 1 : 0);
+  i1 = i1 < kCdf - 1 ? i1 : kCdf - 1;  // (only matters when !*fast)
+  const int i0 = i1 > 0 ? i1 - 1 : 0;
+  const float t0 = up ? rec.t0 : rec.tm1, t1 = up ? rec.tp1 : rec.t0;
+  const float diff = fmaxf(t1 - t0, 1e-6f);
+  const float wgt = fminf(fmaxf((u - t0) / diff, 0.f), 1.f);
+  const float a0 = loc[i0], a1 = loc[i1];
+  const float d = a1 - a0;
+  return (wgt < 0.5f) ? fmaf(wgt, d, a0) : fmaf(-d, 1.0f - wgt, a1);
+}
+
 // record index of u (any float: values outside [0, 1) map to some valid record and take the search path)
 SO3D_HD int guide_bucket(float u) {
   const bool upper = u > 0.875f;
